@@ -1,0 +1,644 @@
+/*
+ * sirius_oracle.c -- CPU restatement of the Sirius prover hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle and the CPU timing baseline.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ * Nothing under sirius_b200/ links, imports or executes it; the product path is CUDA-only.
+ *
+ * PARITY PINNING.  The reference (Rust, /root/reference) cannot be compiled in this image (no
+ * cargo/rustc), so this restatement is pinned by
+ *   - the reference's own known-answer vectors: src/fft.rs:242-251 (fft of [0..8)) and
+ *     src/polynomial/lagrange.rs:118-126 (checked in tests/test_oracle.py), and
+ *   - the group law: `CommitmentKey::commit` (src/commitment.rs:81-90) has NO known-answer vector in
+ *     the reference ("parity unpinned by KAT"); its result sum_i v_i*ck_i -> affine is mathematically
+ *     unique, and tests/ cross-check this file against an independent big-int affine implementation
+ *     (oracle/pyref.py).
+ *
+ * The MSM arithmetic lives in a third-party crate that is not vendored: halo2_proofs
+ * (github.com/snarkify/halo2, branch snarkify/dev.scroll.alpha.2, commit unpinned -- Cargo.toml:44-46).
+ * so_msm() restates that crate's published algorithm (arithmetic.rs: best_multiexp / multiexp_serial):
+ * split the input into one contiguous chunk per thread, per chunk a serial windowed bucket method with
+ * c = ceil(ln n) (3 for n<32, 1 for n<4), 256/c+1 segments processed high to low with c doublings in
+ * between, buckets None/Affine/Projective, summation by parts; chunk results added in order.
+ *
+ * Data layout: field element = 4 x u64 little-endian limbs in Montgomery form (R=2^256);
+ * affine point = (x,y), 64 bytes, identity = (0,0).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+
+typedef struct { u64 l[4]; } fe;
+
+typedef struct {
+    u64 p[4];
+    u64 inv;      /* -p^-1 mod 2^64 */
+    u64 r[4];     /* R mod p   (Montgomery one) */
+    u64 r2[4];    /* R^2 mod p */
+} field_t;
+
+static const field_t FIELDS[2] = {
+    /* 0: Fr (bn256 scalar field, grumpkin base field) */
+    {{0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
+     0xc2e1f593efffffffULL,
+     {0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL},
+     {0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL}},
+    /* 1: Fq (bn256 base field, grumpkin scalar field) */
+    {{0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
+     0x87d20782e4866389ULL,
+     {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL},
+     {0xf32cfc5b538afa89ULL, 0xb5e71911d44501fbULL, 0x47ab1eff0a417ff6ULL, 0x06d89f71cab8351fULL}},
+};
+
+/* ------------------------------------------------------------------ field arithmetic */
+
+static inline int fe_is_zero(const fe *a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3]) == 0; }
+static inline int fe_eq(const fe *a, const fe *b) {
+    return a->l[0] == b->l[0] && a->l[1] == b->l[1] && a->l[2] == b->l[2] && a->l[3] == b->l[3];
+}
+static inline int geq_p(const u64 a[4], const u64 p[4]) {
+    for (int i = 3; i >= 0; i--) {
+        if (a[i] > p[i]) return 1;
+        if (a[i] < p[i]) return 0;
+    }
+    return 1;
+}
+static inline void sub_p(u64 a[4], const u64 p[4]) {
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)a[i] - p[i] - (u64)br;
+        a[i] = (u64)d;
+        br = (d >> 64) & 1;
+    }
+}
+static inline void fe_add(fe *o, const fe *a, const fe *b, const field_t *F) {
+    u128 c = 0;
+    u64 t[4];
+    for (int i = 0; i < 4; i++) {
+        c += (u128)a->l[i] + b->l[i];
+        t[i] = (u64)c;
+        c >>= 64;
+    }
+    /* p < 2^254 so a+b < 2^255: no carry out */
+    if (geq_p(t, F->p)) sub_p(t, F->p);
+    memcpy(o->l, t, 32);
+}
+static inline void fe_sub(fe *o, const fe *a, const fe *b, const field_t *F) {
+    u64 t[4];
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 d = (u128)a->l[i] - b->l[i] - (u64)br;
+        t[i] = (u64)d;
+        br = (d >> 64) & 1;
+    }
+    if (br) {
+        u128 c = 0;
+        for (int i = 0; i < 4; i++) {
+            c += (u128)t[i] + F->p[i];
+            t[i] = (u64)c;
+            c >>= 64;
+        }
+    }
+    memcpy(o->l, t, 32);
+}
+static inline void fe_neg(fe *o, const fe *a, const field_t *F) {
+    fe z = {{0, 0, 0, 0}};
+    fe_sub(o, &z, a, F);
+}
+static inline void fe_dbl(fe *o, const fe *a, const field_t *F) { fe_add(o, a, a, F); }
+
+/* Montgomery product a*b/R mod p (CIOS, 64-bit limbs). */
+static inline void fe_mul(fe *o, const fe *a, const fe *b, const field_t *F) {
+    u64 t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)a->l[j] * b->l[i] + t[j];
+            t[j] = (u64)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (u64)c;
+        t[5] = (u64)(c >> 64);
+        u64 m = t[0] * F->inv;
+        c = (u128)m * F->p[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)m * F->p[j] + t[j];
+            t[j - 1] = (u64)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (u64)c;
+        t[4] = t[5] + (u64)(c >> 64);
+    }
+    if (t[4] || geq_p(t, F->p)) sub_p(t, F->p);
+    memcpy(o->l, t, 32);
+}
+static inline void fe_sqr(fe *o, const fe *a, const field_t *F) { fe_mul(o, a, a, F); }
+static inline void fe_one(fe *o, const field_t *F) { memcpy(o->l, F->r, 32); }
+static inline void fe_zero(fe *o) { memset(o->l, 0, 32); }
+static inline void fe_from_mont(fe *o, const fe *a, const field_t *F) {
+    fe one = {{1, 0, 0, 0}};
+    fe_mul(o, a, &one, F);
+}
+static inline void fe_to_mont(fe *o, const fe *a, const field_t *F) {
+    fe r2;
+    memcpy(r2.l, F->r2, 32);
+    fe_mul(o, a, &r2, F);
+}
+/* a^e, e given as 4 little-endian u64 (plain integer exponent) */
+static void fe_pow(fe *o, const fe *a, const u64 e[4], const field_t *F) {
+    fe acc, base = *a;
+    fe_one(&acc, F);
+    for (int i = 0; i < 256; i++) {
+        if ((e[i / 64] >> (i % 64)) & 1) fe_mul(&acc, &acc, &base, F);
+        fe_sqr(&base, &base, F);
+    }
+    *o = acc;
+}
+static void fe_inv(fe *o, const fe *a, const field_t *F) {
+    u64 e[4];
+    memcpy(e, F->p, 32);
+    e[0] -= 2; /* p is odd and > 2, no borrow */
+    fe_pow(o, a, e, F);
+}
+
+/* ------------------------------------------------------------------ curves (a = 0), Jacobian */
+
+typedef struct { fe x, y; } aff;      /* identity = (0,0) */
+typedef struct { fe x, y, z; } jac;   /* identity: z = 0 */
+
+static inline const field_t *curve_base(int curve) { return &FIELDS[curve == 0 ? 1 : 0]; }
+static inline const field_t *curve_scalar(int curve) { return &FIELDS[curve == 0 ? 0 : 1]; }
+
+static inline int aff_is_id(const aff *p) { return fe_is_zero(&p->x) && fe_is_zero(&p->y); }
+static inline void jac_set_id(jac *p) { memset(p, 0, sizeof(*p)); }
+static inline int jac_is_id(const jac *p) { return fe_is_zero(&p->z); }
+
+static void jac_double(jac *o, const jac *p, const field_t *F) {
+    if (jac_is_id(p)) { jac_set_id(o); return; }
+    /* dbl-2009-l, a = 0 */
+    fe A, B, C, D, E, Fv, t, x3, y3, z3;
+    fe_sqr(&A, &p->x, F);
+    fe_sqr(&B, &p->y, F);
+    fe_sqr(&C, &B, F);
+    fe_add(&t, &p->x, &B, F);
+    fe_sqr(&t, &t, F);
+    fe_sub(&t, &t, &A, F);
+    fe_sub(&t, &t, &C, F);
+    fe_dbl(&D, &t, F);
+    fe_dbl(&E, &A, F);
+    fe_add(&E, &E, &A, F);
+    fe_sqr(&Fv, &E, F);
+    fe_dbl(&t, &D, F);
+    fe_sub(&x3, &Fv, &t, F);
+    fe_mul(&z3, &p->y, &p->z, F);
+    fe_dbl(&z3, &z3, F);
+    fe_sub(&t, &D, &x3, F);
+    fe_mul(&y3, &E, &t, F);
+    fe_dbl(&t, &C, F);
+    fe_dbl(&t, &t, F);
+    fe_dbl(&t, &t, F);
+    fe_sub(&y3, &y3, &t, F);
+    o->x = x3; o->y = y3; o->z = z3;
+}
+
+static void jac_add(jac *o, const jac *p, const jac *q, const field_t *F) {
+    if (jac_is_id(p)) { *o = *q; return; }
+    if (jac_is_id(q)) { *o = *p; return; }
+    fe z1z1, z2z2, u1, u2, s1, s2, h, r, t;
+    fe_sqr(&z1z1, &p->z, F);
+    fe_sqr(&z2z2, &q->z, F);
+    fe_mul(&u1, &p->x, &z2z2, F);
+    fe_mul(&u2, &q->x, &z1z1, F);
+    fe_mul(&s1, &p->y, &q->z, F);
+    fe_mul(&s1, &s1, &z2z2, F);
+    fe_mul(&s2, &q->y, &p->z, F);
+    fe_mul(&s2, &s2, &z1z1, F);
+    if (fe_eq(&u1, &u2)) {
+        if (fe_eq(&s1, &s2)) { jac_double(o, p, F); return; }
+        jac_set_id(o);
+        return;
+    }
+    fe hh, hhh, v, x3, y3, z3;
+    fe_sub(&h, &u2, &u1, F);
+    fe_sub(&r, &s2, &s1, F);
+    fe_sqr(&hh, &h, F);
+    fe_mul(&hhh, &hh, &h, F);
+    fe_mul(&v, &u1, &hh, F);
+    fe_sqr(&x3, &r, F);
+    fe_sub(&x3, &x3, &hhh, F);
+    fe_dbl(&t, &v, F);
+    fe_sub(&x3, &x3, &t, F);
+    fe_sub(&t, &v, &x3, F);
+    fe_mul(&y3, &r, &t, F);
+    fe_mul(&t, &s1, &hhh, F);
+    fe_sub(&y3, &y3, &t, F);
+    fe_mul(&z3, &p->z, &q->z, F);
+    fe_mul(&z3, &z3, &h, F);
+    o->x = x3; o->y = y3; o->z = z3;
+}
+
+static void jac_add_aff(jac *o, const jac *p, const aff *q, const field_t *F) {
+    if (aff_is_id(q)) { *o = *p; return; }
+    if (jac_is_id(p)) {
+        o->x = q->x; o->y = q->y; fe_one(&o->z, F);
+        return;
+    }
+    jac qq;
+    qq.x = q->x; qq.y = q->y; fe_one(&qq.z, F);
+    jac_add(o, p, &qq, F);
+}
+
+static void jac_to_affine(aff *o, const jac *p, const field_t *F) {
+    if (jac_is_id(p)) { memset(o, 0, sizeof(*o)); return; }
+    fe zi, zi2, zi3;
+    fe_inv(&zi, &p->z, F);
+    fe_sqr(&zi2, &zi, F);
+    fe_mul(&zi3, &zi2, &zi, F);
+    fe_mul(&o->x, &p->x, &zi2, F);
+    fe_mul(&o->y, &p->y, &zi3, F);
+}
+
+/* ------------------------------------------------------------------ MSM: halo2 best_multiexp restated */
+
+typedef struct { int kind; aff a; jac j; } bucket_t; /* 0 None, 1 Affine, 2 Projective */
+
+static size_t get_at(size_t segment, size_t c, const unsigned char repr[32]) {
+    size_t skip_bits = segment * c;
+    size_t skip_bytes = skip_bits / 8;
+    if (skip_bytes >= 32) return 0;
+    unsigned char v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i < 8 && skip_bytes + i < 32; i++) v[i] = repr[skip_bytes + i];
+    u64 tmp;
+    memcpy(&tmp, v, 8); /* little-endian host */
+    tmp >>= skip_bits - skip_bytes * 8;
+    tmp %= ((u64)1 << c);
+    return (size_t)tmp;
+}
+
+static void multiexp_serial(const fe *coeffs_mont, const aff *bases, size_t n, jac *acc, int curve) {
+    const field_t *Fb = curve_base(curve), *Fs = curve_scalar(curve);
+    if (n == 0) return;
+    fe *repr = (fe *)malloc(n * sizeof(fe));
+    for (size_t i = 0; i < n; i++) fe_from_mont(&repr[i], &coeffs_mont[i], Fs); /* to_repr(): canonical LE bytes */
+    size_t c;
+    if (n < 4) c = 1;
+    else if (n < 32) c = 3;
+    else c = (size_t)ceil(log((double)n));
+    size_t segments = 256 / c + 1;
+    size_t nb = ((size_t)1 << c) - 1;
+    bucket_t *buckets = (bucket_t *)malloc(nb * sizeof(bucket_t));
+    for (size_t seg = segments; seg-- > 0;) {
+        for (size_t k = 0; k < c; k++) jac_double(acc, acc, Fb);
+        for (size_t b = 0; b < nb; b++) buckets[b].kind = 0;
+        for (size_t i = 0; i < n; i++) {
+            size_t d = get_at(seg, c, (const unsigned char *)repr[i].l);
+            if (d != 0) {
+                bucket_t *B = &buckets[d - 1];
+                if (B->kind == 0) { B->kind = 1; B->a = bases[i]; }
+                else if (B->kind == 1) {
+                    jac t;
+                    if (aff_is_id(&B->a)) jac_set_id(&t);
+                    else { t.x = B->a.x; t.y = B->a.y; fe_one(&t.z, Fb); }
+                    jac_add_aff(&B->j, &t, &bases[i], Fb);
+                    B->kind = 2;
+                } else {
+                    jac_add_aff(&B->j, &B->j, &bases[i], Fb);
+                }
+            }
+        }
+        jac running;
+        jac_set_id(&running);
+        for (size_t b = nb; b-- > 0;) {
+            bucket_t *B = &buckets[b];
+            if (B->kind == 1) jac_add_aff(&running, &running, &B->a, Fb);
+            else if (B->kind == 2) jac_add(&running, &running, &B->j, Fb);
+            jac_add(acc, acc, &running, Fb);
+        }
+    }
+    free(buckets);
+    free(repr);
+}
+
+/* best_multiexp(coeffs, bases).to_affine() -- src/commitment.rs:83.  threads<=0 -> all cores. */
+int so_msm(int curve, const u64 *scalars_mont, const u64 *bases_xy, size_t n, int threads, u64 out_xy[8]) {
+    const field_t *Fb = curve_base(curve);
+    const fe *coeffs = (const fe *)scalars_mont;
+    const aff *bases = (const aff *)bases_xy;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#else
+    threads = 1;
+#endif
+    jac total;
+    jac_set_id(&total);
+    if (n > (size_t)threads) {
+        size_t chunk = n / (size_t)threads;
+        size_t num_chunks = (n + chunk - 1) / chunk;
+        jac *results = (jac *)calloc(num_chunks, sizeof(jac));
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+        for (long ci = 0; ci < (long)num_chunks; ci++) {
+            size_t lo = (size_t)ci * chunk;
+            size_t len = (lo + chunk <= n) ? chunk : n - lo;
+            multiexp_serial(coeffs + lo, bases + lo, len, &results[ci], curve);
+        }
+        for (size_t ci = 0; ci < num_chunks; ci++) jac_add(&total, &total, &results[ci], Fb);
+        free(results);
+    } else {
+        multiexp_serial(coeffs, bases, n, &total, curve);
+    }
+    aff o;
+    jac_to_affine(&o, &total, Fb);
+    memcpy(out_xy, &o, 64);
+    return 0;
+}
+
+/* sum_i s_i P_i by plain double-and-add (definition-level cross-check for so_msm). */
+int so_msm_naive(int curve, const u64 *scalars_mont, const u64 *bases_xy, size_t n, u64 out_xy[8]) {
+    const field_t *Fb = curve_base(curve), *Fs = curve_scalar(curve);
+    const fe *coeffs = (const fe *)scalars_mont;
+    const aff *bases = (const aff *)bases_xy;
+    jac total;
+    jac_set_id(&total);
+    for (size_t i = 0; i < n; i++) {
+        fe s;
+        fe_from_mont(&s, &coeffs[i], Fs);
+        jac acc;
+        jac_set_id(&acc);
+        for (int b = 255; b >= 0; b--) {
+            jac_double(&acc, &acc, Fb);
+            if ((s.l[b / 64] >> (b % 64)) & 1) jac_add_aff(&acc, &acc, &bases[i], Fb);
+        }
+        jac_add(&total, &total, &acc, Fb);
+    }
+    aff o;
+    jac_to_affine(&o, &total, Fb);
+    memcpy(out_xy, &o, 64);
+    return 0;
+}
+
+/* out = a + b (affine, identity = (0,0)) : used to check partial-sum combination (multi-GPU) */
+int so_point_add(int curve, const u64 a_xy[8], const u64 b_xy[8], u64 out_xy[8]) {
+    const field_t *Fb = curve_base(curve);
+    jac t;
+    jac_set_id(&t);
+    jac_add_aff(&t, &t, (const aff *)a_xy, Fb);
+    jac_add_aff(&t, &t, (const aff *)b_xy, Fb);
+    aff o;
+    jac_to_affine(&o, &t, Fb);
+    memcpy(out_xy, &o, 64);
+    return 0;
+}
+
+int so_is_on_curve(int curve, const u64 xy[8]) {
+    const field_t *Fb = curve_base(curve);
+    const aff *p = (const aff *)xy;
+    if (aff_is_id(p)) return 1;
+    fe y2, x3, b, t;
+    fe_sqr(&y2, &p->y, Fb);
+    fe_sqr(&x3, &p->x, Fb);
+    fe_mul(&x3, &x3, &p->x, Fb);
+    fe three = {{3, 0, 0, 0}}, seventeen = {{17, 0, 0, 0}};
+    if (curve == 0) fe_to_mont(&b, &three, Fb);
+    else { fe_to_mont(&b, &seventeen, Fb); fe_neg(&b, &b, Fb); }
+    fe_add(&t, &x3, &b, Fb);
+    return fe_eq(&t, &y2);
+}
+
+/* Synthetic bases G_i = [i+1]G by running addition, batch-normalised.
+ * gen_xy: affine generator in Montgomery form. */
+int so_running_bases(int curve, const u64 gen_xy[8], size_t n, u64 *out_xy) {
+    const field_t *Fb = curve_base(curve);
+    const aff *G = (const aff *)gen_xy;
+    aff *out = (aff *)out_xy;
+    if (n == 0) return 0;
+    jac *pts = (jac *)malloc(n * sizeof(jac));
+    jac cur;
+    jac_set_id(&cur);
+    for (size_t i = 0; i < n; i++) {
+        jac_add_aff(&cur, &cur, G, Fb);
+        pts[i] = cur;
+    }
+    /* batch inversion of z (no identity can occur for n < group order) */
+    fe *pref = (fe *)malloc(n * sizeof(fe));
+    fe acc;
+    fe_one(&acc, Fb);
+    for (size_t i = 0; i < n; i++) {
+        pref[i] = acc;
+        fe_mul(&acc, &acc, &pts[i].z, Fb);
+    }
+    fe inv;
+    fe_inv(&inv, &acc, Fb);
+    for (size_t i = n; i-- > 0;) {
+        fe zi, zi2, zi3;
+        fe_mul(&zi, &inv, &pref[i], Fb);
+        fe_mul(&inv, &inv, &pts[i].z, Fb);
+        fe_sqr(&zi2, &zi, Fb);
+        fe_mul(&zi3, &zi2, &zi, Fb);
+        fe_mul(&out[i].x, &pts[i].x, &zi2, Fb);
+        fe_mul(&out[i].y, &pts[i].y, &zi3, Fb);
+    }
+    free(pref);
+    free(pts);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ FFT: src/fft.rs restated */
+
+static size_t bitreverse(size_t input, size_t limit) { /* src/fft.rs:41-49 */
+    size_t r = 0;
+    for (size_t i = 0; i < limit; i++) r |= ((input >> i) & 1) << (limit - 1 - i);
+    return r;
+}
+
+/* src/fft.rs:118-155 */
+static void recursive_butterfly(fe *a, size_t n, size_t twiddle_chunk, const fe *tw, const field_t *F, int depth) {
+    if (n == 2) {
+        fe t = a[1];
+        a[1] = a[0];
+        fe_add(&a[0], &a[0], &t, F);
+        fe_sub(&a[1], &a[1], &t, F);
+        return;
+    }
+    fe *left = a, *right = a + n / 2;
+#ifdef _OPENMP
+    if (depth < 6) {
+#pragma omp task shared(tw)
+        recursive_butterfly(left, n / 2, twiddle_chunk * 2, tw, F, depth + 1);
+#pragma omp task shared(tw)
+        recursive_butterfly(right, n / 2, twiddle_chunk * 2, tw, F, depth + 1);
+#pragma omp taskwait
+    } else
+#endif
+    {
+        recursive_butterfly(left, n / 2, twiddle_chunk * 2, tw, F, depth + 1);
+        recursive_butterfly(right, n / 2, twiddle_chunk * 2, tw, F, depth + 1);
+    }
+    fe t = right[0];
+    right[0] = left[0];
+    fe_add(&left[0], &left[0], &t, F);
+    fe_sub(&right[0], &right[0], &t, F);
+    for (size_t i = 1; i < n / 2; i++) {
+        fe tt;
+        fe_mul(&tt, &right[i], &tw[i * twiddle_chunk], F);
+        right[i] = left[i];
+        fe_add(&left[i], &left[i], &tt, F);
+        fe_sub(&right[i], &right[i], &tt, F);
+    }
+}
+
+/* best_fft, src/fft.rs:61-115: in-place radix-2 DIT, natural order in and out.
+ * `threads` <= 1 takes the iterative branch (:83-111), otherwise the recursive one (:112-114);
+ * both compute the same values (exact arithmetic). */
+int so_best_fft(int field, u64 *a_mont, uint32_t log_n, const u64 omega_mont[4], int threads) {
+    const field_t *F = &FIELDS[field];
+    fe *a = (fe *)a_mont;
+    size_t n = (size_t)1 << log_n;
+    if (n == 1) return 0;
+    for (size_t k = 0; k < n; k++) {
+        size_t rk = bitreverse(k, log_n);
+        if (k < rk) { fe t = a[rk]; a[rk] = a[k]; a[k] = t; }
+    }
+    fe *tw = (fe *)malloc((n / 2) * sizeof(fe));
+    fe w, omega;
+    memcpy(omega.l, omega_mont, 32);
+    fe_one(&w, F);
+    for (size_t i = 0; i < n / 2; i++) {
+        tw[i] = w;
+        fe_mul(&w, &w, &omega, F);
+    }
+    if (threads <= 1) {
+        size_t chunk = 2, twiddle_chunk = n / 2;
+        for (uint32_t s = 0; s < log_n; s++) {
+            for (size_t base = 0; base < n; base += chunk) {
+                fe *left = a + base, *right = a + base + chunk / 2;
+                fe t = right[0];
+                right[0] = left[0];
+                fe_add(&left[0], &left[0], &t, F);
+                fe_sub(&right[0], &right[0], &t, F);
+                for (size_t i = 1; i < chunk / 2; i++) {
+                    fe tt;
+                    fe_mul(&tt, &right[i], &tw[i * twiddle_chunk], F);
+                    right[i] = left[i];
+                    fe_add(&left[i], &left[i], &tt, F);
+                    fe_sub(&right[i], &right[i], &tt, F);
+                }
+            }
+            chunk *= 2;
+            twiddle_chunk /= 2;
+        }
+    } else {
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads)
+#pragma omp single
+#endif
+        recursive_butterfly(a, n, 1, tw, F, 0);
+    }
+    free(tw);
+    return 0;
+}
+
+/* a[i] *= s  (ifft divisor, src/fft.rs:177-181) */
+int so_scale(int field, u64 *a_mont, size_t n, const u64 s_mont[4]) {
+    const field_t *F = &FIELDS[field];
+    fe *a = (fe *)a_mont, s;
+    memcpy(s.l, s_mont, 32);
+#pragma omp parallel for
+    for (long i = 0; i < (long)n; i++) fe_mul(&a[i], &a[i], &s, F);
+    return 0;
+}
+
+/* distribute_powers_zeta, src/fft.rs:207-228: a[i] *= powers[i%3 - 1] for i%3 != 0,
+ * powers = [z, z2] given by the caller in the order to apply. */
+int so_coset_scale(int field, u64 *a_mont, size_t n, const u64 z_mont[4], const u64 z2_mont[4]) {
+    const field_t *F = &FIELDS[field];
+    fe *a = (fe *)a_mont, z[2];
+    memcpy(z[0].l, z_mont, 32);
+    memcpy(z[1].l, z2_mont, 32);
+#pragma omp parallel for
+    for (long i = 0; i < (long)n; i++) {
+        size_t r = (size_t)i % 3;
+        if (r) fe_mul(&a[i], &a[i], &z[r - 1], F);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ elementwise helpers used by tests */
+
+int so_field_mul(int field, const u64 *a, const u64 *b, u64 *o, size_t n) {
+    const field_t *F = &FIELDS[field];
+    for (size_t i = 0; i < n; i++) fe_mul((fe *)o + i, (const fe *)a + i, (const fe *)b + i, F);
+    return 0;
+}
+int so_field_add(int field, const u64 *a, const u64 *b, u64 *o, size_t n) {
+    const field_t *F = &FIELDS[field];
+    for (size_t i = 0; i < n; i++) fe_add((fe *)o + i, (const fe *)a + i, (const fe *)b + i, F);
+    return 0;
+}
+int so_field_sub(int field, const u64 *a, const u64 *b, u64 *o, size_t n) {
+    const field_t *F = &FIELDS[field];
+    for (size_t i = 0; i < n; i++) fe_sub((fe *)o + i, (const fe *)a + i, (const fe *)b + i, F);
+    return 0;
+}
+int so_field_inv(int field, const u64 *a, u64 *o, size_t n) {
+    const field_t *F = &FIELDS[field];
+    for (size_t i = 0; i < n; i++) fe_inv((fe *)o + i, (const fe *)a + i, F);
+    return 0;
+}
+int so_to_mont(int field, const u64 *a, u64 *o, size_t n) {
+    const field_t *F = &FIELDS[field];
+    for (size_t i = 0; i < n; i++) fe_to_mont((fe *)o + i, (const fe *)a + i, F);
+    return 0;
+}
+int so_from_mont(int field, const u64 *a, u64 *o, size_t n) {
+    const field_t *F = &FIELDS[field];
+    for (size_t i = 0; i < n; i++) fe_from_mont((fe *)o + i, (const fe *)a + i, F);
+    return 0;
+}
+
+/* xoshiro256** field-element stream: canonical draw < p by rejection, stored Montgomery. */
+static inline u64 rotl64(u64 x, int k) { return (x << k) | (x >> (64 - k)); }
+int so_random_field(int field, u64 seed, size_t n, u64 *out_mont) {
+    const field_t *F = &FIELDS[field];
+    u64 s[4], x = seed;
+    for (int i = 0; i < 4; i++) {
+        x += 0x9E3779B97F4A7C15ULL;
+        u64 z = x;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        s[i] = z ^ (z >> 31);
+    }
+    for (size_t i = 0; i < n; i++) {
+        fe v;
+        do {
+            for (int k = 0; k < 4; k++) {
+                u64 result = rotl64(s[1] * 5, 7) * 9;
+                u64 t = s[1] << 17;
+                s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+                s[2] ^= t;
+                s[3] = rotl64(s[3], 45);
+                v.l[k] = result;
+            }
+            v.l[3] &= 0x3fffffffffffffffULL;
+        } while (geq_p(v.l, F->p));
+        fe_to_mont((fe *)out_mont + i, &v, F);
+    }
+    return 0;
+}
+
+int so_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
