@@ -1,0 +1,73 @@
+"""ctypes binding of libsirius_b200.so (the C ABI in include/sirius_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no device is present every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsirius_b200.so")
+
+SB_OK = 0
+SB_ERR_CUDA = -1
+SB_ERR_ARG = -2
+SB_ERR_OOM = -3
+SB_ERR_TOO_LONG = -4
+SB_ERR_NCCL = -5
+
+FIELD_FR, FIELD_FQ = 0, 1
+CURVE_BN256, CURVE_GRUMPKIN = 0, 1
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); kept in one table so tests can check the exports against include/sirius_b200.h
+SIGNATURES = {
+    "sb_last_error": (ctypes.c_char_p, []),
+    "sb_version": (ctypes.c_int, []),
+    "sb_init": (ctypes.c_int, [ctypes.c_int]),
+    "sb_shutdown": (None, []),
+    "sb_device_count": (ctypes.c_int, []),
+    "sb_ck_register": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(vp)]),
+    "sb_ck_register_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_int, vp, ctypes.POINTER(vp)]),
+    "sb_ck_release": (None, [vp]),
+    "sb_ck_len": (ctypes.c_size_t, [vp]),
+    "sb_ck_window_bits": (ctypes.c_int, [vp]),
+    "sb_msm": (ctypes.c_int, [vp, u64p, ctypes.c_size_t, u64p]),
+    "sb_msm_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, vp, vp, vp]),
+    "sb_msm_combine_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
+    "sb_selftest_field": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p, u64p]),
+}
+
+_lib = None
+
+
+class SiriusB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsirius_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(sirius_b200 has no CPU fallback)"
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != SB_OK:
+        raise SiriusB200Error(rc, load().sb_last_error().decode(errors="replace"))

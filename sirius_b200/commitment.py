@@ -1,0 +1,98 @@
+"""Mirror of reference src/commitment.rs: `CommitmentKey` with a device-resident key.
+
+    CommitmentKey(curve, ck)      ~ CommitmentKey { ck: Box<[C]> }        (src/commitment.rs:29-32)
+    .commit(v) -> affine point    ~ CommitmentKey::commit                 (src/commitment.rs:81-90)
+    TooLongInput                  ~ Error::TooLongInput{input_len,limit}  (src/commitment.rs:24-27)
+    len(), is_empty()             ~ src/commitment.rs:47-53
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class TooLongInput(ValueError):
+    """commitment::Error::TooLongInput."""
+
+    def __init__(self, input_len: int, limit: int):
+        super().__init__(f"Can't commit too long input: input len: {input_len}, but limit is {limit}")
+        self.input_len = input_len
+        self.limit = limit
+
+
+def _as_u64(a, width: int) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=np.uint64)
+    return arr.reshape(-1, width)
+
+
+class CommitmentKey:
+    def __init__(self, curve: int, ck, window_bits: int = 0):
+        lib = _lib.load()
+        self.curve = int(curve)
+        self._host = _as_u64(ck, 8)
+        self._h = ctypes.c_void_p()
+        _lib.check(
+            lib.sb_ck_register(self.curve, self._host.ctypes.data_as(_lib.u64p), self._host.shape[0], int(window_bits), ctypes.byref(self._h))
+        )
+
+    @classmethod
+    def from_device(cls, curve: int, d_ptr: int, n: int, window_bits: int = 0, stream: int = 0) -> "CommitmentKey":
+        lib = _lib.load()
+        self = cls.__new__(cls)
+        self.curve = int(curve)
+        self._host = None
+        self._h = ctypes.c_void_p()
+        _lib.check(lib.sb_ck_register_device(self.curve, ctypes.c_void_p(d_ptr), n, int(window_bits), ctypes.c_void_p(stream), ctypes.byref(self._h)))
+        return self
+
+    # -- Rust API mirror -------------------------------------------------------------------------
+    def len(self) -> int:
+        return int(_lib.load().sb_ck_len(self._h))
+
+    __len__ = len
+
+    def is_empty(self) -> bool:
+        return self.len() == 0
+
+    @property
+    def window_bits(self) -> int:
+        return int(_lib.load().sb_ck_window_bits(self._h))
+
+    @staticmethod
+    def default_value() -> np.ndarray:
+        """C::identity(), encoded (0,0)."""
+        return np.zeros(8, dtype=np.uint64)
+
+    def commit(self, v) -> np.ndarray:
+        """sum_i v[i] * ck[i] as an affine point (uint64[8]); raises TooLongInput like the Rust Err."""
+        s = _as_u64(v, 4)
+        n = s.shape[0]
+        if n > self.len():
+            raise TooLongInput(n, self.len())
+        out = np.zeros(8, dtype=np.uint64)
+        rc = _lib.load().sb_msm(self._h, s.ctypes.data_as(_lib.u64p), n, out.ctypes.data_as(_lib.u64p))
+        _lib.check(rc)
+        return out
+
+    def commit_device(self, d_scalars: int, n: int, d_out_xy: int = 0, d_out_xyzz: int = 0, stream: int = 0) -> None:
+        """Scalars already in HBM; enqueues on `stream` and returns without synchronising."""
+        if n > self.len():
+            raise TooLongInput(n, self.len())
+        rc = _lib.load().sb_msm_device(
+            self._h, ctypes.c_void_p(d_scalars), n, ctypes.c_void_p(d_out_xy or None), ctypes.c_void_p(d_out_xyzz or None), ctypes.c_void_p(stream or None)
+        )
+        _lib.check(rc)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().sb_ck_release(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

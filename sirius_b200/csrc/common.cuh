@@ -1,0 +1,55 @@
+// common.cuh -- error plumbing, the library stream and a grow-only device workspace.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <mutex>
+
+#include "../../include/sirius_b200.h"
+
+namespace sb {
+
+void set_error(const char* fmt, ...);
+
+#define SB_CUDA_TRY(expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            sb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return SB_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+#define SB_TRY(expr)            \
+    do {                        \
+        int _rc = (expr);       \
+        if (_rc != SB_OK) return _rc; \
+    } while (0)
+
+#define SB_KERNEL_CHECK() SB_CUDA_TRY(cudaGetLastError())
+
+// Library-wide state for the device this process drives (one process per GPU).
+struct Runtime {
+    std::mutex mu;          // serialises library calls that share the workspace (commit is called sequentially
+                            // by the reference, SURVEY 3.3, but cargo test runs tests on many threads)
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool ready = false;
+};
+Runtime& runtime();
+int ensure_runtime();
+
+// Grow-only scratch buffer; contents are dead between calls.
+struct Scratch {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace sb

@@ -1,0 +1,144 @@
+// curve.cuh -- short-Weierstrass a = 0 group law (bn256 G1: y^2 = x^3 + 3 over Fq; grumpkin:
+// y^2 = x^3 - 17 over Fr) in XYZZ coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2).
+//
+// The reference gets its group law from halo2curves (Jacobian) through `best_multiexp`
+// (reference src/commitment.rs:83).  The sum of points is unique, so any complete addition law gives the
+// same affine result; XYZZ is used here because the mixed addition (accumulator += affine base) is the
+// inner loop of the MSM and costs 8M + 2S with no inversion.
+//
+// Every operation handles the exceptional cases explicitly (identity operands, P + P, P + (-P)), so results
+// are exact for adversarial inputs (repeated bases, cancelling scalars) -- parity is bit-exact, not generic-case.
+#pragma once
+#include "field.cuh"
+
+namespace sb {
+
+enum : int { CURVE_BN256 = 0, CURVE_GRUMPKIN = 1 };
+
+template <class F>
+struct alignas(16) Affine {  // identity encoded as (0,0) (reference src/commitment.rs:43-45)
+    F x, y;
+    SB_HD bool is_identity() const { return x.is_zero() && y.is_zero(); }
+};
+
+template <class F>
+struct alignas(16) XYZZ {  // identity: zz == 0
+    F x, y, zz, zzz;
+    SB_HD bool is_identity() const { return zz.is_zero(); }
+    static SB_HD XYZZ identity() {
+        XYZZ r;
+        r.x = F::zero(); r.y = F::zero(); r.zz = F::zero(); r.zzz = F::zero();
+        return r;
+    }
+    static SB_HD XYZZ from_affine(const Affine<F>& p) {
+        XYZZ r;
+        if (p.is_identity()) return identity();
+        r.x = p.x; r.y = p.y; r.zz = F::one(); r.zzz = F::one();
+        return r;
+    }
+};
+
+// 2 * (affine p), p not the identity.  y = 0 cannot happen on a prime-order curve, but is handled.
+template <class F>
+SB_HD XYZZ<F> xyzz_double_affine(const F& px, const F& py) {
+    XYZZ<F> r;
+    if (py.is_zero()) return XYZZ<F>::identity();
+    F u = dbl(py);
+    F v = sqr(u);
+    F w = mul(u, v);
+    F s = mul(px, v);
+    F xx = sqr(px);
+    F m = add(dbl(xx), xx);
+    r.x = sub(sqr(m), dbl(s));
+    r.y = sub(mul(m, sub(s, r.x)), mul(w, py));
+    r.zz = v;
+    r.zzz = w;
+    return r;
+}
+
+template <class F>
+SB_HD XYZZ<F> xyzz_double(const XYZZ<F>& p) {
+    if (p.is_identity() || p.y.is_zero()) return XYZZ<F>::identity();
+    XYZZ<F> r;
+    F u = dbl(p.y);
+    F v = sqr(u);
+    F w = mul(u, v);
+    F s = mul(p.x, v);
+    F xx = sqr(p.x);
+    F m = add(dbl(xx), xx);
+    r.x = sub(sqr(m), dbl(s));
+    r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
+    r.zz = mul(v, p.zz);
+    r.zzz = mul(w, p.zzz);
+    return r;
+}
+
+// acc += (negate ? -q : q), q affine.
+template <class F>
+SB_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q, bool negate) {
+    if (q.is_identity()) return;
+    F qy = negate ? neg(q.y) : q.y;
+    if (acc.is_identity()) {
+        acc.x = q.x; acc.y = qy; acc.zz = F::one(); acc.zzz = F::one();
+        return;
+    }
+    F u2 = mul(q.x, acc.zz);
+    F s2 = mul(qy, acc.zzz);
+    F p = sub(u2, acc.x);
+    F r = sub(s2, acc.y);
+    if (p.is_zero()) {
+        if (r.is_zero()) acc = xyzz_double_affine(q.x, qy);
+        else acc = XYZZ<F>::identity();
+        return;
+    }
+    F pp = sqr(p);
+    F ppp = mul(p, pp);
+    F qq = mul(acc.x, pp);
+    F x3 = sub(sub(sqr(r), ppp), dbl(qq));
+    F y3 = sub(mul(r, sub(qq, x3)), mul(acc.y, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = mul(acc.zz, pp);
+    acc.zzz = mul(acc.zzz, ppp);
+}
+
+// acc += q, both XYZZ.
+template <class F>
+SB_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
+    if (q.is_identity()) return;
+    if (acc.is_identity()) { acc = q; return; }
+    F u1 = mul(acc.x, q.zz);
+    F u2 = mul(q.x, acc.zz);
+    F s1 = mul(acc.y, q.zzz);
+    F s2 = mul(q.y, acc.zzz);
+    F p = sub(u2, u1);
+    F r = sub(s2, s1);
+    if (p.is_zero()) {
+        if (r.is_zero()) acc = xyzz_double(acc);
+        else acc = XYZZ<F>::identity();
+        return;
+    }
+    F pp = sqr(p);
+    F ppp = mul(p, pp);
+    F qq = mul(u1, pp);
+    F x3 = sub(sub(sqr(r), ppp), dbl(qq));
+    F y3 = sub(mul(r, sub(qq, x3)), mul(s1, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = mul(mul(acc.zz, q.zz), pp);
+    acc.zzz = mul(mul(acc.zzz, q.zzz), ppp);
+}
+
+template <class F>
+SB_HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
+    Affine<F> r;
+    if (p.is_identity()) { r.x = F::zero(); r.y = F::zero(); return r; }
+    F i = inv(mul(p.zz, p.zzz));      // 1/(zz*zzz)
+    F izz = mul(i, p.zzz);            // 1/zz
+    F izzz = mul(i, p.zz);            // 1/zzz
+    r.x = mul(p.x, izz);
+    r.y = mul(p.y, izzz);
+    return r;
+}
+
+}  // namespace sb

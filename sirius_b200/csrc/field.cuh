@@ -1,0 +1,458 @@
+// field.cuh -- 254-bit prime-field arithmetic for bn256 Fr / Fq on sm_100a.
+//
+// Replaces (on the device) the halo2curves field types the reference uses everywhere on its hot path
+// (re-exported at reference src/lib.rs:24-27).  Same memory format as the Rust side hands over
+// (SURVEY App. A): 4 x u64 little-endian limbs == 8 x u32 little-endian limbs, Montgomery form, R = 2^256.
+//
+// Two implementations of the Montgomery product live here:
+//   * mul_portable(): plain C++ (32x32->64 products), compiles for host and device; it is the
+//     on-device cross-check for the PTX path (tests/ run both on the GPU and compare bit for bit);
+//   * mul(): on the device, an even/odd-limb interleaved CIOS written as PTX carry chains
+//     (mad.lo.cc / madc.hi.cc), which ptxas fuses into IMAD.WIDE.U32(.X) -- the integer pipe is the
+//     roofline of every kernel in this library, so this routine is the inner loop.
+//
+// Values are kept fully reduced in [0, p) at every function boundary.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SB_HD __host__ __device__ __forceinline__
+#define SB_D __device__ __forceinline__
+#else
+#define SB_HD inline
+#define SB_D inline
+#endif
+
+namespace sb {
+
+enum : int { FIELD_FR = 0, FIELD_FQ = 1 };
+
+// bn256 scalar field (= grumpkin base field)
+struct FrParams {
+    static constexpr int ID = FIELD_FR;
+    static constexpr uint32_t P0 = 0xf0000001u, P1 = 0x43e1f593u, P2 = 0x79b97091u, P3 = 0x2833e848u,
+                              P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+    static constexpr uint32_t INV = 0xefffffffu;  // -p^-1 mod 2^32
+    // R mod p
+    static constexpr uint32_t R0 = 0x4ffffffbu, R1 = 0xac96341cu, R2_ = 0x9f60cd29u, R3 = 0x36fc7695u,
+                              R4 = 0x7879462eu, R5 = 0x666ea36fu, R6 = 0x9a07df2fu, R7 = 0x0e0a77c1u;
+    // R^2 mod p
+    static constexpr uint32_t RR0 = 0xae216da7u, RR1 = 0x1bb8e645u, RR2 = 0xe35c59e3u, RR3 = 0x53fe3ab1u,
+                              RR4 = 0x53bb8085u, RR5 = 0x8c49833du, RR6 = 0x7f4e44a5u, RR7 = 0x0216d0b1u;
+};
+
+// bn256 base field (= grumpkin scalar field)
+struct FqParams {
+    static constexpr int ID = FIELD_FQ;
+    static constexpr uint32_t P0 = 0xd87cfd47u, P1 = 0x3c208c16u, P2 = 0x6871ca8du, P3 = 0x97816a91u,
+                              P4 = 0x8181585du, P5 = 0xb85045b6u, P6 = 0xe131a029u, P7 = 0x30644e72u;
+    static constexpr uint32_t INV = 0xe4866389u;
+    static constexpr uint32_t R0 = 0xc58f0d9du, R1 = 0xd35d438du, R2_ = 0xf5c70b3du, R3 = 0x0a78eb28u,
+                              R4 = 0x7879462cu, R5 = 0x666ea36fu, R6 = 0x9a07df2fu, R7 = 0x0e0a77c1u;
+    static constexpr uint32_t RR0 = 0x538afa89u, RR1 = 0xf32cfc5bu, RR2 = 0xd44501fbu, RR3 = 0xb5e71911u,
+                              RR4 = 0x0a417ff6u, RR5 = 0x47ab1effu, RR6 = 0xcab8351fu, RR7 = 0x06d89f71u;
+};
+
+template <class P>
+struct alignas(16) Fe {
+    uint32_t v[8];
+
+    using Params = P;
+
+    static SB_HD Fe zero() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.v[i] = 0;
+        return r;
+    }
+    static SB_HD Fe one() {  // Montgomery form of 1
+        Fe r;
+        r.v[0] = P::R0; r.v[1] = P::R1; r.v[2] = P::R2_; r.v[3] = P::R3;
+        r.v[4] = P::R4; r.v[5] = P::R5; r.v[6] = P::R6; r.v[7] = P::R7;
+        return r;
+    }
+    static SB_HD Fe r_squared() {
+        Fe r;
+        r.v[0] = P::RR0; r.v[1] = P::RR1; r.v[2] = P::RR2; r.v[3] = P::RR3;
+        r.v[4] = P::RR4; r.v[5] = P::RR5; r.v[6] = P::RR6; r.v[7] = P::RR7;
+        return r;
+    }
+    static SB_HD uint32_t modulus_limb(int i) {
+        switch (i) {
+            case 0: return P::P0; case 1: return P::P1; case 2: return P::P2; case 3: return P::P3;
+            case 4: return P::P4; case 5: return P::P5; case 6: return P::P6; default: return P::P7;
+        }
+    }
+
+    SB_HD bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= v[i];
+        return o == 0;
+    }
+    SB_HD bool operator==(const Fe& b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i];
+        return o == 0;
+    }
+    SB_HD bool operator!=(const Fe& b) const { return !(*this == b); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// portable limb helpers (host + device)
+// ---------------------------------------------------------------------------------------------
+
+// r = a - p if a >= p else a   (a < 2p assumed, 8 limbs, no carry in)
+template <class P>
+SB_HD void reduce_once_portable(uint32_t r[8]) {
+    uint32_t t[8];
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)r[i] - Fe<P>::modulus_limb(i) - br;
+        t[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    if (!br) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = t[i];
+    }
+}
+
+template <class P>
+SB_HD Fe<P> add_portable(const Fe<P>& a, const Fe<P>& b) {
+    Fe<P> r;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a.v[i] + b.v[i];
+        r.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    reduce_once_portable<P>(r.v);  // a+b < 2p < 2^255
+    return r;
+}
+
+template <class P>
+SB_HD Fe<P> sub_portable(const Fe<P>& a, const Fe<P>& b) {
+    Fe<P> r;
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a.v[i] - b.v[i] - br;
+        r.v[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    if (br) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            c += (uint64_t)r.v[i] + Fe<P>::modulus_limb(i);
+            r.v[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    return r;
+}
+
+// CIOS Montgomery product with 32-bit limbs and 64-bit accumulators.
+template <class P>
+SB_HD Fe<P> mul_portable(const Fe<P>& a, const Fe<P>& b) {
+    uint32_t t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c += (uint64_t)a.v[j] * b.v[i] + t[j];
+            t[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[8] = (uint32_t)c;
+        t[9] = (uint32_t)(c >> 32);
+        uint32_t m = t[0] * P::INV;
+        c = (uint64_t)m * Fe<P>::modulus_limb(0) + t[0];
+        c >>= 32;
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            c += (uint64_t)m * Fe<P>::modulus_limb(j) + t[j];
+            t[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[7] = (uint32_t)c;
+        t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    Fe<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+    reduce_once_portable<P>(r.v);  // result < 2p, t[8] == 0
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device PTX path
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+
+// r = (r >= p) ? r - p : r
+template <class P>
+SB_D void reduce_once_ptx(uint32_t r[8]) {
+    uint32_t t0, t1, t2, t3, t4, t5, t6, t7, br;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t0), "=r"(t1), "=r"(t2), "=r"(t3), "=r"(t4), "=r"(t5), "=r"(t6), "=r"(t7), "=r"(br)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(P::P0), "r"(P::P1), "r"(P::P2), "r"(P::P3), "r"(P::P4), "r"(P::P5), "r"(P::P6), "r"(P::P7));
+    if (br == 0) {  // no borrow: r >= p
+        r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3; r[4] = t4; r[5] = t5; r[6] = t6; r[7] = t7;
+    }
+}
+
+template <class P>
+SB_D Fe<P> add_ptx(const Fe<P>& a, const Fe<P>& b) {
+    Fe<P> r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    reduce_once_ptx<P>(r.v);
+    return r;
+}
+
+template <class P>
+SB_D Fe<P> sub_ptx(const Fe<P>& a, const Fe<P>& b) {
+    Fe<P> r;
+    uint32_t br;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(br)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    // br is 0 or 0xffffffff: add (p & br)
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+        : "r"(P::P0 & br), "r"(P::P1 & br), "r"(P::P2 & br), "r"(P::P3 & br), "r"(P::P4 & br), "r"(P::P5 & br),
+          "r"(P::P6 & br), "r"(P::P7 & br));
+    return r;
+}
+
+// X[0..7] += (x0,x1,x2,x3) * s as four (lo,hi) pairs on one carry chain; carry out added into X[8].
+SB_D void chain_even(uint32_t X[9], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t s) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(X[8])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(s));
+}
+
+// Y[0..7] += (x0..x3) * s, same pairing, no carry out (bounded by the caller's invariant).
+SB_D void chain_odd(uint32_t Y[9], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t s) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+        "madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(s));
+}
+
+// One frame shift of the interleaved CIOS (see mul_ptx): X[0] += Y[1] and, on the same carry chain,
+// Y[k] = Y[k+2] + (x0..x3)*s pairs.  Y[8] is cleared (it becomes the next even array's carry limb).
+SB_D void fold_shift_chain_odd(uint32_t X[9], uint32_t Y[9], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t s) {
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "madc.lo.cc.u32 %1, %10, %14, %3;\n\t"
+        "madc.hi.cc.u32 %2, %10, %14, %4;\n\t"
+        "madc.lo.cc.u32 %3, %11, %14, %5;\n\t"
+        "madc.hi.cc.u32 %4, %11, %14, %6;\n\t"
+        "madc.lo.cc.u32 %5, %12, %14, %7;\n\t"
+        "madc.hi.cc.u32 %6, %12, %14, %8;\n\t"
+        "madc.lo.cc.u32 %7, %13, %14, %9;\n\t"
+        "madc.hi.u32 %8, %13, %14, 0;\n\t"
+        "mov.u32 %9, 0;"
+        : "+r"(X[0]), "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]), "+r"(Y[8])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(s));
+}
+
+// Montgomery product, even/odd interleaved CIOS.
+//
+// The running sum S is held as S = E + O * 2^32 with E = e[0..8] (9 limbs) and O = o[0..7].  Products
+// a[j]*b_i with even j land on aligned (lo,hi) limb pairs of E, odd j on aligned pairs of O, so each
+// row is two independent carry chains with no limb-by-limb ripple.  After adding m*p (m = e[0]*INV)
+// e[0] == 0 and S/2^32 = (e[1] + e[2..8] * 2^32) + O: the old O becomes the new E, e[2..8] becomes
+// the new O, and the stray e[1] is folded into new-E limb 0 whose carry (weight 2^32) enters the new
+// O chain as its carry-in.  Invariant: S < 2p at row boundaries, S < 2^288 inside a row, hence the
+// "no carry out" claims of chain_odd / fold_shift_chain_odd.
+template <class P>
+SB_D Fe<P> mul_ptx(const Fe<P>& a, const Fe<P>& b) {
+    uint32_t A[9], B[9];
+    const uint32_t b0 = b.v[0];
+    // row 0: E = A, O = B
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(A[0]), "=r"(A[1]), "=r"(A[2]), "=r"(A[3]), "=r"(A[4]), "=r"(A[5]), "=r"(A[6]), "=r"(A[7])
+        : "r"(a.v[0]), "r"(a.v[2]), "r"(a.v[4]), "r"(a.v[6]), "r"(b0));
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(B[0]), "=r"(B[1]), "=r"(B[2]), "=r"(B[3]), "=r"(B[4]), "=r"(B[5]), "=r"(B[6]), "=r"(B[7])
+        : "r"(a.v[1]), "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]), "r"(b0));
+    A[8] = 0;
+    B[8] = 0;
+    {
+        uint32_t m = A[0] * P::INV;
+        chain_odd(B, P::P1, P::P3, P::P5, P::P7, m);
+        chain_even(A, P::P0, P::P2, P::P4, P::P6, m);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        {  // odd row: even array = B, odd array = A
+            const uint32_t bi = b.v[i];
+            fold_shift_chain_odd(B, A, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+            chain_even(B, a.v[0], a.v[2], a.v[4], a.v[6], bi);
+            uint32_t m = B[0] * P::INV;
+            chain_odd(A, P::P1, P::P3, P::P5, P::P7, m);
+            chain_even(B, P::P0, P::P2, P::P4, P::P6, m);
+        }
+        if (i + 1 < 8) {  // even row: even array = A, odd array = B
+            const uint32_t bi = b.v[i + 1];
+            fold_shift_chain_odd(A, B, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+            chain_even(A, a.v[0], a.v[2], a.v[4], a.v[6], bi);
+            uint32_t m = A[0] * P::INV;
+            chain_odd(B, P::P1, P::P3, P::P5, P::P7, m);
+            chain_even(A, P::P0, P::P2, P::P4, P::P6, m);
+        }
+    }
+    // after row 7: even array = B (B[0] == 0), odd array = A.  S/2^32 = B[1..8] + A[0..7]
+    Fe<P> r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+        : "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]), "r"(B[8]),
+          "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]));
+    reduce_once_ptx<P>(r.v);
+    return r;
+}
+#endif  // __CUDA_ARCH__
+
+// ---------------------------------------------------------------------------------------------
+// public dispatch
+// ---------------------------------------------------------------------------------------------
+template <class P>
+SB_HD Fe<P> add(const Fe<P>& a, const Fe<P>& b) {
+#if defined(__CUDA_ARCH__)
+    return add_ptx(a, b);
+#else
+    return add_portable(a, b);
+#endif
+}
+template <class P>
+SB_HD Fe<P> sub(const Fe<P>& a, const Fe<P>& b) {
+#if defined(__CUDA_ARCH__)
+    return sub_ptx(a, b);
+#else
+    return sub_portable(a, b);
+#endif
+}
+template <class P>
+SB_HD Fe<P> mul(const Fe<P>& a, const Fe<P>& b) {
+#if defined(__CUDA_ARCH__) && !defined(SB_FORCE_PORTABLE_MUL)
+    return mul_ptx(a, b);
+#else
+    return mul_portable(a, b);
+#endif
+}
+template <class P>
+SB_HD Fe<P> sqr(const Fe<P>& a) { return mul(a, a); }
+template <class P>
+SB_HD Fe<P> dbl(const Fe<P>& a) { return add(a, a); }
+template <class P>
+SB_HD Fe<P> neg(const Fe<P>& a) {
+    return a.is_zero() ? a : sub(Fe<P>::zero(), a);
+}
+template <class P>
+SB_HD Fe<P> from_mont(const Fe<P>& a) {
+    Fe<P> o = Fe<P>::zero();
+    o.v[0] = 1;
+    return mul(a, o);
+}
+template <class P>
+SB_HD Fe<P> to_mont(const Fe<P>& a) { return mul(a, Fe<P>::r_squared()); }
+
+// a^(p-2) by square-and-multiply over the constant exponent (a != 0).
+template <class P>
+SB_HD Fe<P> inv(const Fe<P>& a) {
+    Fe<P> acc = Fe<P>::one();
+    // exponent p-2: only limb 0 differs from p (p is odd, P0 >= 2)
+    for (int i = 7; i >= 0; i--) {
+        uint32_t e = Fe<P>::modulus_limb(i) - (i == 0 ? 2u : 0u);
+        for (int bit = 31; bit >= 0; bit--) {
+            acc = sqr(acc);
+            if ((e >> bit) & 1) acc = mul(acc, a);
+        }
+    }
+    return acc;
+}
+
+using Fr = Fe<FrParams>;
+using Fq = Fe<FqParams>;
+
+}  // namespace sb

@@ -1,0 +1,751 @@
+// msm.cu -- Pedersen commitment = multi-scalar multiplication on one B200.
+//
+// Replaces the body of `CommitmentKey::commit` (reference src/commitment.rs:81-90), i.e. halo2's CPU
+// `best_multiexp(v, &ck[..v.len()]).to_affine()`, by a device pipeline:
+//
+//   register (once per CommitmentKey):  table[w][i] = 2^(c*w) * ck[i]            k_precompute
+//   commit:  scalars --from-Montgomery, signed c-bit digits--> (bucket, table index, sign)      k_decompose
+//            counting sort of the n*W digit entries by bucket                    k_scan_* / k_scatter
+//            bucket sums: fixed-size chunks of the sorted entries, one chunk per thread, mixed XYZZ adds
+//                         (skew-proof: a bucket of any size is split across as many threads as it needs)
+//                                                                                k_accumulate, k_fixup
+//            sum_b (b+1) * B_b by a warp-shuffle suffix-scan tree                k_reduce_level0 / k_reduce_level
+//            XYZZ -> affine                                                      k_finalize
+//
+// Because every window's base multiple is precomputed, all W windows share ONE set of 2^(c-1) buckets and
+// there is no per-window doubling chain at the end.  All arithmetic is exact, so any grouping of the
+// additions gives the reference's bit pattern.
+//
+// Roofline: the work is ~W mixed additions per scalar (8M+2S 254-bit Montgomery products each) -- integer-pipe
+// bound; algorithmic HBM traffic is 96 B/point.
+#include <algorithm>
+#include <new>
+
+#include "common.cuh"
+#include "curve.cuh"
+
+namespace sb {
+
+constexpr int LS = 16;          // sorted entries per accumulate chunk (one thread each)
+constexpr int FIX_SMALL = 8;    // buckets split in <= FIX_SMALL pieces are summed by one lane
+constexpr int RED_L0 = 4;       // buckets per lane at level 0 of the bucket reduction
+constexpr int SCAN_ITEMS = 16;  // items per thread in the scan kernels
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+
+template <class F>
+struct alignas(16) Node {  // subtree summary for sum_b (b+1) B_b : S = sum B_b, Wt = sum (b - first + 1) B_b
+    XYZZ<F> S, Wt;
+};
+
+// ------------------------------------------------------------------------------------------------
+// 128-bit global loads/stores of field-sized objects
+// ------------------------------------------------------------------------------------------------
+template <class T>
+SB_D T load_vec(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiples only");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+    return r;
+}
+template <class T>
+SB_D T load_vec_nc(const T* p) {  // read-only path for data not written by this kernel
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiples only");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(s + i);
+    return r;
+}
+template <class T>
+SB_D void store_vec(T* p, const T& v) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiples only");
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp helpers on XYZZ points
+// ------------------------------------------------------------------------------------------------
+template <class F>
+SB_D XYZZ<F> shfl_point(const XYZZ<F>& v, int src_lane) {
+    XYZZ<F> r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 32; i++) d[i] = __shfl_sync(0xffffffffu, s[i], src_lane);
+    return r;
+}
+template <class F>
+SB_D XYZZ<F> shfl_down_point(const XYZZ<F>& v, int delta) {
+    XYZZ<F> r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 32; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+    return r;
+}
+template <class F>
+SB_D XYZZ<F> shfl_xor_point(const XYZZ<F>& v, int mask) {
+    XYZZ<F> r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 32; i++) d[i] = __shfl_xor_sync(0xffffffffu, s[i], mask);
+    return r;
+}
+// all lanes end with the sum over the warp
+template <class F>
+SB_D XYZZ<F> warp_sum(XYZZ<F> v) {
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        XYZZ<F> t = shfl_xor_point(v, d);
+        xyzz_add(v, t);
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// register-time: table of window multiples
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void k_precompute(const Affine<F>* __restrict__ bases, size_t n, int c, int W, Affine<F>* __restrict__ table) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = load_vec_nc(bases + i);
+    store_vec(table + i, p);
+    XYZZ<F> acc = XYZZ<F>::from_affine(p);
+    for (int w = 1; w < W; w++) {
+        for (int j = 0; j < c; j++) acc = xyzz_double(acc);
+        Affine<F> q = xyzz_to_affine(acc);
+        store_vec(table + (size_t)w * n + i, q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// commit-time: digits, counting sort
+// ------------------------------------------------------------------------------------------------
+// dig[w*n + i] = 0 (digit 0) or ((|d|) | sign<<31) for the signed base-2^c digit d of scalar i, window w.
+template <class S>
+__global__ void k_decompose(const S* __restrict__ scalars, uint32_t n, int c, int W, uint32_t* __restrict__ dig,
+                            uint32_t* __restrict__ counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S s = from_mont(load_vec_nc(scalars + i));  // canonical integer, as `to_repr()` in halo2's multiexp
+    uint32_t limb[9];
+#pragma unroll
+    for (int k = 0; k < 8; k++) limb[k] = s.v[k];
+    limb[8] = 0;
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        int off = w * c;
+        int li = off >> 5, sh = off & 31;
+        uint32_t raw = 0;
+        if (li < 8) {
+            uint64_t two = (uint64_t)limb[li] | ((uint64_t)limb[li + 1] << 32);
+            raw = (uint32_t)(two >> sh) & mask;
+        }
+        raw += carry;
+        uint32_t out = 0;
+        if (raw > half) {
+            uint32_t mag = (1u << c) - raw;  // digit = raw - 2^c  (negative, |d| < 2^(c-1)); raw == 2^c -> 0
+            carry = 1;
+            if (mag) out = mag | 0x80000000u;
+        } else {
+            carry = 0;
+            out = raw;
+        }
+        dig[(size_t)w * n + i] = out;
+        if (out) atomicAdd(&counts[(out & 0x7fffffffu) - 1], 1u);
+    }
+}
+
+__global__ void k_scan_tile_sums(const uint32_t* __restrict__ counts, uint32_t K, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint32_t idx = base + k;
+        s += (idx < K) ? counts[idx] : 0u;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int wi = 0; wi < SCAN_THREADS / 32; wi++) t += warp_tot[wi];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of up to 8192 tile sums in one block of 1024 threads (8 items per thread)
+__global__ void k_scan_tiles(uint32_t* tile_sums, uint32_t num_tiles) {
+    __shared__ uint32_t sh[1024];
+    uint32_t v[8];
+    uint32_t base = threadIdx.x * 8;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = (base + k < num_tiles) ? tile_sums[base + k] : 0u;
+        s += v[k];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t excl = sh[threadIdx.x] - s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (base + k < num_tiles) tile_sums[base + k] = excl;
+        excl += v[k];
+    }
+}
+
+// offsets[i] = exclusive prefix of counts; cursor[i] = offsets[i]; offsets[K] = total
+__global__ void k_scan_apply(const uint32_t* __restrict__ counts, uint32_t K, const uint32_t* __restrict__ tile_excl,
+                             uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t sh[SCAN_THREADS];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint32_t idx = base + k;
+        v[k] = (idx < K) ? counts[idx] : 0u;
+        s += v[k];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < SCAN_THREADS; d <<= 1) {
+        uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t run = tile_excl[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint32_t idx = base + k;
+        if (idx < K) {
+            offsets[idx] = run;
+            cursor[idx] = run;
+        }
+        run += v[k];
+        if (idx == K - 1) offsets[K] = run;
+    }
+}
+
+// entry (bucket key, table index | sign<<31) placed at its bucket's next free slot
+__global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t n_ck, int W, uint32_t* __restrict__ cursor,
+                          uint32_t* __restrict__ ekey, uint32_t* __restrict__ eidx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < W; w++) {
+        uint32_t d = dig[(size_t)w * n + i];
+        if (d) {
+            uint32_t b = (d & 0x7fffffffu) - 1;
+            uint32_t pos = atomicAdd(&cursor[b], 1u);
+            ekey[pos] = b;
+            eidx[pos] = ((uint32_t)w * n_ck + i) | (d & 0x80000000u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bucket sums
+// ------------------------------------------------------------------------------------------------
+// Thread t owns sorted entries [t*LS, (t+1)*LS).  A bucket lying entirely inside the chunk is written to
+// buckets[]; a piece of a bucket that continues into a neighbouring chunk goes to PH[t] (piece starts at the
+// chunk start) or PT[t] (piece ends at the chunk end) and is finished by k_fixup.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ ekey, const uint32_t* __restrict__ eidx,
+             const uint32_t* __restrict__ offsets, uint32_t K, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ PH,
+             XYZZ<F>* __restrict__ PT) {
+    const uint32_t M = offsets[K];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t start64 = (uint64_t)t * LS;
+    if (start64 >= M) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (M - start < (uint32_t)LS) ? M : start + LS;
+
+    uint32_t cur = ekey[start];
+    uint32_t seg_start = start;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    uint32_t e = eidx[start];
+    Affine<F> base = load_vec_nc(table + (e & 0x7fffffffu));
+    for (uint32_t pos = start; pos < end; pos++) {
+        // prefetch the next entry's base while this one is being added
+        uint32_t k_next = cur, e_next = 0;
+        Affine<F> base_next;
+        if (pos + 1 < end) {
+            k_next = ekey[pos + 1];
+            e_next = eidx[pos + 1];
+            base_next = load_vec_nc(table + (e_next & 0x7fffffffu));
+        }
+        xyzz_madd(acc, base, (e >> 31) != 0);
+        if (pos + 1 == end || k_next != cur) {
+            const uint32_t seg_end = pos + 1;
+            const uint32_t o = offsets[cur], o2 = offsets[cur + 1];
+            if (o == seg_start && o2 == seg_end) store_vec(buckets + cur, acc);
+            else if (seg_start == start) store_vec(PH + t, acc);
+            else store_vec(PT + t, acc);
+            acc = XYZZ<F>::identity();
+            seg_start = seg_end;
+            cur = k_next;
+        }
+        e = e_next;
+        base = base_next;
+    }
+}
+
+// One lane per bucket: empty buckets are set to the identity, buckets split over several chunks are summed
+// from their pieces.  Buckets with more than FIX_SMALL pieces (skewed scalars: many equal digits) are summed
+// by the whole warp, lanes striding over the pieces, then a shuffle tree.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_fixup(const uint32_t* __restrict__ offsets, uint32_t K, XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ PH,
+        const XYZZ<F>* __restrict__ PT) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t o = 0, o2 = 0, t0 = 0, np = 0;
+    if (b < K) {
+        o = offsets[b];
+        o2 = offsets[b + 1];
+        if (o2 > o) {
+            t0 = o / LS;
+            np = (o2 - 1) / LS - t0 + 1;
+        }
+    }
+    if (b < K) {
+        if (np == 0) {
+            store_vec(buckets + b, XYZZ<F>::identity());
+        } else if (np >= 2 && np <= (uint32_t)FIX_SMALL) {
+            XYZZ<F> acc = (o % LS == 0) ? load_vec(PH + t0) : load_vec(PT + t0);
+            for (uint32_t p = 1; p < np; p++) {
+                XYZZ<F> q = load_vec(PH + t0 + p);
+                xyzz_add(acc, q);
+            }
+            store_vec(buckets + b, acc);
+        }
+    }
+    uint32_t heavy = __ballot_sync(0xffffffffu, b < K && np > (uint32_t)FIX_SMALL);
+    while (heavy) {
+        const int src = __ffs(heavy) - 1;
+        heavy &= heavy - 1;
+        const uint32_t h_o = __shfl_sync(0xffffffffu, o, src);
+        const uint32_t h_t0 = __shfl_sync(0xffffffffu, t0, src);
+        const uint32_t h_np = __shfl_sync(0xffffffffu, np, src);
+        XYZZ<F> acc = XYZZ<F>::identity();
+        for (uint32_t p = lane; p < h_np; p += 32) {
+            XYZZ<F> q = (p == 0 && (h_o % LS != 0)) ? load_vec(PT + h_t0) : load_vec(PH + h_t0 + p);
+            xyzz_add(acc, q);
+        }
+        acc = warp_sum(acc);
+        if (lane == src) store_vec(buckets + b, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sum_b (b+1) B_b : warp-shuffle suffix-scan tree
+// ------------------------------------------------------------------------------------------------
+// A warp turns 32 children (S_j, Wt_j), each covering `child_len` consecutive buckets, into their parent:
+//   S = sum_j S_j,   Wt = sum_j Wt_j + child_len * sum_j j*S_j,   sum_j j*S_j = sum_{j>=1} Suffix_j.
+template <class F>
+SB_D void warp_combine(XYZZ<F> S, XYZZ<F> Wt, int log_child_len, int lane, XYZZ<F>& outS, XYZZ<F>& outWt) {
+    XYZZ<F> sumW = warp_sum(Wt);
+    XYZZ<F> suf = S;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        XYZZ<F> t = shfl_down_point(suf, d);
+        if (lane + d < 32) xyzz_add(suf, t);
+    }
+    outS = shfl_point(suf, 0);
+    XYZZ<F> js = (lane >= 1) ? suf : XYZZ<F>::identity();
+    js = warp_sum(js);
+    for (int k = 0; k < log_child_len; k++) js = xyzz_double(js);
+    xyzz_add(sumW, js);
+    outWt = sumW;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce_level0(const XYZZ<F>* __restrict__ buckets, uint32_t K, Node<F>* __restrict__ out, uint32_t num_out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
+    const uint64_t first = (uint64_t)g * RED_L0;
+#pragma unroll 1
+    for (int j = RED_L0 - 1; j >= 0; j--) {
+        uint64_t b = first + j;
+        if (b < K) {
+            XYZZ<F> q = load_vec(buckets + b);
+            xyzz_add(run, q);
+        }
+        xyzz_add(acc, run);
+    }
+    XYZZ<F> S, Wt;
+    int log_l0 = 0;
+    while ((1 << log_l0) < RED_L0) log_l0++;
+    warp_combine(run, acc, log_l0, lane, S, Wt);
+    if (lane == 0 && (g >> 5) < num_out) {
+        Node<F>* o = out + (g >> 5);
+        store_vec(&o->S, S);
+        store_vec(&o->Wt, Wt);
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce_level(const Node<F>* __restrict__ in, uint32_t count, int log_child_len, Node<F>* __restrict__ out, uint32_t num_out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    XYZZ<F> s = XYZZ<F>::identity(), w = XYZZ<F>::identity();
+    if (g < count) {
+        s = load_vec(&in[g].S);
+        w = load_vec(&in[g].Wt);
+    }
+    XYZZ<F> S, Wt;
+    warp_combine(s, w, log_child_len, lane, S, Wt);
+    if (lane == 0 && (g >> 5) < num_out) {
+        Node<F>* o = out + (g >> 5);
+        store_vec(&o->S, S);
+        store_vec(&o->Wt, Wt);
+    }
+}
+
+template <class F>
+__global__ void k_finalize(const Node<F>* __restrict__ root, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> r = load_vec(&root->Wt);
+    if (out_xyzz) store_vec(out_xyzz, r);
+    if (out_xy) store_vec(out_xy, xyzz_to_affine(r));
+}
+
+template <class F>
+__global__ void k_identity_out(Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (out_xyzz) store_vec(out_xyzz, XYZZ<F>::identity());
+    if (out_xy) {
+        Affine<F> z;
+        z.x = F::zero();
+        z.y = F::zero();
+        store_vec(out_xy, z);
+    }
+}
+
+template <class F>
+__global__ void k_combine(const XYZZ<F>* __restrict__ parts, int count, Affine<F>* out_xy) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (int i = 0; i < count; i++) {
+        XYZZ<F> q = load_vec(parts + i);
+        xyzz_add(acc, q);
+    }
+    store_vec(out_xy, xyzz_to_affine(acc));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+}  // namespace sb
+
+struct sb_ck {
+    int curve;
+    size_t n;
+    int c, W;
+    uint32_t K;
+    void* table;  // Affine[W][n]
+};
+
+namespace sb {
+
+static Scratch g_ws;
+
+static int default_window_bits(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    int c = lg - 5;
+    if (c < 8) c = 8;
+    if (c > 20) c = 20;
+    return c;
+}
+
+struct MsmPlan {
+    size_t n, nW, chunks;
+    uint32_t K, tiles, nodes0;
+    size_t off_dig, off_counts, off_offsets, off_cursor, off_tiles, off_ekey, off_eidx, off_buckets, off_ph, off_pt,
+        off_nodes_a, off_nodes_b, off_out_xy, off_out_xyzz, off_scalars, total;
+};
+
+static MsmPlan make_plan(const sb_ck* ck, size_t n, bool stage_scalars) {
+    MsmPlan p{};
+    p.n = n;
+    p.nW = n * (size_t)ck->W;
+    p.chunks = (p.nW + LS - 1) / LS;
+    p.K = ck->K;
+    p.tiles = (p.K + SCAN_TILE - 1) / SCAN_TILE;
+    p.nodes0 = (p.K + 32 * RED_L0 - 1) / (32 * RED_L0);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    p.off_dig = take(p.nW * 4);
+    p.off_counts = take((size_t)p.K * 4);
+    p.off_offsets = take(((size_t)p.K + 1) * 4);
+    p.off_cursor = take((size_t)p.K * 4);
+    p.off_tiles = take(8192 * 4);
+    p.off_ekey = take(p.nW * 4);
+    p.off_eidx = take(p.nW * 4);
+    p.off_buckets = take((size_t)p.K * 128);
+    p.off_ph = take(p.chunks * 128);
+    p.off_pt = take(p.chunks * 128);
+    p.off_nodes_a = take((size_t)p.nodes0 * 256);
+    p.off_nodes_b = take(((size_t)p.nodes0 / 32 + 1) * 256);
+    p.off_out_xy = take(64);
+    p.off_out_xyzz = take(128);
+    p.off_scalars = take(stage_scalars ? n * 32 : 0);
+    p.total = off;
+    return p;
+}
+
+template <class F, class S>
+static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, void* d_out_xy, void* d_out_xyzz,
+                       cudaStream_t st) {
+    const uint32_t n = (uint32_t)p.n;
+    auto* dig = (uint32_t*)(ws + p.off_dig);
+    auto* counts = (uint32_t*)(ws + p.off_counts);
+    auto* offsets = (uint32_t*)(ws + p.off_offsets);
+    auto* cursor = (uint32_t*)(ws + p.off_cursor);
+    auto* tiles = (uint32_t*)(ws + p.off_tiles);
+    auto* ekey = (uint32_t*)(ws + p.off_ekey);
+    auto* eidx = (uint32_t*)(ws + p.off_eidx);
+    auto* buckets = (XYZZ<F>*)(ws + p.off_buckets);
+    auto* PH = (XYZZ<F>*)(ws + p.off_ph);
+    auto* PT = (XYZZ<F>*)(ws + p.off_pt);
+    auto* nodes_a = (Node<F>*)(ws + p.off_nodes_a);
+    auto* nodes_b = (Node<F>*)(ws + p.off_nodes_b);
+    const uint32_t K = p.K;
+
+    SB_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)K * 4, st));
+    k_decompose<S><<<(n + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, ck->c, ck->W, dig, counts);
+    SB_KERNEL_CHECK();
+    k_scan_tile_sums<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, K, tiles);
+    SB_KERNEL_CHECK();
+    k_scan_tiles<<<1, 1024, 0, st>>>(tiles, p.tiles);
+    SB_KERNEL_CHECK();
+    k_scan_apply<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, K, tiles, offsets, cursor);
+    SB_KERNEL_CHECK();
+    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(dig, n, (uint32_t)ck->n, ck->W, cursor, ekey, eidx);
+    SB_KERNEL_CHECK();
+    {
+        size_t blocks = (p.chunks + 127) / 128;
+        k_accumulate<F><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, K, buckets, PH, PT);
+        SB_KERNEL_CHECK();
+    }
+    k_fixup<F><<<(K + 127) / 128, 128, 0, st>>>(offsets, K, buckets, PH, PT);
+    SB_KERNEL_CHECK();
+    {
+        uint32_t lanes = (K + RED_L0 - 1) / RED_L0;
+        lanes = (lanes + 31) / 32 * 32;
+        k_reduce_level0<F><<<(lanes + 127) / 128, 128, 0, st>>>(buckets, K, nodes_a, p.nodes0);
+        SB_KERNEL_CHECK();
+    }
+    uint32_t count = p.nodes0;
+    int log_len = 5;
+    for (int l = RED_L0; l > 1; l >>= 1) log_len++;
+    Node<F>*cur = nodes_a, *nxt = nodes_b;
+    while (count > 1) {
+        uint32_t lanes = (count + 31) / 32 * 32;
+        k_reduce_level<F><<<(lanes + 127) / 128, 128, 0, st>>>(cur, count, log_len, nxt, (count + 31) / 32);
+        SB_KERNEL_CHECK();
+        count = (count + 31) / 32;
+        log_len += 5;
+        std::swap(cur, nxt);
+    }
+    k_finalize<F><<<1, 32, 0, st>>>(cur, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+static int msm_dispatch(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, void* d_out_xy, void* d_out_xyzz,
+                        cudaStream_t st) {
+    if (p.n == 0) {
+        if (ck->curve == CURVE_BN256) k_identity_out<Fq><<<1, 32, 0, st>>>((Affine<Fq>*)d_out_xy, (XYZZ<Fq>*)d_out_xyzz);
+        else k_identity_out<Fr><<<1, 32, 0, st>>>((Affine<Fr>*)d_out_xy, (XYZZ<Fr>*)d_out_xyzz);
+        SB_KERNEL_CHECK();
+        return SB_OK;
+    }
+    if (ck->curve == CURVE_BN256) return msm_enqueue<Fq, Fr>(ck, p, ws, d_scalars, d_out_xy, d_out_xyzz, st);
+    return msm_enqueue<Fr, Fq>(ck, p, ws, d_scalars, d_out_xy, d_out_xyzz, st);
+}
+
+static int ck_build(int curve, const void* d_bases, size_t n, int window_bits, cudaStream_t st, sb_ck_t* out) {
+    if (curve != CURVE_BN256 && curve != CURVE_GRUMPKIN) {
+        set_error("sb_ck_register: unknown curve %d", curve);
+        return SB_ERR_ARG;
+    }
+    int c = window_bits > 0 ? window_bits : default_window_bits(n);
+    if (c < 2 || c > 24) {
+        set_error("sb_ck_register: window_bits %d out of range [2,24]", c);
+        return SB_ERR_ARG;
+    }
+    int W = 254 / c + 1;
+    if ((uint64_t)n * (uint64_t)W >= (1ull << 31)) {
+        set_error("sb_ck_register: n*W = %zu*%d does not fit the 31-bit table index", n, W);
+        return SB_ERR_ARG;
+    }
+    sb_ck* ck = new (std::nothrow) sb_ck();
+    if (!ck) return SB_ERR_OOM;
+    ck->curve = curve;
+    ck->n = n;
+    ck->c = c;
+    ck->W = W;
+    ck->K = 1u << (c - 1);
+    ck->table = nullptr;
+    if (n) {
+        cudaError_t e = cudaMalloc(&ck->table, n * (size_t)W * 64);
+        if (e != cudaSuccess) {
+            set_error("sb_ck_register: cudaMalloc(%zu) failed: %s", n * (size_t)W * 64, cudaGetErrorString(e));
+            delete ck;
+            return SB_ERR_OOM;
+        }
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        if (curve == CURVE_BN256) k_precompute<Fq><<<blocks, 128, 0, st>>>((const Affine<Fq>*)d_bases, n, c, W, (Affine<Fq>*)ck->table);
+        else k_precompute<Fr><<<blocks, 128, 0, st>>>((const Affine<Fr>*)d_bases, n, c, W, (Affine<Fr>*)ck->table);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+        if (e2 != cudaSuccess) {
+            set_error("sb_ck_register: precompute failed: %s", cudaGetErrorString(e2));
+            cudaFree(ck->table);
+            delete ck;
+            return SB_ERR_CUDA;
+        }
+    }
+    *out = ck;
+    return SB_OK;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int sb_ck_register(int curve, const uint64_t* bases_xy, size_t n, int window_bits, sb_ck_t* out) {
+    if (!out || (!bases_xy && n)) {
+        set_error("sb_ck_register: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    void* d_bases = nullptr;
+    if (n) {
+        SB_CUDA_TRY(cudaMalloc(&d_bases, n * 64));
+        cudaError_t e = cudaMemcpyAsync(d_bases, bases_xy, n * 64, cudaMemcpyHostToDevice, rt.stream);
+        if (e != cudaSuccess) {
+            cudaFree(d_bases);
+            set_error("sb_ck_register: H2D failed: %s", cudaGetErrorString(e));
+            return SB_ERR_CUDA;
+        }
+    }
+    int rc = ck_build(curve, d_bases, n, window_bits, rt.stream, out);
+    if (d_bases) cudaFree(d_bases);
+    return rc;
+}
+
+int sb_ck_register_device(int curve, const void* d_bases_xy, size_t n, int window_bits, void* stream, sb_ck_t* out) {
+    if (!out || (!d_bases_xy && n)) {
+        set_error("sb_ck_register_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    return ck_build(curve, d_bases_xy, n, window_bits, stream ? (cudaStream_t)stream : rt.stream, out);
+}
+
+void sb_ck_release(sb_ck_t ck) {
+    if (!ck) return;
+    if (ck->table) cudaFree(ck->table);
+    delete ck;
+}
+
+size_t sb_ck_len(sb_ck_t ck) { return ck ? ck->n : 0; }
+int sb_ck_window_bits(sb_ck_t ck) { return ck ? ck->c : 0; }
+
+int sb_msm_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, void* d_out_xy, void* d_out_xyzz, void* stream) {
+    if (!ck || (!d_scalars_mont && n) || (!d_out_xy && !d_out_xyzz)) {
+        set_error("sb_msm_device: null argument");
+        return SB_ERR_ARG;
+    }
+    if (n > ck->n) {
+        set_error("Can't commit too long input: input len: %zu, but limit is %zu", n, ck->n);
+        return SB_ERR_TOO_LONG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    MsmPlan p = make_plan(ck, n, false);
+    SB_TRY(g_ws.reserve(p.total));
+    return msm_dispatch(ck, p, (char*)g_ws.ptr, d_scalars_mont, d_out_xy, d_out_xyzz, stream ? (cudaStream_t)stream : rt.stream);
+}
+
+int sb_msm(sb_ck_t ck, const uint64_t* scalars_mont, size_t n, uint64_t out_xy[8]) {
+    if (!ck || (!scalars_mont && n) || !out_xy) {
+        set_error("sb_msm: null argument");
+        return SB_ERR_ARG;
+    }
+    if (n > ck->n) {
+        set_error("Can't commit too long input: input len: %zu, but limit is %zu", n, ck->n);
+        return SB_ERR_TOO_LONG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    MsmPlan p = make_plan(ck, n, true);
+    SB_TRY(g_ws.reserve(p.total));
+    char* ws = (char*)g_ws.ptr;
+    if (n) SB_CUDA_TRY(cudaMemcpyAsync(ws + p.off_scalars, scalars_mont, n * 32, cudaMemcpyHostToDevice, rt.stream));
+    SB_TRY(msm_dispatch(ck, p, ws, ws + p.off_scalars, ws + p.off_out_xy, nullptr, rt.stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(out_xy, ws + p.off_out_xy, 64, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
+}
+
+int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, void* d_out_xy, void* stream) {
+    if (!d_partials_xyzz || !d_out_xy || count < 0) {
+        set_error("sb_msm_combine_device: bad argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    if (curve == CURVE_BN256) k_combine<Fq><<<1, 32, 0, st>>>((const XYZZ<Fq>*)d_partials_xyzz, count, (Affine<Fq>*)d_out_xy);
+    else if (curve == CURVE_GRUMPKIN) k_combine<Fr><<<1, 32, 0, st>>>((const XYZZ<Fr>*)d_partials_xyzz, count, (Affine<Fr>*)d_out_xy);
+    else {
+        set_error("sb_msm_combine_device: unknown curve %d", curve);
+        return SB_ERR_ARG;
+    }
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// runtime.cu -- device selection, error strings, scratch memory, and the on-device arithmetic self test.
+#include <string.h>
+
+#include "common.cuh"
+#include "curve.cuh"
+
+namespace sb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+Runtime& runtime() {
+    static Runtime rt;
+    return rt;
+}
+
+static int init_locked(Runtime& rt, int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s): libsirius_b200 has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+        return SB_ERR_CUDA;
+    }
+    if (device >= 0) {
+        SB_CUDA_TRY(cudaSetDevice(device));
+    }
+    int cur = 0;
+    SB_CUDA_TRY(cudaGetDevice(&cur));
+    if (rt.ready && rt.device == cur) return SB_OK;
+    cudaDeviceProp prop;
+    SB_CUDA_TRY(cudaGetDeviceProperties(&prop, cur));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", cur, prop.major, prop.minor);
+        return SB_ERR_CUDA;
+    }
+    if (rt.stream) cudaStreamDestroy(rt.stream);
+    SB_CUDA_TRY(cudaStreamCreateWithFlags(&rt.stream, cudaStreamNonBlocking));
+    rt.device = cur;
+    rt.sm_count = prop.multiProcessorCount;
+    rt.ready = true;
+    return SB_OK;
+}
+
+int ensure_runtime() {
+    Runtime& rt = runtime();
+    if (rt.ready) {
+        // calls may come from any host thread (cargo test): bind the thread to the library's device
+        cudaError_t e = cudaSetDevice(rt.device);
+        if (e != cudaSuccess) {
+            set_error("cudaSetDevice(%d): %s", rt.device, cudaGetErrorString(e));
+            return SB_ERR_CUDA;
+        }
+        return SB_OK;
+    }
+    std::lock_guard<std::mutex> lk(rt.mu);
+    return init_locked(rt, -1);
+}
+
+int Scratch::reserve(size_t bytes) {
+    if (bytes <= cap) return SB_OK;
+    Runtime& rt = runtime();
+    if (ptr) {
+        cudaStreamSynchronize(rt.stream);
+        cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&ptr, want);
+    }
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        set_error("workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return SB_ERR_OOM;
+    }
+    cap = want;
+    return SB_OK;
+}
+
+void Scratch::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void k_selftest_field(const F* a, const F* b, size_t n, F* o_ptx, F* o_port, F* o_add, F* o_sub, F* o_inv) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i], y = b[i];
+    o_ptx[i] = mul(x, y);
+    o_port[i] = mul_portable(x, y);
+    o_add[i] = add(x, y);
+    o_sub[i] = sub(x, y);
+    o_inv[i] = x.is_zero() ? x : inv(x);
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+const char* sb_last_error(void) { return g_err; }
+int sb_version(void) { return 1; }
+
+int sb_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+int sb_init(int device) {
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    return init_locked(rt, device);
+}
+
+void sb_shutdown(void) {
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    if (rt.stream) {
+        cudaStreamSynchronize(rt.stream);
+        cudaStreamDestroy(rt.stream);
+        rt.stream = nullptr;
+    }
+    rt.ready = false;
+}
+
+int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul_ptx, uint64_t* out_mul_portable,
+                      uint64_t* out_add, uint64_t* out_sub, uint64_t* out_inv) {
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    char* d = nullptr;
+    size_t bytes = n * 32;
+    SB_CUDA_TRY(cudaMalloc(&d, bytes * 7));
+    int rc = SB_OK;
+    do {
+        if (cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, rt.stream) != cudaSuccess ||
+            cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, rt.stream) != cudaSuccess) {
+            set_error("selftest H2D failed");
+            rc = SB_ERR_CUDA;
+            break;
+        }
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        if (field == FIELD_FR)
+            k_selftest_field<Fr><<<blocks, 128, 0, rt.stream>>>((const Fr*)d, (const Fr*)(d + bytes), n, (Fr*)(d + 2 * bytes), (Fr*)(d + 3 * bytes),
+                                                               (Fr*)(d + 4 * bytes), (Fr*)(d + 5 * bytes), (Fr*)(d + 6 * bytes));
+        else
+            k_selftest_field<Fq><<<blocks, 128, 0, rt.stream>>>((const Fq*)d, (const Fq*)(d + bytes), n, (Fq*)(d + 2 * bytes), (Fq*)(d + 3 * bytes),
+                                                               (Fq*)(d + 4 * bytes), (Fq*)(d + 5 * bytes), (Fq*)(d + 6 * bytes));
+        cudaError_t e = cudaGetLastError();
+        uint64_t* outs[5] = {out_mul_ptx, out_mul_portable, out_add, out_sub, out_inv};
+        for (int k = 0; k < 5 && e == cudaSuccess; k++) e = cudaMemcpyAsync(outs[k], d + (2 + k) * bytes, bytes, cudaMemcpyDeviceToHost, rt.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
+        if (e != cudaSuccess) {
+            set_error("selftest failed: %s", cudaGetErrorString(e));
+            rc = SB_ERR_CUDA;
+        }
+    } while (0);
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

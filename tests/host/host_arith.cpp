@@ -1,0 +1,50 @@
+// Host build of the PORTABLE code paths in sirius_b200/csrc/{field,curve}.cuh, so the formulas the CUDA
+// kernels use can be checked against the oracle on a machine without a GPU (pytest -m "not gpu").
+#include <cstddef>
+#include <cstring>
+#include "../../sirius_b200/csrc/curve.cuh"
+
+using namespace sb;
+
+template <class F>
+static void t_mul(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
+    const F* A = (const F*)a; const F* B = (const F*)b; F* O = (F*)o;
+    for (size_t i = 0; i < n; i++) O[i] = mul(A[i], B[i]);
+}
+template <class F>
+static void t_addsub(const uint64_t* a, const uint64_t* b, uint64_t* o_add, uint64_t* o_sub, size_t n) {
+    const F* A = (const F*)a; const F* B = (const F*)b;
+    for (size_t i = 0; i < n; i++) { ((F*)o_add)[i] = add(A[i], B[i]); ((F*)o_sub)[i] = sub(A[i], B[i]); }
+}
+template <class F>
+static void t_inv(const uint64_t* a, uint64_t* o, size_t n) {
+    for (size_t i = 0; i < n; i++) ((F*)o)[i] = inv(((const F*)a)[i]);
+}
+// sum_i (+/-) P_i with madd, then tree-combine two halves with xyzz_add, double once, -> affine
+template <class F>
+static void t_points(const uint64_t* pts, const uint8_t* negs, size_t n, uint64_t* out_sum, uint64_t* out_dbl) {
+    const Affine<F>* P = (const Affine<F>*)pts;
+    XYZZ<F> lo = XYZZ<F>::identity(), hi = XYZZ<F>::identity();
+    for (size_t i = 0; i < n / 2; i++) xyzz_madd(lo, P[i], negs[i] != 0);
+    for (size_t i = n / 2; i < n; i++) xyzz_madd(hi, P[i], negs[i] != 0);
+    xyzz_add(lo, hi);
+    Affine<F> s = xyzz_to_affine(lo);
+    memcpy(out_sum, &s, 64);
+    Affine<F> d = xyzz_to_affine(xyzz_double(lo));
+    memcpy(out_dbl, &d, 64);
+}
+
+extern "C" {
+void ha_mul(int field, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
+    if (field == FIELD_FR) t_mul<Fr>(a, b, o, n); else t_mul<Fq>(a, b, o, n);
+}
+void ha_addsub(int field, const uint64_t* a, const uint64_t* b, uint64_t* oa, uint64_t* os, size_t n) {
+    if (field == FIELD_FR) t_addsub<Fr>(a, b, oa, os, n); else t_addsub<Fq>(a, b, oa, os, n);
+}
+void ha_inv(int field, const uint64_t* a, uint64_t* o, size_t n) {
+    if (field == FIELD_FR) t_inv<Fr>(a, o, n); else t_inv<Fq>(a, o, n);
+}
+void ha_points(int curve, const uint64_t* pts, const uint8_t* negs, size_t n, uint64_t* out_sum, uint64_t* out_dbl) {
+    if (curve == CURVE_BN256) t_points<Fq>(pts, negs, n, out_sum, out_dbl); else t_points<Fr>(pts, negs, n, out_sum, out_dbl);
+}
+}
