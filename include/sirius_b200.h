@@ -68,6 +68,20 @@ int sb_msm_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, void* d_out_
 /* Multi-GPU combine: sum `count` XYZZ partials (device, 128 B each) and normalise to affine. */
 int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, void* d_out_xy, void* stream);
 
+/* ---- fft (src/fft.rs) ------------------------------------------------------------------------------ */
+
+/* best_fft (src/fft.rs:61-115): in-place radix-2 transform of n = 2^log_n elements, natural order in and
+ * out, out[i] = sum_j a[j] * omega^(i*j).  `omega` (order n) comes from the Rust constants via
+ * get_omega_or_inv (src/fft.rs:12-23), so no root of unity is hard-coded here.  If `scale` is non-NULL every
+ * output is multiplied by it (the ifft divisor TWO_INV^k, src/fft.rs:25-27,177-181).  field must be SB_FIELD_FR
+ * (Fq has 2-adicity 1). */
+int sb_ntt(int field, uint64_t* a, uint32_t log_n, const uint64_t omega[4], const uint64_t* scale);
+int sb_ntt_device(int field, void* d_a, uint32_t log_n, const uint64_t omega[4], const uint64_t* scale, void* stream);
+/* distribute_powers_zeta (src/fft.rs:207-228): a[i] *= z if i%3==1, a[i] *= z2 if i%3==2.
+ * coset_fft passes (ZETA, ZETA^2), coset_ifft passes (ZETA^2, ZETA). */
+int sb_coset_scale(int field, uint64_t* a, size_t n, const uint64_t z[4], const uint64_t z2[4]);
+int sb_coset_scale_device(int field, void* d_a, size_t n, const uint64_t z[4], const uint64_t z2[4], void* stream);
+
 /* ---- self test hooks used by tests/ (device arithmetic vs its portable twin) ----------------------- */
 int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul_ptx,
                       uint64_t* out_mul_portable, uint64_t* out_add, uint64_t* out_sub, uint64_t* out_inv);

@@ -25,16 +25,17 @@ for lg in sizes:
         ck = sirius_b200.CommitmentKey.from_device(curve, d_b.data_ptr(), n, window_bits=c)
         torch.cuda.synchronize()
         treg = time.time() - t0
-        st = torch.cuda.current_stream().cuda_stream
+        ts = torch.cuda.Stream()
+        st = ts.cuda_stream
         for _ in range(2):
             ck.commit_device(d_s.data_ptr(), n, out.data_ptr(), 0, st)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 5
-        e0.record()
+        e0.record(ts)
         for _ in range(reps):
             ck.commit_device(d_s.data_ptr(), n, out.data_ptr(), 0, st)
-        e1.record()
+        e1.record(ts)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         print(f"n=2^{lg} c={ck.window_bits} register={treg:.2f}s msm={ms:.3f} ms  {n/ms/1e3:.1f} Mscalar/s", flush=True)
