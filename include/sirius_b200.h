@@ -65,6 +65,12 @@ int sb_msm(sb_ck_t ck, const uint64_t* scalars_mont, size_t n, uint64_t out_xy[8
 /* Device-resident scalars; result written to d_out (64 B device affine, and 128 B XYZZ to d_out_xyzz if
  * non-NULL -- the un-normalised partial sum used by the multi-GPU gather). */
 int sb_msm_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, void* d_out_xy, void* d_out_xyzz, void* stream);
+/* `batch` commitments against the same key in one pipeline (the d cross-term commits of one
+ * commit_cross_terms call, src/nifs/sangria/mod.rs:151-154, are independent of each other): vector b is
+ * scalars[b][0..n) on the host, or d_scalars + b*stride elements on the device; out gets batch points. */
+int sb_msm_batch(sb_ck_t ck, const uint64_t* const* scalars_mont, size_t n, size_t batch, uint64_t* out_xy);
+int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t stride, size_t batch, void* d_out_xy,
+                        void* d_out_xyzz, void* stream);
 /* Multi-GPU combine: sum `count` XYZZ partials (device, 128 B each) and normalise to affine. */
 int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, void* d_out_xy, void* stream);
 

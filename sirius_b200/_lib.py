@@ -37,6 +37,8 @@ SIGNATURES = {
     "sb_ck_window_bits": (ctypes.c_int, [vp]),
     "sb_msm": (ctypes.c_int, [vp, u64p, ctypes.c_size_t, u64p]),
     "sb_msm_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, vp, vp, vp]),
+    "sb_msm_batch": (ctypes.c_int, [vp, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p]),
+    "sb_msm_batch_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp]),
     "sb_msm_combine_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
     "sb_ntt": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint32, u64p, u64p]),
     "sb_ntt_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint32, u64p, u64p, vp]),

@@ -77,6 +77,28 @@ class CommitmentKey:
         _lib.check(rc)
         return out
 
+    def commit_batch(self, vs) -> np.ndarray:
+        """[commit(v) for v in vs] in one device pipeline (all vectors the same length) -> uint64 [len(vs), 8]."""
+        arrs = [_as_u64(v, 4) for v in vs]
+        if not arrs:
+            return np.zeros((0, 8), dtype=np.uint64)
+        n = arrs[0].shape[0]
+        assert all(a.shape[0] == n for a in arrs), "commit_batch: vectors must have equal length"
+        if n > self.len():
+            raise TooLongInput(n, self.len())
+        ptrs = (_lib.u64p * len(arrs))(*[a.ctypes.data_as(_lib.u64p) for a in arrs])
+        out = np.zeros((len(arrs), 8), dtype=np.uint64)
+        _lib.check(_lib.load().sb_msm_batch(self._h, ptrs, n, len(arrs), out.ctypes.data_as(_lib.u64p)))
+        return out
+
+    def commit_batch_device(self, d_scalars: int, n: int, stride: int, batch: int, d_out_xy: int = 0, d_out_xyzz: int = 0, stream: int = 0) -> None:
+        if n > self.len():
+            raise TooLongInput(n, self.len())
+        rc = _lib.load().sb_msm_batch_device(
+            self._h, ctypes.c_void_p(d_scalars), n, stride, batch, ctypes.c_void_p(d_out_xy or None), ctypes.c_void_p(d_out_xyzz or None), ctypes.c_void_p(stream or None)
+        )
+        _lib.check(rc)
+
     def commit_device(self, d_scalars: int, n: int, d_out_xy: int = 0, d_out_xyzz: int = 0, stream: int = 0) -> None:
         """Scalars already in HBM; enqueues on `stream` and returns without synchronising."""
         if n > self.len():

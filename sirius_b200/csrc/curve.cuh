@@ -38,6 +38,23 @@ struct alignas(16) XYZZ {  // identity: zz == 0
     }
 };
 
+// The latency-bound kernels (bucket fix-up, reduction tree, finalisation) instantiate the group law with
+// INL = false: Montgomery products become calls to one out-of-line copy, which keeps those kernels' code
+// inside the instruction cache.  The accumulate kernel (throughput-bound) uses the fully inlined forms.
+#if defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ Fe<P> mul_outlined(Fe<P> a, Fe<P> b) { return mul(a, b); }
+#endif
+template <bool INL, class P>
+SB_HD Fe<P> mulx(const Fe<P>& a, const Fe<P>& b) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (INL) return mul(a, b);
+    else return mul_outlined(a, b);
+#else
+    return mul(a, b);
+#endif
+}
+
 // 2 * (affine p), p not the identity.  y = 0 cannot happen on a prime-order curve, but is handled.
 template <class F>
 SB_HD XYZZ<F> xyzz_double_affine(const F& px, const F& py) {
@@ -56,20 +73,20 @@ SB_HD XYZZ<F> xyzz_double_affine(const F& px, const F& py) {
     return r;
 }
 
-template <class F>
+template <bool INL = true, class F>
 SB_HD XYZZ<F> xyzz_double(const XYZZ<F>& p) {
     if (p.is_identity() || p.y.is_zero()) return XYZZ<F>::identity();
     XYZZ<F> r;
     F u = dbl(p.y);
-    F v = sqr(u);
-    F w = mul(u, v);
-    F s = mul(p.x, v);
-    F xx = sqr(p.x);
+    F v = mulx<INL>(u, u);
+    F w = mulx<INL>(u, v);
+    F s = mulx<INL>(p.x, v);
+    F xx = mulx<INL>(p.x, p.x);
     F m = add(dbl(xx), xx);
-    r.x = sub(sqr(m), dbl(s));
-    r.y = sub(mul(m, sub(s, r.x)), mul(w, p.y));
-    r.zz = mul(v, p.zz);
-    r.zzz = mul(w, p.zzz);
+    r.x = sub(mulx<INL>(m, m), dbl(s));
+    r.y = sub(mulx<INL>(m, sub(s, r.x)), mulx<INL>(w, p.y));
+    r.zz = mulx<INL>(v, p.zz);
+    r.zzz = mulx<INL>(w, p.zzz);
     return r;
 }
 
@@ -103,41 +120,41 @@ SB_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q, bool negate) {
 }
 
 // acc += q, both XYZZ.
-template <class F>
+template <bool INL = true, class F>
 SB_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
     if (q.is_identity()) return;
     if (acc.is_identity()) { acc = q; return; }
-    F u1 = mul(acc.x, q.zz);
-    F u2 = mul(q.x, acc.zz);
-    F s1 = mul(acc.y, q.zzz);
-    F s2 = mul(q.y, acc.zzz);
+    F u1 = mulx<INL>(acc.x, q.zz);
+    F u2 = mulx<INL>(q.x, acc.zz);
+    F s1 = mulx<INL>(acc.y, q.zzz);
+    F s2 = mulx<INL>(q.y, acc.zzz);
     F p = sub(u2, u1);
     F r = sub(s2, s1);
     if (p.is_zero()) {
-        if (r.is_zero()) acc = xyzz_double(acc);
+        if (r.is_zero()) acc = xyzz_double<INL>(acc);
         else acc = XYZZ<F>::identity();
         return;
     }
-    F pp = sqr(p);
-    F ppp = mul(p, pp);
-    F qq = mul(u1, pp);
-    F x3 = sub(sub(sqr(r), ppp), dbl(qq));
-    F y3 = sub(mul(r, sub(qq, x3)), mul(s1, ppp));
+    F pp = mulx<INL>(p, p);
+    F ppp = mulx<INL>(p, pp);
+    F qq = mulx<INL>(u1, pp);
+    F x3 = sub(sub(mulx<INL>(r, r), ppp), dbl(qq));
+    F y3 = sub(mulx<INL>(r, sub(qq, x3)), mulx<INL>(s1, ppp));
     acc.x = x3;
     acc.y = y3;
-    acc.zz = mul(mul(acc.zz, q.zz), pp);
-    acc.zzz = mul(mul(acc.zzz, q.zzz), ppp);
+    acc.zz = mulx<INL>(mulx<INL>(acc.zz, q.zz), pp);
+    acc.zzz = mulx<INL>(mulx<INL>(acc.zzz, q.zzz), ppp);
 }
 
-template <class F>
+template <bool INL = true, class F>
 SB_HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
     Affine<F> r;
     if (p.is_identity()) { r.x = F::zero(); r.y = F::zero(); return r; }
-    F i = inv(mul(p.zz, p.zzz));      // 1/(zz*zzz)
-    F izz = mul(i, p.zzz);            // 1/zz
-    F izzz = mul(i, p.zz);            // 1/zzz
-    r.x = mul(p.x, izz);
-    r.y = mul(p.y, izzz);
+    F i = inv_binary(mulx<INL>(p.zz, p.zzz));  // 1/(zz*zzz)
+    F izz = mulx<INL>(i, p.zzz);               // 1/zz
+    F izzz = mulx<INL>(i, p.zz);               // 1/zzz
+    r.x = mulx<INL>(p.x, izz);
+    r.y = mulx<INL>(p.y, izzz);
     return r;
 }
 

@@ -26,8 +26,10 @@
 
 namespace sb {
 
-constexpr int LS = 16;          // sorted entries per accumulate chunk (one thread each)
-constexpr int FIX_SMALL = 8;    // buckets split in <= FIX_SMALL pieces are summed by one lane
+constexpr int LS_MIN_LOG = 4;   // sorted entries per accumulate chunk (one thread each): 2^4 .. 2^8, chosen per call
+constexpr int LS_MAX_LOG = 8;
+constexpr int FIX_SEQ = 32;     // buckets split in <= FIX_SEQ pieces are summed by one thread, larger ones by a block
+constexpr int HEAVY_THREADS = 256;
 constexpr int RED_L0 = 4;       // buckets per lane at level 0 of the bucket reduction
 constexpr int SCAN_ITEMS = 16;  // items per thread in the scan kernels
 constexpr int SCAN_THREADS = 256;
@@ -106,7 +108,7 @@ SB_D XYZZ<F> warp_sum(XYZZ<F> v) {
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
         XYZZ<F> t = shfl_xor_point(v, d);
-        xyzz_add(v, t);
+        xyzz_add<false>(v, t);
     }
     return v;
 }
@@ -122,8 +124,8 @@ __global__ void k_precompute(const Affine<F>* __restrict__ bases, size_t n, int 
     store_vec(table + i, p);
     XYZZ<F> acc = XYZZ<F>::from_affine(p);
     for (int w = 1; w < W; w++) {
-        for (int j = 0; j < c; j++) acc = xyzz_double(acc);
-        Affine<F> q = xyzz_to_affine(acc);
+        for (int j = 0; j < c; j++) acc = xyzz_double<false>(acc);
+        Affine<F> q = xyzz_to_affine<false>(acc);
         store_vec(table + (size_t)w * n + i, q);
     }
 }
@@ -132,12 +134,16 @@ __global__ void k_precompute(const Affine<F>* __restrict__ bases, size_t n, int 
 // commit-time: digits, counting sort
 // ------------------------------------------------------------------------------------------------
 // dig[w*n + i] = 0 (digit 0) or ((|d|) | sign<<31) for the signed base-2^c digit d of scalar i, window w.
+// Batched: `total` = batch * n scalars (batch b = i / n shares the same key, its buckets are [b*K, (b+1)*K)),
+// the scalar vectors being `stride` elements apart.
 template <class S>
-__global__ void k_decompose(const S* __restrict__ scalars, uint32_t n, int c, int W, uint32_t* __restrict__ dig,
-                            uint32_t* __restrict__ counts) {
+__global__ void k_decompose(const S* __restrict__ scalars, uint32_t n, uint32_t total, size_t stride, uint32_t K, int c, int W,
+                            uint32_t* __restrict__ dig, uint32_t* __restrict__ counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    S s = from_mont(load_vec_nc(scalars + i));  // canonical integer, as `to_repr()` in halo2's multiexp
+    if (i >= total) return;
+    const uint32_t batch = i / n;
+    const uint32_t bucket_base = batch * K;
+    S s = from_mont(load_vec_nc(scalars + (size_t)batch * stride + (i - batch * n)));  // canonical integer (`to_repr()`)
     uint32_t limb[9];
 #pragma unroll
     for (int k = 0; k < 8; k++) limb[k] = s.v[k];
@@ -163,8 +169,8 @@ __global__ void k_decompose(const S* __restrict__ scalars, uint32_t n, int c, in
             carry = 0;
             out = raw;
         }
-        dig[(size_t)w * n + i] = out;
-        if (out) atomicAdd(&counts[(out & 0x7fffffffu) - 1], 1u);
+        dig[(size_t)w * total + i] = out;
+        if (out) atomicAdd(&counts[bucket_base + (out & 0x7fffffffu) - 1], 1u);
     }
 }
 
@@ -250,17 +256,19 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ counts, uint32_t K, co
 }
 
 // entry (bucket key, table index | sign<<31) placed at its bucket's next free slot
-__global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t n_ck, int W, uint32_t* __restrict__ cursor,
-                          uint32_t* __restrict__ ekey, uint32_t* __restrict__ eidx) {
+__global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t total, uint32_t K, uint32_t n_ck, int W,
+                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ ekey, uint32_t* __restrict__ eidx) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= total) return;
+    const uint32_t batch = i / n;
+    const uint32_t pt = i - batch * n;
     for (int w = 0; w < W; w++) {
-        uint32_t d = dig[(size_t)w * n + i];
+        uint32_t d = dig[(size_t)w * total + i];
         if (d) {
-            uint32_t b = (d & 0x7fffffffu) - 1;
+            uint32_t b = batch * K + (d & 0x7fffffffu) - 1;
             uint32_t pos = atomicAdd(&cursor[b], 1u);
             ekey[pos] = b;
-            eidx[pos] = ((uint32_t)w * n_ck + i) | (d & 0x80000000u);
+            eidx[pos] = ((uint32_t)w * n_ck + pt) | (d & 0x80000000u);
         }
     }
 }
@@ -268,26 +276,28 @@ __global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t
 // ------------------------------------------------------------------------------------------------
 // bucket sums
 // ------------------------------------------------------------------------------------------------
-// Thread t owns sorted entries [t*LS, (t+1)*LS).  A bucket lying entirely inside the chunk is written to
-// buckets[]; a piece of a bucket that continues into a neighbouring chunk goes to PH[t] (piece starts at the
-// chunk start) or PT[t] (piece ends at the chunk end) and is finished by k_fixup.
+// Thread t owns sorted entries [t*LS, (t+1)*LS), LS = 2^ls_log.  A bucket lying entirely inside the chunk is
+// written to buckets[]; a piece of a bucket that continues into a neighbouring chunk goes to PH[t] (piece
+// starts at the chunk start) or PT[t] (piece ends at the chunk end) and is finished by k_fixup.
 template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ ekey, const uint32_t* __restrict__ eidx,
-             const uint32_t* __restrict__ offsets, uint32_t K, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ PH,
-             XYZZ<F>* __restrict__ PT) {
-    const uint32_t M = offsets[K];
+             const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* __restrict__ buckets,
+             XYZZ<F>* __restrict__ PH, XYZZ<F>* __restrict__ PT) {
+    const uint32_t M = offsets[KB];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t start64 = (uint64_t)t * LS;
+    const uint64_t start64 = (uint64_t)t << ls_log;
     if (start64 >= M) return;
     const uint32_t start = (uint32_t)start64;
-    const uint32_t end = (M - start < (uint32_t)LS) ? M : start + LS;
+    const uint32_t LS = 1u << ls_log;
+    const uint32_t end = (M - start < LS) ? M : start + LS;
 
     uint32_t cur = ekey[start];
     uint32_t seg_start = start;
     XYZZ<F> acc = XYZZ<F>::identity();
     uint32_t e = eidx[start];
     Affine<F> base = load_vec_nc(table + (e & 0x7fffffffu));
+#pragma unroll 1
     for (uint32_t pos = start; pos < end; pos++) {
         // prefetch the next entry's base while this one is being added
         uint32_t k_next = cur, e_next = 0;
@@ -313,50 +323,67 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ e
     }
 }
 
-// One lane per bucket: empty buckets are set to the identity, buckets split over several chunks are summed
-// from their pieces.  Buckets with more than FIX_SMALL pieces (skewed scalars: many equal digits) are summed
-// by the whole warp, lanes striding over the pieces, then a shuffle tree.
+// One thread per bucket: empty buckets are set to the identity; a bucket split over 2..FIX_SEQ chunks is summed
+// from its pieces here; a bucket split over more chunks (skewed scalars: many equal digits) is queued for
+// k_fixup_heavy.
 template <class F>
 __global__ void __launch_bounds__(128)
-k_fixup(const uint32_t* __restrict__ offsets, uint32_t K, XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ PH,
-        const XYZZ<F>* __restrict__ PT) {
+k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* __restrict__ buckets,
+        const XYZZ<F>* __restrict__ PH, const XYZZ<F>* __restrict__ PT, uint32_t* __restrict__ heavy_count,
+        uint32_t* __restrict__ heavy_list) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    uint32_t o = 0, o2 = 0, t0 = 0, np = 0;
-    if (b < K) {
-        o = offsets[b];
-        o2 = offsets[b + 1];
-        if (o2 > o) {
-            t0 = o / LS;
-            np = (o2 - 1) / LS - t0 + 1;
-        }
+    if (b >= KB) return;
+    const uint32_t o = offsets[b], o2 = offsets[b + 1];
+    if (o2 == o) {
+        store_vec(buckets + b, XYZZ<F>::identity());
+        return;
     }
-    if (b < K) {
-        if (np == 0) {
-            store_vec(buckets + b, XYZZ<F>::identity());
-        } else if (np >= 2 && np <= (uint32_t)FIX_SMALL) {
-            XYZZ<F> acc = (o % LS == 0) ? load_vec(PH + t0) : load_vec(PT + t0);
-            for (uint32_t p = 1; p < np; p++) {
-                XYZZ<F> q = load_vec(PH + t0 + p);
-                xyzz_add(acc, q);
-            }
-            store_vec(buckets + b, acc);
-        }
+    const uint32_t t0 = o >> ls_log;
+    const uint32_t np = ((o2 - 1) >> ls_log) - t0 + 1;
+    if (np == 1) return;  // written by k_accumulate
+    if (np > (uint32_t)FIX_SEQ) {
+        heavy_list[atomicAdd(heavy_count, 1u)] = b;
+        return;
     }
-    uint32_t heavy = __ballot_sync(0xffffffffu, b < K && np > (uint32_t)FIX_SMALL);
-    while (heavy) {
-        const int src = __ffs(heavy) - 1;
-        heavy &= heavy - 1;
-        const uint32_t h_o = __shfl_sync(0xffffffffu, o, src);
-        const uint32_t h_t0 = __shfl_sync(0xffffffffu, t0, src);
-        const uint32_t h_np = __shfl_sync(0xffffffffu, np, src);
+    XYZZ<F> acc = (o & ((1u << ls_log) - 1)) ? load_vec(PT + t0) : load_vec(PH + t0);
+#pragma unroll 1
+    for (uint32_t p = 1; p < np; p++) {
+        XYZZ<F> q = load_vec(PH + t0 + p);
+        xyzz_add<false>(acc, q);
+    }
+    store_vec(buckets + b, acc);
+}
+
+// One block per queued bucket: threads stride over its pieces, then a shared-memory tree.
+template <class F>
+__global__ void __launch_bounds__(HEAVY_THREADS)
+k_fixup_heavy(const uint32_t* __restrict__ offsets, int ls_log, XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ PH,
+              const XYZZ<F>* __restrict__ PT, const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
+    __shared__ XYZZ<F> sh[HEAVY_THREADS];
+    const uint32_t count = *heavy_count;
+    for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+        const uint32_t b = heavy_list[h];
+        const uint32_t o = offsets[b], o2 = offsets[b + 1];
+        const uint32_t t0 = o >> ls_log;
+        const uint32_t np = ((o2 - 1) >> ls_log) - t0 + 1;
         XYZZ<F> acc = XYZZ<F>::identity();
-        for (uint32_t p = lane; p < h_np; p += 32) {
-            XYZZ<F> q = (p == 0 && (h_o % LS != 0)) ? load_vec(PT + h_t0) : load_vec(PH + h_t0 + p);
-            xyzz_add(acc, q);
+        for (uint32_t p = threadIdx.x; p < np; p += HEAVY_THREADS) {
+            XYZZ<F> q = (p == 0 && (o & ((1u << ls_log) - 1))) ? load_vec(PT + t0) : load_vec(PH + t0 + p);
+            xyzz_add<false>(acc, q);
         }
-        acc = warp_sum(acc);
-        if (lane == src) store_vec(buckets + b, acc);
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int d = HEAVY_THREADS / 2; d >= 1; d >>= 1) {
+            if ((int)threadIdx.x < d) {
+                XYZZ<F> x = sh[threadIdx.x];
+                XYZZ<F> y = sh[threadIdx.x + d];
+                xyzz_add<false>(x, y);
+                sh[threadIdx.x] = x;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_vec(buckets + b, sh[0]);
+        __syncthreads();
     }
 }
 
@@ -372,19 +399,22 @@ SB_D void warp_combine(XYZZ<F> S, XYZZ<F> Wt, int log_child_len, int lane, XYZZ<
 #pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
         XYZZ<F> t = shfl_down_point(suf, d);
-        if (lane + d < 32) xyzz_add(suf, t);
+        if (lane + d < 32) xyzz_add<false>(suf, t);
     }
     outS = shfl_point(suf, 0);
     XYZZ<F> js = (lane >= 1) ? suf : XYZZ<F>::identity();
     js = warp_sum(js);
-    for (int k = 0; k < log_child_len; k++) js = xyzz_double(js);
-    xyzz_add(sumW, js);
+#pragma unroll 1
+    for (int k = 0; k < log_child_len; k++) js = xyzz_double<false>(js);
+    xyzz_add<false>(sumW, js);
     outWt = sumW;
 }
 
 template <class F>
 __global__ void __launch_bounds__(128)
-k_reduce_level0(const XYZZ<F>* __restrict__ buckets, uint32_t K, Node<F>* __restrict__ out, uint32_t num_out) {
+k_reduce_level0(const XYZZ<F>* __restrict__ buckets_all, uint32_t K, Node<F>* __restrict__ out_all, uint32_t num_out) {
+    const XYZZ<F>* buckets = buckets_all + (size_t)blockIdx.y * K;
+    Node<F>* out = out_all + (size_t)blockIdx.y * num_out;
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
@@ -394,9 +424,9 @@ k_reduce_level0(const XYZZ<F>* __restrict__ buckets, uint32_t K, Node<F>* __rest
         uint64_t b = first + j;
         if (b < K) {
             XYZZ<F> q = load_vec(buckets + b);
-            xyzz_add(run, q);
+            xyzz_add<false>(run, q);
         }
-        xyzz_add(acc, run);
+        xyzz_add<false>(acc, run);
     }
     XYZZ<F> S, Wt;
     int log_l0 = 0;
@@ -411,7 +441,9 @@ k_reduce_level0(const XYZZ<F>* __restrict__ buckets, uint32_t K, Node<F>* __rest
 
 template <class F>
 __global__ void __launch_bounds__(128)
-k_reduce_level(const Node<F>* __restrict__ in, uint32_t count, int log_child_len, Node<F>* __restrict__ out, uint32_t num_out) {
+k_reduce_level(const Node<F>* __restrict__ in_all, uint32_t count, int log_child_len, Node<F>* __restrict__ out_all, uint32_t num_out) {
+    const Node<F>* in = in_all + (size_t)blockIdx.y * count;
+    Node<F>* out = out_all + (size_t)blockIdx.y * num_out;
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     XYZZ<F> s = XYZZ<F>::identity(), w = XYZZ<F>::identity();
@@ -428,23 +460,26 @@ k_reduce_level(const Node<F>* __restrict__ in, uint32_t count, int log_child_len
     }
 }
 
+// one thread per batch entry (one warp each, so the serial inversions run on different schedulers)
 template <class F>
-__global__ void k_finalize(const Node<F>* __restrict__ root, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    XYZZ<F> r = load_vec(&root->Wt);
-    if (out_xyzz) store_vec(out_xyzz, r);
-    if (out_xy) store_vec(out_xy, xyzz_to_affine(r));
+__global__ void k_finalize(const Node<F>* __restrict__ roots, uint32_t batch, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
+    const uint32_t b = blockIdx.x;
+    if (threadIdx.x != 0 || b >= batch) return;
+    XYZZ<F> r = load_vec(&roots[b].Wt);
+    if (out_xyzz) store_vec(out_xyzz + b, r);
+    if (out_xy) store_vec(out_xy + b, xyzz_to_affine<false>(r));
 }
 
 template <class F>
-__global__ void k_identity_out(Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (out_xyzz) store_vec(out_xyzz, XYZZ<F>::identity());
+__global__ void k_identity_out(uint32_t batch, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
+    const uint32_t b = blockIdx.x;
+    if (threadIdx.x != 0 || b >= batch) return;
+    if (out_xyzz) store_vec(out_xyzz + b, XYZZ<F>::identity());
     if (out_xy) {
         Affine<F> z;
         z.x = F::zero();
         z.y = F::zero();
-        store_vec(out_xy, z);
+        store_vec(out_xy + b, z);
     }
 }
 
@@ -454,9 +489,9 @@ __global__ void k_combine(const XYZZ<F>* __restrict__ parts, int count, Affine<F
     XYZZ<F> acc = XYZZ<F>::identity();
     for (int i = 0; i < count; i++) {
         XYZZ<F> q = load_vec(parts + i);
-        xyzz_add(acc, q);
+        xyzz_add<false>(acc, q);
     }
-    store_vec(out_xy, xyzz_to_affine(acc));
+    store_vec(out_xy, xyzz_to_affine<false>(acc));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -486,19 +521,35 @@ static int default_window_bits(size_t n) {
 }
 
 struct MsmPlan {
-    size_t n, nW, chunks;
-    uint32_t K, tiles, nodes0;
+    size_t n, total, nW, chunks;
+    uint32_t batch, K, KB, tiles, nodes0;
+    int ls_log;
     size_t off_dig, off_counts, off_offsets, off_cursor, off_tiles, off_ekey, off_eidx, off_buckets, off_ph, off_pt,
-        off_nodes_a, off_nodes_b, off_out_xy, off_out_xyzz, off_scalars, total;
+        off_heavy, off_nodes_a, off_nodes_b, off_out_xy, off_out_xyzz, off_scalars, total_bytes;
 };
 
-static MsmPlan make_plan(const sb_ck* ck, size_t n, bool stage_scalars) {
-    MsmPlan p{};
+static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars, MsmPlan& p) {
+    p = MsmPlan{};
     p.n = n;
-    p.nW = n * (size_t)ck->W;
-    p.chunks = (p.nW + LS - 1) / LS;
+    p.batch = (uint32_t)batch;
+    p.total = n * batch;
+    p.nW = p.total * (size_t)ck->W;
     p.K = ck->K;
-    p.tiles = (p.K + SCAN_TILE - 1) / SCAN_TILE;
+    const uint64_t kb = (uint64_t)ck->K * batch;
+    if (p.nW >= (1ull << 31) || kb > (1ull << 25)) {
+        set_error("sb_msm: batch too large (n*W*batch = %zu, buckets = %llu)", p.nW, (unsigned long long)kb);
+        return SB_ERR_ARG;
+    }
+    p.KB = (uint32_t)kb;
+    // chunk length: aim at ~4 pieces per bucket, between 2^4 and 2^8 entries
+    {
+        size_t per_bucket = p.nW / (p.KB ? p.KB : 1);
+        int l = LS_MIN_LOG;
+        while (l < LS_MAX_LOG && ((size_t)4 << l) < per_bucket) l++;
+        p.ls_log = l;
+    }
+    p.chunks = (p.nW + ((size_t)1 << p.ls_log) - 1) >> p.ls_log;
+    p.tiles = (p.KB + SCAN_TILE - 1) / SCAN_TILE;
     p.nodes0 = (p.K + 32 * RED_L0 - 1) / (32 * RED_L0);
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -507,28 +558,29 @@ static MsmPlan make_plan(const sb_ck* ck, size_t n, bool stage_scalars) {
         return o;
     };
     p.off_dig = take(p.nW * 4);
-    p.off_counts = take((size_t)p.K * 4);
-    p.off_offsets = take(((size_t)p.K + 1) * 4);
-    p.off_cursor = take((size_t)p.K * 4);
+    p.off_counts = take(((size_t)p.KB + 1) * 4);  // +1: heavy-bucket counter lives behind the counts (one memset)
+    p.off_offsets = take(((size_t)p.KB + 1) * 4);
+    p.off_cursor = take((size_t)p.KB * 4);
     p.off_tiles = take(8192 * 4);
     p.off_ekey = take(p.nW * 4);
     p.off_eidx = take(p.nW * 4);
-    p.off_buckets = take((size_t)p.K * 128);
+    p.off_buckets = take((size_t)p.KB * 128);
     p.off_ph = take(p.chunks * 128);
     p.off_pt = take(p.chunks * 128);
-    p.off_nodes_a = take((size_t)p.nodes0 * 256);
-    p.off_nodes_b = take(((size_t)p.nodes0 / 32 + 1) * 256);
-    p.off_out_xy = take(64);
-    p.off_out_xyzz = take(128);
-    p.off_scalars = take(stage_scalars ? n * 32 : 0);
-    p.total = off;
-    return p;
+    p.off_heavy = take((p.chunks / FIX_SEQ + 2) * 4);
+    p.off_nodes_a = take((size_t)p.nodes0 * batch * 256);
+    p.off_nodes_b = take(((size_t)p.nodes0 / 32 + 1) * batch * 256);
+    p.off_out_xy = take(64 * batch);
+    p.off_out_xyzz = take(128 * batch);
+    p.off_scalars = take(stage_scalars ? p.total * 32 : 0);
+    p.total_bytes = off;
+    return SB_OK;
 }
 
 template <class F, class S>
-static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, void* d_out_xy, void* d_out_xyzz,
-                       cudaStream_t st) {
-    const uint32_t n = (uint32_t)p.n;
+static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, size_t stride, void* d_out_xy,
+                       void* d_out_xyzz, cudaStream_t st) {
+    const uint32_t n = (uint32_t)p.n, total = (uint32_t)p.total;
     auto* dig = (uint32_t*)(ws + p.off_dig);
     auto* counts = (uint32_t*)(ws + p.off_counts);
     auto* offsets = (uint32_t*)(ws + p.off_offsets);
@@ -539,32 +591,37 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     auto* buckets = (XYZZ<F>*)(ws + p.off_buckets);
     auto* PH = (XYZZ<F>*)(ws + p.off_ph);
     auto* PT = (XYZZ<F>*)(ws + p.off_pt);
+    auto* heavy_list = (uint32_t*)(ws + p.off_heavy);
     auto* nodes_a = (Node<F>*)(ws + p.off_nodes_a);
     auto* nodes_b = (Node<F>*)(ws + p.off_nodes_b);
-    const uint32_t K = p.K;
+    const uint32_t K = p.K, KB = p.KB;
+    uint32_t* heavy_count = counts + KB;
 
-    SB_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)K * 4, st));
-    k_decompose<S><<<(n + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, ck->c, ck->W, dig, counts);
+    SB_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)KB + 1) * 4, st));
+    k_decompose<S><<<(total + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, total, stride, K, ck->c, ck->W, dig, counts);
     SB_KERNEL_CHECK();
-    k_scan_tile_sums<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, K, tiles);
+    k_scan_tile_sums<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles);
     SB_KERNEL_CHECK();
     k_scan_tiles<<<1, 1024, 0, st>>>(tiles, p.tiles);
     SB_KERNEL_CHECK();
-    k_scan_apply<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, K, tiles, offsets, cursor);
+    k_scan_apply<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets, cursor);
     SB_KERNEL_CHECK();
-    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(dig, n, (uint32_t)ck->n, ck->W, cursor, ekey, eidx);
+    k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, ck->W, cursor, ekey, eidx);
     SB_KERNEL_CHECK();
     {
         size_t blocks = (p.chunks + 127) / 128;
-        k_accumulate<F><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, K, buckets, PH, PT);
+        k_accumulate<F><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         SB_KERNEL_CHECK();
     }
-    k_fixup<F><<<(K + 127) / 128, 128, 0, st>>>(offsets, K, buckets, PH, PT);
+    k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(offsets, KB, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
+    SB_KERNEL_CHECK();
+    k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(offsets, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
     SB_KERNEL_CHECK();
     {
         uint32_t lanes = (K + RED_L0 - 1) / RED_L0;
         lanes = (lanes + 31) / 32 * 32;
-        k_reduce_level0<F><<<(lanes + 127) / 128, 128, 0, st>>>(buckets, K, nodes_a, p.nodes0);
+        dim3 grid((lanes + 127) / 128, p.batch);
+        k_reduce_level0<F><<<grid, 128, 0, st>>>(buckets, K, nodes_a, p.nodes0);
         SB_KERNEL_CHECK();
     }
     uint32_t count = p.nodes0;
@@ -573,27 +630,29 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     Node<F>*cur = nodes_a, *nxt = nodes_b;
     while (count > 1) {
         uint32_t lanes = (count + 31) / 32 * 32;
-        k_reduce_level<F><<<(lanes + 127) / 128, 128, 0, st>>>(cur, count, log_len, nxt, (count + 31) / 32);
+        dim3 grid((lanes + 127) / 128, p.batch);
+        k_reduce_level<F><<<grid, 128, 0, st>>>(cur, count, log_len, nxt, (count + 31) / 32);
         SB_KERNEL_CHECK();
         count = (count + 31) / 32;
         log_len += 5;
         std::swap(cur, nxt);
     }
-    k_finalize<F><<<1, 32, 0, st>>>(cur, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
+    k_finalize<F><<<p.batch, 32, 0, st>>>(cur, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
     SB_KERNEL_CHECK();
     return SB_OK;
 }
 
-static int msm_dispatch(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, void* d_out_xy, void* d_out_xyzz,
-                        cudaStream_t st) {
+static int msm_dispatch(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, size_t stride, void* d_out_xy,
+                        void* d_out_xyzz, cudaStream_t st) {
+    if (p.batch == 0) return SB_OK;
     if (p.n == 0) {
-        if (ck->curve == CURVE_BN256) k_identity_out<Fq><<<1, 32, 0, st>>>((Affine<Fq>*)d_out_xy, (XYZZ<Fq>*)d_out_xyzz);
-        else k_identity_out<Fr><<<1, 32, 0, st>>>((Affine<Fr>*)d_out_xy, (XYZZ<Fr>*)d_out_xyzz);
+        if (ck->curve == CURVE_BN256) k_identity_out<Fq><<<p.batch, 32, 0, st>>>(p.batch, (Affine<Fq>*)d_out_xy, (XYZZ<Fq>*)d_out_xyzz);
+        else k_identity_out<Fr><<<p.batch, 32, 0, st>>>(p.batch, (Affine<Fr>*)d_out_xy, (XYZZ<Fr>*)d_out_xyzz);
         SB_KERNEL_CHECK();
         return SB_OK;
     }
-    if (ck->curve == CURVE_BN256) return msm_enqueue<Fq, Fr>(ck, p, ws, d_scalars, d_out_xy, d_out_xyzz, st);
-    return msm_enqueue<Fr, Fq>(ck, p, ws, d_scalars, d_out_xy, d_out_xyzz, st);
+    if (ck->curve == CURVE_BN256) return msm_enqueue<Fq, Fr>(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st);
+    return msm_enqueue<Fr, Fq>(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st);
 }
 
 static int ck_build(int curve, const void* d_bases, size_t n, int window_bits, cudaStream_t st, sb_ck_t* out) {
@@ -691,21 +750,59 @@ void sb_ck_release(sb_ck_t ck) {
 size_t sb_ck_len(sb_ck_t ck) { return ck ? ck->n : 0; }
 int sb_ck_window_bits(sb_ck_t ck) { return ck ? ck->c : 0; }
 
-int sb_msm_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, void* d_out_xy, void* d_out_xyzz, void* stream) {
-    if (!ck || (!d_scalars_mont && n) || (!d_out_xy && !d_out_xyzz)) {
-        set_error("sb_msm_device: null argument");
-        return SB_ERR_ARG;
-    }
+static int check_len(sb_ck_t ck, size_t n) {
     if (n > ck->n) {
         set_error("Can't commit too long input: input len: %zu, but limit is %zu", n, ck->n);
         return SB_ERR_TOO_LONG;
     }
+    return SB_OK;
+}
+
+int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t stride, size_t batch, void* d_out_xy,
+                        void* d_out_xyzz, void* stream) {
+    if (!ck || (!d_scalars_mont && n && batch) || (!d_out_xy && !d_out_xyzz) || stride < n) {
+        set_error("sb_msm_batch_device: bad argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(check_len(ck, n));
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
     std::lock_guard<std::mutex> lk(rt.mu);
-    MsmPlan p = make_plan(ck, n, false);
-    SB_TRY(g_ws.reserve(p.total));
-    return msm_dispatch(ck, p, (char*)g_ws.ptr, d_scalars_mont, d_out_xy, d_out_xyzz, stream ? (cudaStream_t)stream : rt.stream);
+    MsmPlan p;
+    SB_TRY(make_plan(ck, n, batch, false, p));
+    SB_TRY(g_ws.reserve(p.total_bytes));
+    return msm_dispatch(ck, p, (char*)g_ws.ptr, d_scalars_mont, stride, d_out_xy, d_out_xyzz, stream ? (cudaStream_t)stream : rt.stream);
+}
+
+int sb_msm_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, void* d_out_xy, void* d_out_xyzz, void* stream) {
+    return sb_msm_batch_device(ck, d_scalars_mont, n, n, 1, d_out_xy, d_out_xyzz, stream);
+}
+
+int sb_msm_batch(sb_ck_t ck, const uint64_t* const* scalars_mont, size_t n, size_t batch, uint64_t* out_xy) {
+    if (!ck || (!scalars_mont && batch) || !out_xy) {
+        set_error("sb_msm_batch: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(check_len(ck, n));
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    if (batch == 0) return SB_OK;
+    MsmPlan p;
+    SB_TRY(make_plan(ck, n, batch, true, p));
+    SB_TRY(g_ws.reserve(p.total_bytes));
+    char* ws = (char*)g_ws.ptr;
+    for (size_t b = 0; b < batch && n; b++) {
+        if (!scalars_mont[b]) {
+            set_error("sb_msm_batch: null scalar vector %zu", b);
+            return SB_ERR_ARG;
+        }
+        SB_CUDA_TRY(cudaMemcpyAsync(ws + p.off_scalars + b * n * 32, scalars_mont[b], n * 32, cudaMemcpyHostToDevice, rt.stream));
+    }
+    SB_TRY(msm_dispatch(ck, p, ws, ws + p.off_scalars, n, ws + p.off_out_xy, nullptr, rt.stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(out_xy, ws + p.off_out_xy, 64 * batch, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
 }
 
 int sb_msm(sb_ck_t ck, const uint64_t* scalars_mont, size_t n, uint64_t out_xy[8]) {
@@ -713,21 +810,8 @@ int sb_msm(sb_ck_t ck, const uint64_t* scalars_mont, size_t n, uint64_t out_xy[8
         set_error("sb_msm: null argument");
         return SB_ERR_ARG;
     }
-    if (n > ck->n) {
-        set_error("Can't commit too long input: input len: %zu, but limit is %zu", n, ck->n);
-        return SB_ERR_TOO_LONG;
-    }
-    SB_TRY(ensure_runtime());
-    Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
-    MsmPlan p = make_plan(ck, n, true);
-    SB_TRY(g_ws.reserve(p.total));
-    char* ws = (char*)g_ws.ptr;
-    if (n) SB_CUDA_TRY(cudaMemcpyAsync(ws + p.off_scalars, scalars_mont, n * 32, cudaMemcpyHostToDevice, rt.stream));
-    SB_TRY(msm_dispatch(ck, p, ws, ws + p.off_scalars, ws + p.off_out_xy, nullptr, rt.stream));
-    SB_CUDA_TRY(cudaMemcpyAsync(out_xy, ws + p.off_out_xy, 64, cudaMemcpyDeviceToHost, rt.stream));
-    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
-    return SB_OK;
+    const uint64_t* one[1] = {scalars_mont};
+    return sb_msm_batch(ck, one, n, 1, out_xy);
 }
 
 int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, void* d_out_xy, void* stream) {

@@ -18,7 +18,7 @@ static void t_addsub(const uint64_t* a, const uint64_t* b, uint64_t* o_add, uint
 }
 template <class F>
 static void t_inv(const uint64_t* a, uint64_t* o, size_t n) {
-    for (size_t i = 0; i < n; i++) ((F*)o)[i] = inv(((const F*)a)[i]);
+    for (size_t i = 0; i < n; i++) ((F*)o)[i] = (i & 1) ? inv(((const F*)a)[i]) : inv_binary(((const F*)a)[i]);
 }
 // sum_i (+/-) P_i with madd, then tree-combine two halves with xyzz_add, double once, -> affine
 template <class F>

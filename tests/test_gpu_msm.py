@@ -106,6 +106,21 @@ def test_msm_medium_skew(sb, oracle, curve, kind):
     ck.close()
 
 
+@pytest.mark.parametrize("curve", [R.CURVE_BN256, R.CURVE_GRUMPKIN])
+def test_msm_batch(sb, oracle, curve):
+    """the d cross-term commits of one commit_cross_terms call as one batched pipeline"""
+    n = 5000
+    bases = oracle.running_bases(curve, n + 5)
+    ck = sb.CommitmentKey(curve, bases, window_bits=10)
+    vs = [_scalars(oracle, curve, n, 40 + j, kind) for j, kind in enumerate(["uniform", "witness", "equal", "edge", "uniform"])]
+    vs[4][:] = 0  # an all-zero cross term (T_d of a satisfied instance) -> identity commitment
+    got = ck.commit_batch(vs)
+    for j, v in enumerate(vs):
+        assert np.array_equal(got[j], oracle.msm(curve, v, bases)), j
+    assert not got[4].any()
+    ck.close()
+
+
 def test_msm_too_long_input(sb, oracle):
     bases = oracle.running_bases(R.CURVE_BN256, 8)
     ck = sb.CommitmentKey(R.CURVE_BN256, bases)
