@@ -37,7 +37,33 @@ extern "C" {
 #define SB_CURVE_BN256 0
 #define SB_CURVE_GRUMPKIN 1
 
-typedef struct sb_ck* sb_ck_t; /* device-resident CommitmentKey (src/commitment.rs:29-32) */
+typedef struct sb_ck* sb_ck_t;           /* device-resident CommitmentKey (src/commitment.rs:29-32) */
+typedef struct sb_prog* sb_prog_t;       /* uploaded GraphEvaluator program (src/polynomial/graph_evaluator.rs:164-180) */
+typedef struct sb_columns* sb_columns_t; /* device-resident selectors + fixed columns of a PlonkStructure (src/plonk/mod.rs:132-133) */
+
+/* ValueSource (graph_evaluator.rs:57-68) and Calculation (graph_evaluator.rs:72-89) discriminants */
+#define SB_VS_CONSTANT 0
+#define SB_VS_INTERMEDIATE 1
+#define SB_VS_FIXED 2
+#define SB_VS_POLY 3
+#define SB_VS_CHALLENGE 4
+#define SB_OP_ADD 0
+#define SB_OP_SUB 1
+#define SB_OP_MUL 2
+#define SB_OP_SQUARE 3
+#define SB_OP_DOUBLE 4
+#define SB_OP_NEGATE 5
+#define SB_OP_HORNER 6 /* defined by the reference but never emitted by add_expression; rejected */
+#define SB_OP_STORE 7
+
+/* One CalculationInfo (graph_evaluator.rs:152-156): `target = opcode(a, b)`.  For FIXED/POLY sources
+ * *_index is the column index and *_rot the index into the program's rotation table. */
+typedef struct {
+    uint8_t opcode, a_kind, b_kind, _pad;
+    uint32_t a_index, a_rot;
+    uint32_t b_index, b_rot;
+    uint32_t target;
+} sb_calc;
 
 const char* sb_last_error(void);
 int sb_version(void);
@@ -73,6 +99,49 @@ int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t
                         void* d_out_xyzz, void* stream);
 /* Multi-GPU combine: sum `count` XYZZ partials (device, 128 B each) and normalise to affine. */
 int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, void* d_out_xy, void* stream);
+
+/* ---- gate evaluation, Sangria cross terms, folds ------------------------------------------------------ */
+
+/* Upload a compiled GraphEvaluator (calculations, constants incl. the leading [0,1,2], rotations). */
+int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint64_t* constants_mont, size_t n_constants,
+                    const int32_t* rotations, size_t n_rotations, sb_prog_t* out);
+void sb_expr_free(sb_prog_t prog);
+uint32_t sb_expr_num_slots(sb_prog_t prog);
+
+/* Selector (1 byte per row, Vec<Vec<bool>>) and fixed (Vec<Vec<F>>) columns of a PlonkStructure, 2^log_rows rows. */
+int sb_columns_register(int field, uint32_t log_rows, const uint8_t* const* selectors, size_t num_selectors,
+                        const uint64_t* const* fixed, size_t num_fixed, sb_columns_t* out);
+void sb_columns_release(sb_columns_t cols);
+
+/* GraphEvaluator::evaluate for every row (graph_evaluator.rs:361-388) with GetDataForEval::eval_column_var
+ * column addressing (src/plonk/eval.rs:57-69): out[row] = expr(row).  W1 (and W2 for two-instance expressions,
+ * PlonkEvalDomain, eval.rs:153-228) are the witness round vectors, column-major.  W2 may be NULL. */
+int sb_expr_eval(sb_prog_t prog, sb_columns_t cols, uint32_t num_advice, uint32_t num_lookup, const uint64_t* const* W1,
+                 const size_t* W1_lens, size_t W1_rounds, const uint64_t* const* W2, const size_t* W2_lens, size_t W2_rounds,
+                 const uint64_t* challenges, size_t num_challenges, uint64_t* out);
+int sb_expr_eval_device(sb_prog_t prog, sb_columns_t cols, const void* const* d_adv1_cols, const void* const* d_adv2_cols,
+                        size_t num_fold_vars, const uint64_t* challenges, size_t num_challenges, void* d_out, void* stream);
+
+/* Evaluation half of VanillaFS::commit_cross_terms (src/nifs/sangria/mod.rs:110-147): `prog` is the compiled
+ * HOMOGENEOUS compressed gate expression (CompressedGates::homogeneous, src/plonk/mod.rs:113-115) of folding
+ * degree `degree`; challenges1 = [U1.challenges.., U1.u], challenges2 = [U2.challenges.., 1] (:113-118).
+ * out_T[j-1][row] = T_j(row) for j = 1..degree -- the same vectors GroupedPoly::iter_from_first yields. */
+int sb_cross_terms(sb_prog_t prog, uint32_t degree, sb_columns_t cols, uint32_t num_advice, uint32_t num_lookup,
+                   const uint64_t* const* W1, const size_t* W1_lens, size_t W1_rounds, const uint64_t* const* W2,
+                   const size_t* W2_lens, size_t W2_rounds, const uint64_t* challenges1, const uint64_t* challenges2,
+                   size_t num_challenges, uint64_t* const* out_T);
+/* d_adv*_cols: HOST arrays of num_fold_vars DEVICE column pointers; d_out: degree * 2^log_rows elements. */
+int sb_cross_terms_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, const void* const* d_adv1_cols,
+                          const void* const* d_adv2_cols, size_t num_fold_vars, const uint64_t* challenges1,
+                          const uint64_t* challenges2, size_t num_challenges, void* d_out, void* stream);
+
+/* RelaxedPlonkWitness::fold (src/nifs/sangria/accumulator.rs:363-404):
+ *   axpy : out[i] = w1[i] + r * w2[i]                        (:366-378)
+ *   error: out[i] = e[i] + sum_{j=1..d} r^j * T_j[i]         (:382-397)  (device form: T contiguous [d][n]) */
+int sb_axpy_fold(int field, const uint64_t* w1, const uint64_t* w2, const uint64_t r[4], uint64_t* out, size_t n);
+int sb_axpy_fold_device(int field, const void* d_w1, const void* d_w2, const uint64_t r[4], void* d_out, size_t n, void* stream);
+int sb_error_fold(int field, const uint64_t* e, const uint64_t* const* T, uint32_t d, const uint64_t r[4], uint64_t* out, size_t n);
+int sb_error_fold_device(int field, const void* d_e, const void* d_T, uint32_t d, const uint64_t r[4], void* d_out, size_t n, void* stream);
 
 /* ---- fft (src/fft.rs) ------------------------------------------------------------------------------ */
 

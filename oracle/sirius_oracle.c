@@ -642,3 +642,107 @@ int so_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------ GraphEvaluator interpreter
+ * GraphEvaluator::evaluate (src/polynomial/graph_evaluator.rs:361-388) with Calculation::evaluate (:91-150)
+ * for every row.  calcs[i] = {opcode, a_kind, a_index, a_rot, b_kind, b_index, b_rot, target}.
+ * Column variables follow GetDataForEval::eval_column_var (src/plonk/eval.rs:57-69): selectors, then fixed,
+ * then the caller-provided advice column table (the caller applies PlonkEvalDomain's index map, eval.rs:153-228,
+ * when it builds that table).  Returns 1..4 for the EvalError cases. */
+int so_graph_evaluate(int field, const int32_t *calcs, size_t n_calcs, const u64 *constants, size_t n_constants,
+                      const int32_t *rotations, size_t n_rotations, const uint8_t *const *selectors, size_t n_sel,
+                      const u64 *const *fixed, size_t n_fixed, const u64 *const *advice, size_t n_advice,
+                      const u64 *challenges, size_t n_challenges, uint32_t log_rows, int threads, u64 *out) {
+    const field_t *F = &FIELDS[field];
+    const size_t n = (size_t)1 << log_rows;
+    int err = 0;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#else
+    threads = 1;
+#endif
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (long row = 0; row < (long)n; row++) {
+        fe *inter = (fe *)malloc((n_calcs ? n_calcs : 1) * sizeof(fe));   /* fresh Vec per row (:354-359) */
+        size_t *rots = (size_t *)malloc((n_rotations ? n_rotations : 1) * sizeof(size_t));
+        for (size_t r = 0; r < n_rotations; r++) {
+            long v = ((long)row + rotations[r]) % (long)n;  /* rem_euclid (:51-53) */
+            if (v < 0) v += (long)n;
+            rots[r] = (size_t)v;
+        }
+        for (size_t i = 0; i < n_calcs; i++) {
+            const int32_t *c = calcs + 8 * i;
+            fe v[2];
+            int nsrc = (c[0] <= 2) ? 2 : 1;
+            for (int s = 0; s < nsrc; s++) {
+                int kind = c[1 + 3 * s];
+                size_t idx = (size_t)c[2 + 3 * s], rot = (size_t)c[3 + 3 * s];
+                switch (kind) {
+                    case 0: if (idx >= n_constants) { err = 1; fe_zero(&v[s]); } else v[s] = ((const fe *)constants)[idx]; break;
+                    case 1: v[s] = inter[idx]; break;
+                    case 2: if (idx >= n_fixed) { err = 2; fe_zero(&v[s]); } else v[s] = ((const fe *)fixed[idx])[rots[rot]]; break;
+                    case 3: {
+                        size_t r = rots[rot];
+                        if (idx < n_sel) { if (selectors[idx][r]) fe_one(&v[s], F); else fe_zero(&v[s]); }
+                        else if (idx < n_sel + n_fixed) v[s] = ((const fe *)fixed[idx - n_sel])[r];
+                        else if (idx - n_sel - n_fixed < n_advice) v[s] = ((const fe *)advice[idx - n_sel - n_fixed])[r];
+                        else { err = 2; fe_zero(&v[s]); }
+                        break;
+                    }
+                    case 4: if (idx >= n_challenges) { err = 3; fe_zero(&v[s]); } else v[s] = ((const fe *)challenges)[idx]; break;
+                    default: err = 4; fe_zero(&v[s]);
+                }
+            }
+            fe r;
+            switch (c[0]) {
+                case 0: fe_add(&r, &v[0], &v[1], F); break;
+                case 1: fe_sub(&r, &v[0], &v[1], F); break;
+                case 2: fe_mul(&r, &v[0], &v[1], F); break;
+                case 3: fe_sqr(&r, &v[0], F); break;
+                case 4: fe_dbl(&r, &v[0], F); break;
+                case 5: fe_neg(&r, &v[0], F); break;
+                case 7: r = v[0]; break;
+                default: err = 4; fe_zero(&r);
+            }
+            inter[c[7]] = r;
+        }
+        if (n_calcs) ((fe *)out)[row] = inter[calcs[8 * (n_calcs - 1) + 7]];
+        else fe_zero(&((fe *)out)[row]);
+        free(rots);
+        free(inter);
+    }
+    return err;
+}
+
+/* RelaxedPlonkWitness::fold (src/nifs/sangria/accumulator.rs:363-404) */
+int so_axpy(int field, const u64 *w1, const u64 *w2, const u64 r[4], u64 *out, size_t n) {
+    const field_t *F = &FIELDS[field];
+    fe rr;
+    memcpy(rr.l, r, 32);
+#pragma omp parallel for
+    for (long i = 0; i < (long)n; i++) {
+        fe t;
+        fe_mul(&t, &rr, (const fe *)w2 + i, F);
+        fe_add((fe *)out + i, (const fe *)w1 + i, &t, F);
+    }
+    return 0;
+}
+int so_error_fold(int field, const u64 *e, const u64 *const *T, size_t d, const u64 r[4], u64 *out, size_t n) {
+    const field_t *F = &FIELDS[field];
+    fe rr, pw[64];
+    memcpy(rr.l, r, 32);
+    if (d > 64) return 1;
+    fe cur = rr;
+    for (size_t j = 0; j < d; j++) { pw[j] = cur; fe_mul(&cur, &cur, &rr, F); }
+#pragma omp parallel for
+    for (long i = 0; i < (long)n; i++) {
+        fe acc = ((const fe *)e)[i];
+        for (size_t j = 0; j < d; j++) {
+            fe t;
+            fe_mul(&t, &pw[j], (const fe *)T[j] + i, F);
+            fe_add(&acc, &acc, &t, F);
+        }
+        ((fe *)out)[i] = acc;
+    }
+    return 0;
+}

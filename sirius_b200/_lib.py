@@ -40,12 +40,35 @@ SIGNATURES = {
     "sb_msm_batch": (ctypes.c_int, [vp, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p]),
     "sb_msm_batch_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp]),
     "sb_msm_combine_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
+    "sb_expr_compile": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32), ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "sb_expr_free": (None, [vp]),
+    "sb_expr_num_slots": (ctypes.c_uint32, [vp]),
+    "sb_columns_register": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint32, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint8)), ctypes.c_size_t, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "sb_columns_release": (None, [vp]),
+    "sb_expr_eval": (ctypes.c_int, [vp, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(u64p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.POINTER(u64p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]),
+    "sb_expr_eval_device": (ctypes.c_int, [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.c_size_t, u64p, ctypes.c_size_t, vp, vp]),
+    "sb_cross_terms": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(u64p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.POINTER(u64p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.POINTER(u64p)]),
+    "sb_cross_terms_device": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, vp, vp]),
+    "sb_axpy_fold": (ctypes.c_int, [ctypes.c_int, u64p, u64p, u64p, u64p, ctypes.c_size_t]),
+    "sb_axpy_fold_device": (ctypes.c_int, [ctypes.c_int, vp, vp, u64p, vp, ctypes.c_size_t, vp]),
+    "sb_error_fold": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.POINTER(u64p), ctypes.c_uint32, u64p, u64p, ctypes.c_size_t]),
+    "sb_error_fold_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_uint32, u64p, vp, ctypes.c_size_t, vp]),
     "sb_ntt": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint32, u64p, u64p]),
     "sb_ntt_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint32, u64p, u64p, vp]),
     "sb_coset_scale": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p, u64p]),
     "sb_coset_scale_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, u64p, u64p, vp]),
     "sb_selftest_field": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p, u64p]),
 }
+
+
+
+class sb_calc(ctypes.Structure):
+    _fields_ = [
+        ("opcode", ctypes.c_uint8), ("a_kind", ctypes.c_uint8), ("b_kind", ctypes.c_uint8), ("_pad", ctypes.c_uint8),
+        ("a_index", ctypes.c_uint32), ("a_rot", ctypes.c_uint32), ("b_index", ctypes.c_uint32), ("b_rot", ctypes.c_uint32),
+        ("target", ctypes.c_uint32),
+    ]
+
 
 _lib = None
 

@@ -1,0 +1,863 @@
+// expr.cu -- gate-expression evaluation over all rows, Sangria cross terms, and the witness folds.
+//
+// Replaces, on the device:
+//   * GraphEvaluator::evaluate (reference src/polynomial/graph_evaluator.rs:361-388) driven row by row from
+//     VanillaFS::commit_cross_terms (src/nifs/sangria/mod.rs:110-147), is_sat_accumulation (:334-383) and
+//     PlonkStructure::is_sat (src/plonk/mod.rs:304-361).  The Rust side keeps building `Expression`s and
+//     compiling them with GraphEvaluator::new; the compiled calculation list crosses the ABI (sb_expr_compile).
+//   * the cross terms T_1..T_d themselves: the reference expands the homogeneous gate polynomial P into
+//     degree-grouped expressions (GroupedPoly, src/polynomial/grouped_poly.rs:58-110,216-268) and evaluates each
+//     with its own pass over the columns.  T_j is the coefficient of X^j in P(w1 + X*w2, c1 + X*c2) (fixed and
+//     selector columns are not folded), so here ONE fused pass evaluates P at X = 0..d for every row and applies
+//     the inverse Vandermonde matrix -- exact field arithmetic, hence the same bits.
+//   * RelaxedPlonkWitness::fold (src/nifs/sangria/accumulator.rs:363-404): W1 + r*W2 and E + sum r^j T_j.
+//
+// Kernel shape: one thread per row, the calculation list is interpreted uniformly by the whole block (no
+// divergence), intermediates live in shared memory slots assigned by liveness at compile time, column reads are
+// coalesced (consecutive rows -> consecutive 32-byte elements).
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "field.cuh"
+
+namespace sb {
+
+constexpr int EXPR_THREADS = 128;
+constexpr int EXPR_MAX_DEGREE = 15;
+
+enum : uint32_t { VS_CONSTANT = 0, VS_INTERMEDIATE = 1, VS_FIXED = 2, VS_POLY = 3, VS_CHALLENGE = 4 };
+enum : uint32_t { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_SQUARE = 3, OP_DOUBLE = 4, OP_NEGATE = 5, OP_HORNER = 6, OP_STORE = 7 };
+
+struct DevOp {       // 16 bytes, read uniformly by every thread
+    uint32_t code;   // op | a_kind << 8 | b_kind << 16
+    uint32_t a, b;   // constant index / slot / column | rot_idx << 24 / challenge index
+    uint32_t dst;    // slot
+};
+
+struct ColumnsDev {
+    uint32_t log_rows;
+    uint32_t num_selectors, num_fixed;
+    const uint8_t* const* selectors;  // device array of device pointers
+    const void* const* fixed;
+};
+
+template <class F>
+struct EvalArgs {
+    const DevOp* ops;
+    uint32_t num_ops;
+    uint32_t num_slots;
+    uint32_t result_slot;
+    const F* constants;
+    const int32_t* rotations;
+    ColumnsDev cols;
+    uint32_t num_fold_vars;        // advice + 5 * lookups of ONE instance
+    const F* const* adv1;          // num_fold_vars column pointers (instance 1)
+    const F* const* adv2;          // instance 2 (cross terms / two-instance expressions) or nullptr
+    const F* challenges;           // single evaluation: challenge table; cross terms: [(d+1)][num_challenges]
+    uint32_t num_challenges;
+};
+
+template <class T>
+SB_D T ldg32(const T* p) {
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+    d[0] = __ldg(s);
+    d[1] = __ldg(s + 1);
+    return r;
+}
+template <class T>
+SB_D void stg32(T* p, const T& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    d[0] = s[0];
+    d[1] = s[1];
+}
+
+// shared-memory slot file: slot s of thread t is two 16-byte halves in separate planes (conflict-free)
+template <class F>
+SB_D F slot_load(const uint4* sm, uint32_t slot, uint32_t nthreads) {
+    F r;
+    uint4* d = reinterpret_cast<uint4*>(&r);
+    d[0] = sm[(slot * 2) * nthreads + threadIdx.x];
+    d[1] = sm[(slot * 2 + 1) * nthreads + threadIdx.x];
+    return r;
+}
+template <class F>
+SB_D void slot_store(uint4* sm, uint32_t slot, uint32_t nthreads, const F& v) {
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    sm[(slot * 2) * nthreads + threadIdx.x] = s[0];
+    sm[(slot * 2 + 1) * nthreads + threadIdx.x] = s[1];
+}
+
+// Value of column variable `index` (selectors -> fixed -> fold variables, reference src/plonk/eval.rs:57-69) at
+// `row`.  Fold variables of instance 1 are blended with instance 2 at the integer point t: w1 + t*w2
+// (t == 0 and two-instance indices >= num_fold_vars reproduce PlonkEvalDomain::eval_advice_var, :153-228).
+template <class F>
+SB_D F column_value(const EvalArgs<F>& A, uint32_t index, uint32_t row, uint32_t t) {
+    if (index < A.cols.num_selectors) {
+        return A.cols.selectors[index][row] ? F::one() : F::zero();
+    }
+    index -= A.cols.num_selectors;
+    if (index < A.cols.num_fixed) {
+        return ldg32(reinterpret_cast<const F*>(A.cols.fixed[index]) + row);
+    }
+    index -= A.cols.num_fixed;
+    if (index >= A.num_fold_vars) {  // explicit second-instance variable (grouped / folded expressions)
+        return ldg32(A.adv2[index - A.num_fold_vars] + row);
+    }
+    F v = ldg32(A.adv1[index] + row);
+    if (t) {
+        F w = ldg32(A.adv2[index] + row);
+        for (uint32_t k = 0; k < t; k++) v = add(v, w);
+    }
+    return v;
+}
+
+template <class F>
+SB_D F fetch(const EvalArgs<F>& A, uint32_t kind, uint32_t v, const uint4* sm, uint32_t row, uint32_t row_mask, uint32_t t) {
+    switch (kind) {
+        case VS_CONSTANT: return ldg32(A.constants + v);
+        case VS_INTERMEDIATE: return slot_load<F>(sm, v, blockDim.x);
+        case VS_CHALLENGE: return ldg32(A.challenges + (size_t)t * A.num_challenges + v);
+        default: {  // VS_POLY / VS_FIXED
+            const int32_t rot = A.rotations[v >> 24];
+            const uint32_t r = (uint32_t)((int32_t)row + rot) & row_mask;  // get_rotation_idx, graph_evaluator.rs:51-53
+            if (kind == VS_FIXED) return ldg32(reinterpret_cast<const F*>(A.cols.fixed[v & 0xffffffu]) + r);
+            return column_value(A, v & 0xffffffu, r, t);
+        }
+    }
+}
+
+// runs the calculation list once for (row, t); result left in registers
+template <class F>
+SB_D F run_program(const EvalArgs<F>& A, uint4* sm, uint32_t row, uint32_t row_mask, uint32_t t) {
+    F last = F::zero();
+    for (uint32_t i = 0; i < A.num_ops; i++) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(A.ops + i));
+        const uint32_t op = raw.x & 0xff, ak = (raw.x >> 8) & 0xff, bk = (raw.x >> 16) & 0xff;
+        F a = fetch(A, ak, raw.y, sm, row, row_mask, t);
+        F r;
+        switch (op) {
+            case OP_ADD: r = add(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
+            case OP_SUB: r = sub(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
+            case OP_MUL: r = mul(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
+            case OP_SQUARE: r = sqr(a); break;
+            case OP_DOUBLE: r = dbl(a); break;
+            case OP_NEGATE: r = neg(a); break;
+            default: r = a; break;  // OP_STORE
+        }
+        slot_store(sm, raw.w, blockDim.x, r);
+        last = r;
+    }
+    return last;  // GraphEvaluator::evaluate returns the last calculation's value (:382-387)
+}
+
+template <class F>
+__global__ void __launch_bounds__(EXPR_THREADS)
+k_expr_eval(EvalArgs<F> A, F* __restrict__ out) {
+    extern __shared__ uint4 sm[];
+    const uint32_t n = 1u << A.cols.log_rows;
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    F r = run_program(A, sm, row, n - 1, 0);
+    stg32(out + row, r);
+}
+
+// out[(j-1)*n + row] = T_j(row), j = 1..degree;  vinv is the (degree+1)^2 inverse Vandermonde on points 0..degree
+template <class F>
+__global__ void __launch_bounds__(EXPR_THREADS)
+k_cross_terms(EvalArgs<F> A, uint32_t degree, const F* __restrict__ vinv, F* __restrict__ out) {
+    extern __shared__ uint4 sm[];
+    const uint32_t n = 1u << A.cols.log_rows;
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    // evaluations are parked in extra slots behind the program's own
+    for (uint32_t t = 0; t <= degree; t++) {
+        F e = run_program(A, sm, row, n - 1, t);
+        slot_store(sm, A.num_slots + t, blockDim.x, e);
+    }
+    for (uint32_t j = 1; j <= degree; j++) {
+        F acc = F::zero();
+        for (uint32_t t = 0; t <= degree; t++) {
+            F c = ldg32(vinv + j * (degree + 1) + t);
+            acc = add(acc, mul(c, slot_load<F>(sm, A.num_slots + t, blockDim.x)));
+        }
+        stg32(out + (size_t)(j - 1) * n + row, acc);
+    }
+}
+
+// W[i] = W1[i] + r * W2[i]      (accumulator.rs:366-378)
+template <class F>
+__global__ void k_axpy(const F* __restrict__ w1, const F* __restrict__ w2, F r, F* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    stg32(out + i, add(ldg32(w1 + i), mul(r, ldg32(w2 + i))));
+}
+
+// E[i] = E[i] + sum_{j=1..d} r^j * T_j[i]   (accumulator.rs:386-397), T contiguous [d][n], rpow = [r, r^2, ...]
+template <class F>
+__global__ void k_error_fold(const F* __restrict__ e, const F* __restrict__ T, const F* __restrict__ rpow, uint32_t d,
+                             F* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F acc = ldg32(e + i);
+    for (uint32_t j = 0; j < d; j++) acc = add(acc, mul(ldg32(rpow + j), ldg32(T + (size_t)j * n + i)));
+    stg32(out + i, acc);
+}
+
+}  // namespace sb
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using namespace sb;
+
+struct sb_prog {
+    int field;
+    uint32_t num_ops, num_slots, result_slot;
+    uint32_t num_constants, num_rotations;
+    void* d_ops;
+    void* d_constants;
+    void* d_rotations;
+    void* d_args;  // per-call tables: column pointer arrays, challenge table, Vandermonde inverse, r powers
+    size_t args_cap;
+    std::vector<uint32_t> poly_indices;  // distinct column indices the program reads (for validation)
+    uint32_t max_challenge;
+    bool uses_challenge;
+};
+
+struct sb_columns {
+    int field;
+    uint32_t log_rows;
+    uint32_t num_selectors, num_fixed;
+    void* d_data;            // selectors then fixed, contiguous
+    void* d_ptrs;            // [num_selectors + num_fixed] device pointers
+};
+
+namespace sb {
+
+template <class F>
+static void host_vandermonde_inverse(uint32_t degree, std::vector<F>& out) {
+    // Lagrange basis on the points 0..d:  L_t(X) = prod_{s != t} (X - s) / (t - s); column t of V^-1 holds the
+    // coefficients of L_t, i.e. coef_j = sum_t vinv[j][t] * P(t).
+    const uint32_t m = degree + 1;
+    auto from_u32 = [](uint32_t v) {
+        F x = F::zero();
+        x.v[0] = v;
+        return mul_portable(x, F::r_squared());
+    };
+    out.assign((size_t)m * m, F::zero());
+    for (uint32_t t = 0; t < m; t++) {
+        std::vector<F> poly(1, F::one());  // running product prod (X - s)
+        F denom = F::one();
+        for (uint32_t s = 0; s < m; s++) {
+            if (s == t) continue;
+            std::vector<F> next(poly.size() + 1, F::zero());
+            F neg_s = sub_portable(F::zero(), from_u32(s));
+            for (size_t k = 0; k < poly.size(); k++) {
+                next[k + 1] = add_portable(next[k + 1], poly[k]);
+                next[k] = add_portable(next[k], mul_portable(poly[k], neg_s));
+            }
+            poly.swap(next);
+            F diff = sub_portable(from_u32(t), from_u32(s));
+            denom = mul_portable(denom, diff);
+        }
+        // host-side inverse of a tiny constant (degree <= 15): Fermat on the portable path
+        F dinv = F::one();
+        {
+            F base = denom;
+            for (int i = 0; i < 8; i++) {
+                uint32_t e = F::modulus_limb(i) - (i == 0 ? 2u : 0u);
+                for (int bit = 0; bit < 32; bit++) {
+                    if ((e >> bit) & 1) dinv = mul_portable(dinv, base);
+                    base = mul_portable(base, base);
+                }
+            }
+        }
+        for (uint32_t j = 0; j < m; j++) out[(size_t)j * m + t] = mul_portable(poly[j], dinv);
+    }
+}
+
+static int args_reserve(sb_prog* p, size_t bytes) {
+    if (bytes <= p->args_cap) return SB_OK;
+    if (p->d_args) cudaFree(p->d_args);
+    p->d_args = nullptr;
+    p->args_cap = 0;
+    SB_CUDA_TRY(cudaMalloc(&p->d_args, bytes));
+    p->args_cap = bytes;
+    return SB_OK;
+}
+
+template <class F>
+static int fill_args(sb_prog* prog, sb_columns* cols, const void* const* adv1, const void* const* adv2, size_t nfv,
+                     EvalArgs<F>& A) {
+    A.ops = (const DevOp*)prog->d_ops;
+    A.num_ops = prog->num_ops;
+    A.num_slots = prog->num_slots;
+    A.result_slot = prog->result_slot;
+    A.constants = (const F*)prog->d_constants;
+    A.rotations = (const int32_t*)prog->d_rotations;
+    A.cols.log_rows = cols->log_rows;
+    A.cols.num_selectors = cols->num_selectors;
+    A.cols.num_fixed = cols->num_fixed;
+    A.cols.selectors = (const uint8_t* const*)cols->d_ptrs;
+    A.cols.fixed = (const void* const*)((char*)cols->d_ptrs + sizeof(void*) * cols->num_selectors);
+    A.num_fold_vars = (uint32_t)nfv;
+    (void)adv1;
+    (void)adv2;
+    return SB_OK;
+}
+
+// validates that every column the program touches exists
+static int validate_program(const sb_prog* prog, const sb_columns* cols, size_t nfv, bool have_adv2, size_t num_challenges) {
+    const size_t base = (size_t)cols->num_selectors + cols->num_fixed;
+    for (uint32_t idx : prog->poly_indices) {
+        if (idx < base) continue;
+        size_t a = idx - base;
+        if (a >= nfv * (have_adv2 ? 2 : 1)) {
+            set_error("expression reads column variable %u but only %zu fold variables were supplied (ColumnVariableIndexOutOfBoundary)", idx, nfv);
+            return SB_ERR_ARG;
+        }
+    }
+    if (prog->uses_challenge && prog->max_challenge >= num_challenges) {
+        set_error("challenge index out of boundary: %u (have %zu)", prog->max_challenge, num_challenges);
+        return SB_ERR_ARG;
+    }
+    return SB_OK;
+}
+
+template <class F>
+static int eval_enqueue(sb_prog* prog, sb_columns* cols, const void* const* h_adv1, const void* const* h_adv2, size_t nfv,
+                        const uint64_t* challenges, size_t num_challenges, void* d_out, cudaStream_t st) {
+    SB_TRY(validate_program(prog, cols, nfv, h_adv2 != nullptr, num_challenges));
+    const size_t ptr_bytes = align_up(sizeof(void*) * nfv * 2, 32);
+    const size_t ch_bytes = align_up(32 * (num_challenges ? num_challenges : 1), 32);
+    SB_TRY(args_reserve(prog, ptr_bytes + ch_bytes));
+    char* d = (char*)prog->d_args;
+    if (nfv) {
+        SB_CUDA_TRY(cudaMemcpyAsync(d, h_adv1, sizeof(void*) * nfv, cudaMemcpyHostToDevice, st));
+        if (h_adv2) SB_CUDA_TRY(cudaMemcpyAsync(d + sizeof(void*) * nfv, h_adv2, sizeof(void*) * nfv, cudaMemcpyHostToDevice, st));
+    }
+    if (num_challenges) SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes, challenges, 32 * num_challenges, cudaMemcpyHostToDevice, st));
+    EvalArgs<F> A;
+    SB_TRY(fill_args<F>(prog, cols, h_adv1, h_adv2, nfv, A));
+    A.adv1 = (const F* const*)d;
+    A.adv2 = h_adv2 ? (const F* const*)(d + sizeof(void*) * nfv) : nullptr;
+    A.challenges = (const F*)(d + ptr_bytes);
+    A.num_challenges = (uint32_t)num_challenges;
+    const uint32_t n = 1u << cols->log_rows;
+    const uint32_t threads = n < (uint32_t)EXPR_THREADS ? n : EXPR_THREADS;
+    const size_t smem = (size_t)(prog->num_slots ? prog->num_slots : 1) * 32 * threads;
+    if (smem > 200 * 1024) {
+        set_error("expression needs %u live intermediates: too many for shared memory", prog->num_slots);
+        return SB_ERR_ARG;
+    }
+    SB_CUDA_TRY(cudaFuncSetAttribute(k_expr_eval<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_expr_eval<F><<<(n + threads - 1) / threads, threads, smem, st>>>(A, (F*)d_out);
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+template <class F>
+static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols, const void* const* h_adv1,
+                               const void* const* h_adv2, size_t nfv, const uint64_t* ch1, const uint64_t* ch2,
+                               size_t num_challenges, void* d_out, cudaStream_t st) {
+    if (degree < 1 || degree > (uint32_t)EXPR_MAX_DEGREE) {
+        set_error("sb_cross_terms: degree %u out of range [1,%d]", degree, EXPR_MAX_DEGREE);
+        return SB_ERR_ARG;
+    }
+    SB_TRY(validate_program(prog, cols, nfv, false, num_challenges));
+    const uint32_t m = degree + 1;
+    const size_t ptr_bytes = align_up(sizeof(void*) * nfv * 2, 32);
+    const size_t ch_bytes = (size_t)32 * m * (num_challenges ? num_challenges : 1);
+    const size_t vinv_bytes = (size_t)32 * m * m;
+    SB_TRY(args_reserve(prog, ptr_bytes + ch_bytes + vinv_bytes));
+    char* d = (char*)prog->d_args;
+    // challenge table: c1 + t*c2 for t = 0..degree, built on the host with the portable field code
+    std::vector<F> table((size_t)m * (num_challenges ? num_challenges : 1));
+    for (size_t i = 0; i < num_challenges; i++) {
+        F c1, c2;
+        memcpy(c1.v, ch1 + 4 * i, 32);
+        memcpy(c2.v, ch2 + 4 * i, 32);
+        F cur = c1;
+        for (uint32_t t = 0; t < m; t++) {
+            table[(size_t)t * num_challenges + i] = cur;
+            cur = add_portable(cur, c2);
+        }
+    }
+    std::vector<F> vinv;
+    host_vandermonde_inverse<F>(degree, vinv);
+    if (nfv) {
+        SB_CUDA_TRY(cudaMemcpyAsync(d, h_adv1, sizeof(void*) * nfv, cudaMemcpyHostToDevice, st));
+        SB_CUDA_TRY(cudaMemcpyAsync(d + sizeof(void*) * nfv, h_adv2, sizeof(void*) * nfv, cudaMemcpyHostToDevice, st));
+    }
+    if (num_challenges) SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes, table.data(), 32 * table.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes + ch_bytes, vinv.data(), vinv_bytes, cudaMemcpyHostToDevice, st));
+    // the staging vectors die at return: pageable cudaMemcpyAsync has already copied them out
+    EvalArgs<F> A;
+    SB_TRY(fill_args<F>(prog, cols, h_adv1, h_adv2, nfv, A));
+    A.adv1 = (const F* const*)d;
+    A.adv2 = (const F* const*)(d + sizeof(void*) * nfv);
+    A.challenges = (const F*)(d + ptr_bytes);
+    A.num_challenges = (uint32_t)num_challenges;
+    const uint32_t n = 1u << cols->log_rows;
+    const uint32_t threads = n < (uint32_t)EXPR_THREADS ? n : EXPR_THREADS;
+    const size_t smem = (size_t)(prog->num_slots + m) * 32 * threads;
+    if (smem > 200 * 1024) {
+        set_error("expression needs %u live intermediates: too many for shared memory", prog->num_slots);
+        return SB_ERR_ARG;
+    }
+    SB_CUDA_TRY(cudaFuncSetAttribute(k_cross_terms<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_cross_terms<F><<<(n + threads - 1) / threads, threads, smem, st>>>(A, degree, (const F*)(d + ptr_bytes + ch_bytes), (F*)d_out);
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+// fold-variable index -> (round, column) : PlonkEvalDomain::eval_advice_var's index_map (src/plonk/eval.rs:170-204)
+static int fold_var_location(size_t index, size_t num_advice, size_t num_lookup, size_t num_witness, size_t* round, size_t* col) {
+    if (index < num_advice) {
+        *round = 0;
+        *col = index;
+        return SB_OK;
+    }
+    size_t li = (index - num_advice) / 5, sub = (index - num_advice) % 5;
+    bool first = sub < 3;
+    if (!first) sub -= 3;
+    if (num_witness == 2) {
+        if (first) { *round = 0; *col = num_advice + li * 3 + sub; }
+        else { *round = 1; *col = li * 2 + sub; }
+        return SB_OK;
+    }
+    if (num_witness == 3) {
+        if (first) { *round = 1; *col = li * 3 + sub; }
+        else { *round = 2; *col = li * 2 + sub; }
+        return SB_OK;
+    }
+    set_error("Invalid witness index. num_witness: %zu, num_advice: %zu, num_lookup: %zu, index: %zu", num_witness, num_advice, num_lookup, index);
+    return SB_ERR_ARG;
+}
+
+static Scratch g_expr_stage;
+
+}  // namespace sb
+
+extern "C" {
+
+int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint64_t* constants_mont, size_t n_constants,
+                    const int32_t* rotations, size_t n_rotations, sb_prog_t* out) {
+    if (!out || (!calcs && n_calcs) || (!constants_mont && n_constants) || (!rotations && n_rotations)) {
+        set_error("sb_expr_compile: null argument");
+        return SB_ERR_ARG;
+    }
+    if (field != FIELD_FR && field != FIELD_FQ) {
+        set_error("sb_expr_compile: unknown field %d", field);
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    // liveness: last reader of every intermediate
+    std::vector<long> last_use(n_calcs, -1);
+    std::vector<long> def_of(n_calcs, -1);  // target -> defining calc
+    for (size_t i = 0; i < n_calcs; i++) {
+        if (calcs[i].target >= n_calcs) {
+            set_error("sb_expr_compile: target %u out of range", calcs[i].target);
+            return SB_ERR_ARG;
+        }
+        def_of[calcs[i].target] = (long)i;
+    }
+    auto check_src = [&](uint32_t kind, uint32_t index, uint32_t rot, size_t at) -> int {
+        switch (kind) {
+            case VS_CONSTANT: if (index >= n_constants) { set_error("calc %zu: constant %u out of range", at, index); return SB_ERR_ARG; } break;
+            case VS_INTERMEDIATE:
+                if (index >= n_calcs || def_of[index] < 0 || def_of[index] >= (long)at) { set_error("calc %zu: intermediate %u used before definition", at, index); return SB_ERR_ARG; }
+                last_use[index] = (long)at;
+                break;
+            case VS_FIXED: case VS_POLY:
+                if (rot >= n_rotations || index >= (1u << 24) || n_rotations > 255) { set_error("calc %zu: rotation/column out of range", at); return SB_ERR_ARG; }
+                break;
+            case VS_CHALLENGE: break;
+            default: set_error("calc %zu: unknown value source %u", at, kind); return SB_ERR_ARG;
+        }
+        return SB_OK;
+    };
+    for (size_t i = 0; i < n_calcs; i++) {
+        const sb_calc& c = calcs[i];
+        if (c.opcode == OP_HORNER) {
+            set_error("sb_expr_compile: Calculation::Horner is never built by GraphEvaluator::add_expression and is not supported");
+            return SB_ERR_ARG;
+        }
+        if (c.opcode > OP_STORE) {
+            set_error("sb_expr_compile: unknown opcode %u", c.opcode);
+            return SB_ERR_ARG;
+        }
+        SB_TRY(check_src(c.a_kind, c.a_index, c.a_rot, i));
+        if (c.opcode <= OP_MUL) SB_TRY(check_src(c.b_kind, c.b_index, c.b_rot, i));
+    }
+    if (n_calcs) last_use[calcs[n_calcs - 1].target] = (long)n_calcs;  // the result stays live
+    // slot assignment
+    std::vector<uint32_t> slot_of(n_calcs, 0);
+    std::vector<uint32_t> free_slots;
+    uint32_t num_slots = 0;
+    std::vector<DevOp> ops(n_calcs);
+    sb_prog* p = new (std::nothrow) sb_prog();
+    if (!p) return SB_ERR_OOM;
+    p->max_challenge = 0;
+    p->uses_challenge = false;
+    auto enc = [&](uint32_t kind, uint32_t index, uint32_t rot) -> uint32_t {
+        if (kind == VS_INTERMEDIATE) return slot_of[index];
+        if (kind == VS_POLY || kind == VS_FIXED) {
+            if (kind == VS_POLY) p->poly_indices.push_back(index);
+            return index | (rot << 24);
+        }
+        if (kind == VS_CHALLENGE) {
+            p->uses_challenge = true;
+            if (index > p->max_challenge) p->max_challenge = index;
+        }
+        return index;
+    };
+    for (size_t i = 0; i < n_calcs; i++) {
+        const sb_calc& c = calcs[i];
+        const bool binary = c.opcode <= OP_MUL;
+        DevOp o;
+        o.code = c.opcode | ((uint32_t)c.a_kind << 8) | ((binary ? (uint32_t)c.b_kind : 0u) << 16);
+        o.a = enc(c.a_kind, c.a_index, c.a_rot);
+        o.b = binary ? enc(c.b_kind, c.b_index, c.b_rot) : 0;
+        // operands dying here release their slots before the destination is chosen
+        if (c.a_kind == VS_INTERMEDIATE && last_use[c.a_index] == (long)i) free_slots.push_back(slot_of[c.a_index]);
+        if (binary && c.b_kind == VS_INTERMEDIATE && last_use[c.b_index] == (long)i && !(c.a_kind == VS_INTERMEDIATE && c.a_index == c.b_index))
+            free_slots.push_back(slot_of[c.b_index]);
+        uint32_t s;
+        if (!free_slots.empty()) {
+            s = free_slots.back();
+            free_slots.pop_back();
+        } else {
+            s = num_slots++;
+        }
+        slot_of[c.target] = s;
+        o.dst = s;
+        ops[i] = o;
+        if (last_use[c.target] < 0) free_slots.push_back(s);  // never read (dead value)
+    }
+    p->field = field;
+    p->num_ops = (uint32_t)n_calcs;
+    p->num_slots = num_slots;
+    p->result_slot = n_calcs ? slot_of[calcs[n_calcs - 1].target] : 0;
+    p->num_constants = (uint32_t)n_constants;
+    p->num_rotations = (uint32_t)n_rotations;
+    p->d_ops = p->d_constants = p->d_rotations = p->d_args = nullptr;
+    p->args_cap = 0;
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaError_t e = cudaMalloc(&p->d_ops, sizeof(DevOp) * (n_calcs ? n_calcs : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_constants, 32 * (n_constants ? n_constants : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_rotations, 4 * (n_rotations ? n_rotations : 1));
+    if (e == cudaSuccess && n_calcs) e = cudaMemcpyAsync(p->d_ops, ops.data(), sizeof(DevOp) * n_calcs, cudaMemcpyHostToDevice, rt.stream);
+    if (e == cudaSuccess && n_constants) e = cudaMemcpyAsync(p->d_constants, constants_mont, 32 * n_constants, cudaMemcpyHostToDevice, rt.stream);
+    if (e == cudaSuccess && n_rotations) e = cudaMemcpyAsync(p->d_rotations, rotations, 4 * n_rotations, cudaMemcpyHostToDevice, rt.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
+    if (e != cudaSuccess) {
+        set_error("sb_expr_compile: %s", cudaGetErrorString(e));
+        sb_expr_free(p);
+        return SB_ERR_CUDA;
+    }
+    *out = p;
+    return SB_OK;
+}
+
+void sb_expr_free(sb_prog_t p) {
+    if (!p) return;
+    if (p->d_ops) cudaFree(p->d_ops);
+    if (p->d_constants) cudaFree(p->d_constants);
+    if (p->d_rotations) cudaFree(p->d_rotations);
+    if (p->d_args) cudaFree(p->d_args);
+    delete p;
+}
+
+uint32_t sb_expr_num_slots(sb_prog_t p) { return p ? p->num_slots : 0; }
+
+int sb_columns_register(int field, uint32_t log_rows, const uint8_t* const* selectors, size_t num_selectors,
+                        const uint64_t* const* fixed, size_t num_fixed, sb_columns_t* out) {
+    if (!out || (!selectors && num_selectors) || (!fixed && num_fixed) || log_rows > 30) {
+        set_error("sb_columns_register: bad argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    const size_t n = (size_t)1 << log_rows;
+    const size_t sel_bytes = align_up(n, 32);
+    const size_t total = sel_bytes * num_selectors + n * 32 * num_fixed;
+    sb_columns* c = new (std::nothrow) sb_columns();
+    if (!c) return SB_ERR_OOM;
+    c->field = field;
+    c->log_rows = log_rows;
+    c->num_selectors = (uint32_t)num_selectors;
+    c->num_fixed = (uint32_t)num_fixed;
+    c->d_data = c->d_ptrs = nullptr;
+    cudaError_t e = cudaMalloc(&c->d_data, total ? total : 32);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_ptrs, sizeof(void*) * (num_selectors + num_fixed + 1));
+    std::vector<void*> ptrs(num_selectors + num_fixed + 1, nullptr);
+    char* base = (char*)c->d_data;
+    for (size_t i = 0; i < num_selectors && e == cudaSuccess; i++) {
+        ptrs[i] = base + sel_bytes * i;
+        e = cudaMemcpyAsync(ptrs[i], selectors[i], n, cudaMemcpyHostToDevice, rt.stream);
+    }
+    base += sel_bytes * num_selectors;
+    for (size_t i = 0; i < num_fixed && e == cudaSuccess; i++) {
+        ptrs[num_selectors + i] = base + n * 32 * i;
+        e = cudaMemcpyAsync(ptrs[num_selectors + i], fixed[i], n * 32, cudaMemcpyHostToDevice, rt.stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_ptrs, ptrs.data(), sizeof(void*) * ptrs.size(), cudaMemcpyHostToDevice, rt.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
+    if (e != cudaSuccess) {
+        set_error("sb_columns_register: %s", cudaGetErrorString(e));
+        sb_columns_release(c);
+        return e == cudaErrorMemoryAllocation ? SB_ERR_OOM : SB_ERR_CUDA;
+    }
+    *out = c;
+    return SB_OK;
+}
+
+void sb_columns_release(sb_columns_t c) {
+    if (!c) return;
+    if (c->d_data) cudaFree(c->d_data);
+    if (c->d_ptrs) cudaFree(c->d_ptrs);
+    delete c;
+}
+
+int sb_expr_eval_device(sb_prog_t prog, sb_columns_t cols, const void* const* d_adv1_cols, const void* const* d_adv2_cols,
+                        size_t num_fold_vars, const uint64_t* challenges, size_t num_challenges, void* d_out, void* stream) {
+    if (!prog || !cols || !d_out || (!d_adv1_cols && num_fold_vars) || (!challenges && num_challenges)) {
+        set_error("sb_expr_eval_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    if (prog->field == FIELD_FR) return eval_enqueue<Fr>(prog, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges, num_challenges, d_out, st);
+    return eval_enqueue<Fq>(prog, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges, num_challenges, d_out, st);
+}
+
+int sb_cross_terms_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, const void* const* d_adv1_cols,
+                          const void* const* d_adv2_cols, size_t num_fold_vars, const uint64_t* challenges1,
+                          const uint64_t* challenges2, size_t num_challenges, void* d_out, void* stream) {
+    if (!prog || !cols || !d_out || ((!d_adv1_cols || !d_adv2_cols) && num_fold_vars) || ((!challenges1 || !challenges2) && num_challenges)) {
+        set_error("sb_cross_terms_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    if (prog->field == FIELD_FR)
+        return cross_terms_enqueue<Fr>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st);
+    return cross_terms_enqueue<Fq>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st);
+}
+
+// Host-memory front end used by the Rust shim: uploads the witness rounds, maps fold variables to columns as
+// PlonkEvalDomain does, runs the fused kernel, downloads T_1..T_d.
+static int stage_witness(const uint64_t* const* W, const size_t* lens, size_t rounds, size_t num_advice, size_t num_lookup,
+                         size_t n, char* d_base, size_t* d_off, std::vector<const void*>& col_ptrs, cudaStream_t st) {
+    std::vector<char*> round_base(rounds);
+    for (size_t r = 0; r < rounds; r++) {
+        round_base[r] = d_base + *d_off;
+        SB_CUDA_TRY(cudaMemcpyAsync(round_base[r], W[r], lens[r] * 32, cudaMemcpyHostToDevice, st));
+        *d_off += align_up(lens[r] * 32, 256);
+    }
+    const size_t nfv = num_advice + 5 * num_lookup;
+    col_ptrs.resize(nfv);
+    for (size_t i = 0; i < nfv; i++) {
+        size_t round = 0, col = 0;
+        if (rounds == 1 && i >= num_advice) {
+            set_error("Invalid witness index. num_witness: 1, num_advice: %zu, num_lookup: %zu, index: %zu", num_advice, num_lookup, i);
+            return SB_ERR_ARG;
+        }
+        if (rounds == 1) { round = 0; col = i; }
+        else SB_TRY(fold_var_location(i, num_advice, num_lookup, rounds, &round, &col));
+        if (round >= rounds || (col + 1) * n > lens[round]) {
+            set_error("Invalid witness index. num_witness: %zu, num_advice: %zu, num_lookup: %zu, index: %zu", rounds, num_advice, num_lookup, i);
+            return SB_ERR_ARG;
+        }
+        col_ptrs[i] = round_base[round] + col * n * 32;
+    }
+    return SB_OK;
+}
+
+int sb_cross_terms(sb_prog_t prog, uint32_t degree, sb_columns_t cols, uint32_t num_advice, uint32_t num_lookup,
+                   const uint64_t* const* W1, const size_t* W1_lens, size_t W1_rounds, const uint64_t* const* W2,
+                   const size_t* W2_lens, size_t W2_rounds, const uint64_t* challenges1, const uint64_t* challenges2,
+                   size_t num_challenges, uint64_t* const* out_T) {
+    if (!prog || !cols || !W1 || !W2 || !W1_lens || !W2_lens || !out_T) {
+        set_error("sb_cross_terms: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    const size_t n = (size_t)1 << cols->log_rows;
+    size_t bytes = 0;
+    for (size_t r = 0; r < W1_rounds; r++) bytes += align_up(W1_lens[r] * 32, 256);
+    for (size_t r = 0; r < W2_rounds; r++) bytes += align_up(W2_lens[r] * 32, 256);
+    const size_t out_off = bytes;
+    bytes += (size_t)degree * n * 32;
+    std::vector<const void*> p1, p2;
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_expr_stage.reserve(bytes));
+        size_t off = 0;
+        SB_TRY(stage_witness(W1, W1_lens, W1_rounds, num_advice, num_lookup, n, (char*)g_expr_stage.ptr, &off, p1, rt.stream));
+        SB_TRY(stage_witness(W2, W2_lens, W2_rounds, num_advice, num_lookup, n, (char*)g_expr_stage.ptr, &off, p2, rt.stream));
+    }
+    char* d_out = (char*)g_expr_stage.ptr + out_off;
+    SB_TRY(sb_cross_terms_device(prog, degree, cols, p1.data(), p2.data(), p1.size(), challenges1, challenges2, num_challenges, d_out, nullptr));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    for (uint32_t j = 0; j < degree; j++)
+        SB_CUDA_TRY(cudaMemcpyAsync(out_T[j], d_out + (size_t)j * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
+}
+
+int sb_expr_eval(sb_prog_t prog, sb_columns_t cols, uint32_t num_advice, uint32_t num_lookup, const uint64_t* const* W1,
+                 const size_t* W1_lens, size_t W1_rounds, const uint64_t* const* W2, const size_t* W2_lens, size_t W2_rounds,
+                 const uint64_t* challenges, size_t num_challenges, uint64_t* out) {
+    if (!prog || !cols || !W1 || !W1_lens || !out) {
+        set_error("sb_expr_eval: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    const size_t n = (size_t)1 << cols->log_rows;
+    size_t bytes = 0;
+    for (size_t r = 0; r < W1_rounds; r++) bytes += align_up(W1_lens[r] * 32, 256);
+    if (W2) for (size_t r = 0; r < W2_rounds; r++) bytes += align_up(W2_lens[r] * 32, 256);
+    const size_t out_off = bytes;
+    bytes += n * 32;
+    std::vector<const void*> p1, p2;
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_expr_stage.reserve(bytes));
+        size_t off = 0;
+        SB_TRY(stage_witness(W1, W1_lens, W1_rounds, num_advice, num_lookup, n, (char*)g_expr_stage.ptr, &off, p1, rt.stream));
+        if (W2) SB_TRY(stage_witness(W2, W2_lens, W2_rounds, num_advice, num_lookup, n, (char*)g_expr_stage.ptr, &off, p2, rt.stream));
+    }
+    char* d_out = (char*)g_expr_stage.ptr + out_off;
+    SB_TRY(sb_expr_eval_device(prog, cols, p1.data(), W2 ? p2.data() : nullptr, p1.size(), challenges, num_challenges, d_out, nullptr));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    SB_CUDA_TRY(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
+}
+
+// ---- folds -------------------------------------------------------------------------------------------
+
+int sb_axpy_fold_device(int field, const void* d_w1, const void* d_w2, const uint64_t r[4], void* d_out, size_t n, void* stream) {
+    if ((!d_w1 || !d_w2 || !d_out) && n) {
+        set_error("sb_axpy_fold_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    if (!n) return SB_OK;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (field == FIELD_FR) {
+        Fr rr;
+        memcpy(rr.v, r, 32);
+        k_axpy<Fr><<<blocks, 256, 0, st>>>((const Fr*)d_w1, (const Fr*)d_w2, rr, (Fr*)d_out, n);
+    } else {
+        Fq rr;
+        memcpy(rr.v, r, 32);
+        k_axpy<Fq><<<blocks, 256, 0, st>>>((const Fq*)d_w1, (const Fq*)d_w2, rr, (Fq*)d_out, n);
+    }
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+static Scratch g_fold_consts;
+
+int sb_error_fold_device(int field, const void* d_e, const void* d_T, uint32_t d, const uint64_t r[4], void* d_out, size_t n, void* stream) {
+    if ((!d_e || !d_T || !d_out) && n) {
+        set_error("sb_error_fold_device: null argument");
+        return SB_ERR_ARG;
+    }
+    if (d > 64) {
+        set_error("sb_error_fold_device: too many cross terms (%u)", d);
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    if (!n) return SB_OK;
+    SB_TRY(g_fold_consts.reserve(64 * 32));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (field == FIELD_FR) {
+        Fr rr, pw[64];
+        memcpy(rr.v, r, 32);
+        Fr cur = rr;
+        for (uint32_t j = 0; j < d; j++) { pw[j] = cur; cur = mul_portable(cur, rr); }  // r^1, r^2, ... (accumulator.rs:382-385)
+        SB_CUDA_TRY(cudaMemcpyAsync(g_fold_consts.ptr, pw, 32 * (d ? d : 1), cudaMemcpyHostToDevice, st));
+        k_error_fold<Fr><<<blocks, 256, 0, st>>>((const Fr*)d_e, (const Fr*)d_T, (const Fr*)g_fold_consts.ptr, d, (Fr*)d_out, n);
+    } else {
+        Fq rr, pw[64];
+        memcpy(rr.v, r, 32);
+        Fq cur = rr;
+        for (uint32_t j = 0; j < d; j++) { pw[j] = cur; cur = mul_portable(cur, rr); }
+        SB_CUDA_TRY(cudaMemcpyAsync(g_fold_consts.ptr, pw, 32 * (d ? d : 1), cudaMemcpyHostToDevice, st));
+        k_error_fold<Fq><<<blocks, 256, 0, st>>>((const Fq*)d_e, (const Fq*)d_T, (const Fq*)g_fold_consts.ptr, d, (Fq*)d_out, n);
+    }
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+static Scratch g_fold_stage;
+
+// RelaxedPlonkWitness::fold on host vectors: out_w = w1 + r*w2 (n_w elements); out_e = e + sum r^j T_j (n_e rows)
+int sb_axpy_fold(int field, const uint64_t* w1, const uint64_t* w2, const uint64_t r[4], uint64_t* out, size_t n) {
+    if ((!w1 || !w2 || !out) && n) {
+        set_error("sb_axpy_fold: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_fold_stage.reserve(n * 96 + 96));
+        SB_CUDA_TRY(cudaMemcpyAsync(g_fold_stage.ptr, w1, n * 32, cudaMemcpyHostToDevice, rt.stream));
+        SB_CUDA_TRY(cudaMemcpyAsync((char*)g_fold_stage.ptr + n * 32, w2, n * 32, cudaMemcpyHostToDevice, rt.stream));
+    }
+    char* d = (char*)g_fold_stage.ptr;
+    SB_TRY(sb_axpy_fold_device(field, d, d + n * 32, r, d + n * 64, n, nullptr));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    SB_CUDA_TRY(cudaMemcpyAsync(out, d + n * 64, n * 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
+}
+
+int sb_error_fold(int field, const uint64_t* e, const uint64_t* const* T, uint32_t d, const uint64_t r[4], uint64_t* out, size_t n) {
+    if ((!e || !out || (!T && d)) && n) {
+        set_error("sb_error_fold: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_fold_stage.reserve(n * 32 * (d + 2) + 96));
+        char* dptr = (char*)g_fold_stage.ptr;
+        SB_CUDA_TRY(cudaMemcpyAsync(dptr, e, n * 32, cudaMemcpyHostToDevice, rt.stream));
+        for (uint32_t j = 0; j < d; j++)
+            SB_CUDA_TRY(cudaMemcpyAsync(dptr + (size_t)(j + 1) * n * 32, T[j], n * 32, cudaMemcpyHostToDevice, rt.stream));
+    }
+    char* dptr = (char*)g_fold_stage.ptr;
+    SB_TRY(sb_error_fold_device(field, dptr, dptr + n * 32, d, r, dptr + (size_t)(d + 1) * n * 32, n, nullptr));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    SB_CUDA_TRY(cudaMemcpyAsync(out, dptr + (size_t)(d + 1) * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
+}
+
+}  // extern "C"

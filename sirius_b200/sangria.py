@@ -1,0 +1,169 @@
+"""Mirror of the Sangria NIFS prover steps that sit on the hot path (reference src/nifs/sangria).
+
+    PlonkStructure (the fields the hot path reads)      src/plonk/mod.rs:127-193
+    VanillaFS.commit_cross_terms(ck, S, U1, W1, U2, W2) src/nifs/sangria/mod.rs:102-158
+    RelaxedPlonkWitness.fold(W2, cross_terms, r)        src/nifs/sangria/accumulator.rs:363-404
+
+Witness round vectors are uint64 [len,4] Montgomery arrays, column-major as `concatenate_with_padding` lays
+them out (src/util/mod.rs:214-218).  Challenges / u / r are uint64[4] Montgomery limbs or lists thereof.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import numpy as np
+
+from . import _lib
+from .commitment import CommitmentKey
+from .polynomial import (
+    OP_MUL,
+    CompressedGates,
+    GraphEvaluator,
+)
+
+
+def _to_mont(vals: Sequence[int], modulus: int) -> np.ndarray:
+    out = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        m = (v % modulus) * (1 << 256) % modulus
+        for k in range(4):
+            out[i, k] = (m >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+class Program:
+    """A GraphEvaluator uploaded through sb_expr_compile."""
+
+    def __init__(self, field: int, ev: GraphEvaluator):
+        lib = _lib.load()
+        calcs = (_lib.sb_calc * max(1, len(ev.calculations)))()
+        for i, (op, a, b, target) in enumerate(ev.calculations):
+            c = calcs[i]
+            c.opcode, c.a_kind, c.a_index, c.a_rot = op, a[0], a[1], a[2]
+            if b is not None and op <= OP_MUL:
+                c.b_kind, c.b_index, c.b_rot = b
+            c.target = target
+        consts = _to_mont(ev.constants, ev.modulus)
+        rots = np.array(ev.rotations if ev.rotations else [0], dtype=np.int32)
+        self.field = field
+        self._h = ctypes.c_void_p()
+        _lib.check(
+            lib.sb_expr_compile(
+                field, ctypes.cast(calcs, ctypes.c_void_p), len(ev.calculations), consts.ctypes.data_as(_lib.u64p), len(ev.constants),
+                rots.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(ev.rotations), ctypes.byref(self._h),
+            )
+        )
+
+    @property
+    def num_slots(self) -> int:
+        return int(_lib.load().sb_expr_num_slots(self._h))
+
+    def close(self):
+        if self._h.value:
+            _lib.load().sb_expr_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class PlonkStructure:
+    """Fields of reference PlonkStructure read by commit_cross_terms / fold (src/plonk/mod.rs:127-193)."""
+
+    field: int
+    modulus: int
+    k: int
+    selectors: List[np.ndarray]          # Vec<Vec<bool>> as uint8 [2^k]
+    fixed_columns: List[np.ndarray]      # Vec<Vec<F>>   as uint64 [2^k,4]
+    num_advice_columns: int
+    num_lookups: int
+    custom_gates_lookup_compressed: CompressedGates
+
+    def __post_init__(self):
+        lib = _lib.load()
+        self.selectors = [np.ascontiguousarray(s, dtype=np.uint8) for s in self.selectors]
+        self.fixed_columns = [np.ascontiguousarray(f, dtype=np.uint64).reshape(-1, 4) for f in self.fixed_columns]
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        sel = (u8p * max(1, len(self.selectors)))(*[s.ctypes.data_as(u8p) for s in self.selectors])
+        fx = (_lib.u64p * max(1, len(self.fixed_columns)))(*[f.ctypes.data_as(_lib.u64p) for f in self.fixed_columns])
+        self._cols = ctypes.c_void_p()
+        _lib.check(lib.sb_columns_register(self.field, self.k, sel, len(self.selectors), fx, len(self.fixed_columns), ctypes.byref(self._cols)))
+        # GraphEvaluator::new(homogeneous) -- what the Rust shim compiles once per structure
+        self._hom_prog = Program(self.field, GraphEvaluator.new(self.custom_gates_lookup_compressed.homogeneous, self.modulus))
+
+    @property
+    def degree(self) -> int:
+        """number of cross terms = grouped().len() - 1 (src/plonk/mod.rs:399)"""
+        return self.custom_gates_lookup_compressed.degree
+
+    def close(self):
+        if getattr(self, "_cols", None) is not None and self._cols.value:
+            _lib.load().sb_columns_release(self._cols)
+            self._cols = ctypes.c_void_p()
+        if getattr(self, "_hom_prog", None) is not None:
+            self._hom_prog.close()
+
+
+def _rounds(W: Sequence[np.ndarray]):
+    arrs = [np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4) for w in W]
+    ptrs = (_lib.u64p * len(arrs))(*[a.ctypes.data_as(_lib.u64p) for a in arrs])
+    lens = (ctypes.c_size_t * len(arrs))(*[a.shape[0] for a in arrs])
+    return arrs, ptrs, lens
+
+
+class VanillaFS:
+    @staticmethod
+    def commit_cross_terms(ck: CommitmentKey, S: PlonkStructure, U1_challenges, U1_u, W1: Sequence[np.ndarray], U2_challenges,
+                           W2: Sequence[np.ndarray]):
+        """-> (cross_terms: list of uint64 [2^k,4], cross_term_commits: uint64 [d,8]).
+        challenges = U1.challenges ++ [U1.u] and U2.challenges ++ [1] (src/nifs/sangria/mod.rs:113-118)."""
+        lib = _lib.load()
+        one = _to_mont([1], S.modulus)
+        c1 = np.concatenate([np.asarray(U1_challenges, dtype=np.uint64).reshape(-1, 4), np.asarray(U1_u, dtype=np.uint64).reshape(1, 4)])
+        c2 = np.concatenate([np.asarray(U2_challenges, dtype=np.uint64).reshape(-1, 4), one])
+        c1, c2 = np.ascontiguousarray(c1), np.ascontiguousarray(c2)
+        a1, p1, l1 = _rounds(W1)
+        a2, p2, l2 = _rounds(W2)
+        n = 1 << S.k
+        d = S.degree
+        T = [np.zeros((n, 4), dtype=np.uint64) for _ in range(d)]
+        outp = (_lib.u64p * d)(*[t.ctypes.data_as(_lib.u64p) for t in T])
+        _lib.check(
+            lib.sb_cross_terms(
+                S._hom_prog._h, d, S._cols, S.num_advice_columns, S.num_lookups, p1, l1, len(a1), p2, l2, len(a2),
+                c1.ctypes.data_as(_lib.u64p), c2.ctypes.data_as(_lib.u64p), c1.shape[0], outp,
+            )
+        )
+        commits = ck.commit_batch(T)  # cross_terms.iter().map(|v| ck.commit(v)) (:151-154)
+        return T, commits
+
+
+class RelaxedPlonkWitness:
+    """W: round vectors, E: error vector (src/nifs/sangria/accumulator.rs:273-276, 488)."""
+
+    def __init__(self, field: int, W: Sequence[np.ndarray], E: np.ndarray):
+        self.field = field
+        self.W = [np.ascontiguousarray(w, dtype=np.uint64).reshape(-1, 4) for w in W]
+        self.E = np.ascontiguousarray(E, dtype=np.uint64).reshape(-1, 4)
+
+    def fold(self, W2: Sequence[np.ndarray], cross_terms: Sequence[np.ndarray], r) -> "RelaxedPlonkWitness":
+        lib = _lib.load()
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        Wn = []
+        for w1, w2 in zip(self.W, W2):
+            w2 = np.ascontiguousarray(w2, dtype=np.uint64).reshape(-1, 4)
+            assert w1.shape == w2.shape, "zip_eq"
+            out = np.zeros_like(w1)
+            _lib.check(lib.sb_axpy_fold(self.field, w1.ctypes.data_as(_lib.u64p), w2.ctypes.data_as(_lib.u64p), r.ctypes.data_as(_lib.u64p), out.ctypes.data_as(_lib.u64p), w1.shape[0]))
+            Wn.append(out)
+        Ts = [np.ascontiguousarray(t, dtype=np.uint64).reshape(-1, 4) for t in cross_terms]
+        ptrs = (_lib.u64p * max(1, len(Ts)))(*[t.ctypes.data_as(_lib.u64p) for t in Ts])
+        En = np.zeros_like(self.E)
+        _lib.check(lib.sb_error_fold(self.field, self.E.ctypes.data_as(_lib.u64p), ptrs, len(Ts), r.ctypes.data_as(_lib.u64p), En.ctypes.data_as(_lib.u64p), self.E.shape[0]))
+        return RelaxedPlonkWitness(self.field, Wn, En)

@@ -1,0 +1,88 @@
+"""CPU tests of the host-side mirror: expression compile parity with the oracle's literal restatement, the
+C-ABI library exports, and the header/binding agreement.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+from oracle import expr_ref as E
+from oracle import pyref as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _to_oracle(e):
+    k = e.kind
+    if k == "const":
+        return E.Const(e.a)
+    if k == "poly":
+        return E.Poly(e.a, e.b)
+    if k == "chal":
+        return E.Chal(e.a)
+    if k == "neg":
+        return E.Neg(_to_oracle(e.a))
+    if k == "sum":
+        return E.Sum(_to_oracle(e.a), _to_oracle(e.b))
+    if k == "prod":
+        return E.Mul(_to_oracle(e.a), _to_oracle(e.b))
+    if k == "scaled":
+        return E.Scaled(_to_oracle(e.a), e.b)
+    raise ValueError(k)
+
+
+def test_main_gate_and_homogeneous_match_oracle():
+    from sirius_b200 import polynomial as P
+
+    for T_list in ([2], [5], [5, 3]):
+        nfix = sum(2 * T + 5 for T in T_list)
+        nadv = sum(T + 2 for T in T_list)
+        gates_p, gates_o, fb, ab = [], [], 0, 0
+        for T in T_list:
+            gates_p.append(P.main_gate_expression(T, fb, ab, 0, nfix))
+            gates_o.append(E.main_gate_expression(T, fb, ab, 0, nfix))
+            fb += 2 * T + 5
+            ab += T + 2
+        for gp, go in zip(gates_p, gates_o):
+            assert _to_oracle(gp) == go
+        cp = P.CompressedGates.new(gates_p, P.QueryIndexContext(num_fixed=nfix, num_advice=nadv))
+        co = E.CompressedGates(gates_o, E.Ctx(num_fixed=nfix, num_advice=nadv))
+        assert _to_oracle(cp.homogeneous) == co.homogeneous
+        assert cp.degree == co.degree == (5 if len(T_list) == 1 else 6)
+        assert cp.ctx.num_challenges == co.ctx.num_challenges
+        # compiled calculation lists are identical too (same CSE, same operand ordering)
+        gp = P.GraphEvaluator.new(cp.homogeneous, R.FR)
+        go = E.GraphEvaluator(co.homogeneous, R.FR)
+        assert gp.constants == go.constants and gp.rotations == go.rotations
+        assert [(o, a, b, t) for o, a, b, t in gp.calculations] == go.calcs
+
+
+def test_library_exports_every_declared_symbol():
+    """include/sirius_b200.h <-> libsirius_b200.so <-> the ctypes table."""
+    from sirius_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "sirius_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import numpy as np
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sirius_b200
+
+    with pytest.raises(sirius_b200.SiriusB200Error):
+        sirius_b200.CommitmentKey(0, np.zeros((4, 8), dtype=np.uint64))
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sirius_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "sirius_oracle" not in src, f
