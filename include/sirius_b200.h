@@ -100,6 +100,9 @@ int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t
 /* Multi-GPU combine: sum `count` XYZZ partials (device, 128 B each) and normalise to affine. */
 int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, void* d_out_xy, void* stream);
 
+/* Synthetic commitment key used by the benches: d_out[i] = [first + i + 1] * G, affine. */
+int sb_index_multiples_device(int curve, const uint64_t gen_xy[8], uint64_t first, size_t n, void* d_out_xy, void* stream);
+
 /* ---- gate evaluation, Sangria cross terms, folds ------------------------------------------------------ */
 
 /* Upload a compiled GraphEvaluator (calculations, constants incl. the leading [0,1,2], rotations). */
@@ -156,6 +159,11 @@ int sb_ntt_device(int field, void* d_a, uint32_t log_n, const uint64_t omega[4],
  * coset_fft passes (ZETA, ZETA^2), coset_ifft passes (ZETA^2, ZETA). */
 int sb_coset_scale(int field, uint64_t* a, size_t n, const uint64_t z[4], const uint64_t z2[4]);
 int sb_coset_scale_device(int field, void* d_a, size_t n, const uint64_t z[4], const uint64_t z2[4], void* stream);
+
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------- */
+uint64_t sb_launch_count(void);  /* kernels launched by this library so far */
+void sb_profile_enable(int on);  /* CUDA events around the MSM bucket-accumulation kernel */
+int sb_profile_collect(double* total_ms, uint64_t* total_points, uint64_t* launches);
 
 /* ---- self test hooks used by tests/ (device arithmetic vs its portable twin) ----------------------- */
 int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul_ptx,

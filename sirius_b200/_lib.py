@@ -39,6 +39,7 @@ SIGNATURES = {
     "sb_msm_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, vp, vp, vp]),
     "sb_msm_batch": (ctypes.c_int, [vp, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p]),
     "sb_msm_batch_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp]),
+    "sb_index_multiples_device": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint64, ctypes.c_size_t, vp, vp]),
     "sb_msm_combine_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
     "sb_expr_compile": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32), ctypes.c_size_t, ctypes.POINTER(vp)]),
     "sb_expr_free": (None, [vp]),
@@ -57,6 +58,9 @@ SIGNATURES = {
     "sb_ntt_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint32, u64p, u64p, vp]),
     "sb_coset_scale": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p, u64p]),
     "sb_coset_scale_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, u64p, u64p, vp]),
+    "sb_launch_count": (ctypes.c_uint64, []),
+    "sb_profile_enable": (None, [ctypes.c_int]),
+    "sb_profile_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "sb_selftest_field": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p, u64p]),
 }
 

@@ -12,6 +12,13 @@
 namespace sb {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+
+// Optional CUDA-event instrumentation of the dominant kernel (MSM bucket accumulation), used by bench.py to
+// report the roofline of that kernel from inside the timed region.
+bool profile_enabled();
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st, uint64_t units);
 
 #define SB_CUDA_TRY(expr)                                                                         \
     do {                                                                                          \
@@ -28,7 +35,12 @@ void set_error(const char* fmt, ...);
         if (_rc != SB_OK) return _rc; \
     } while (0)
 
-#define SB_KERNEL_CHECK() SB_CUDA_TRY(cudaGetLastError())
+// every kernel launch of this library goes through here: counts launches (bench.py's gpu_launches)
+#define SB_KERNEL_CHECK()                   \
+    do {                                    \
+        sb::count_launch();                 \
+        SB_CUDA_TRY(cudaGetLastError());    \
+    } while (0)
 
 // Library-wide state for the device this process drives (one process per GPU).
 struct Runtime {

@@ -18,6 +18,7 @@
 //
 // Roofline: the work is ~W mixed additions per scalar (8M+2S 254-bit Montgomery products each) -- integer-pipe
 // bound; algorithmic HBM traffic is 96 B/point.
+#include <string.h>
 #include <algorithm>
 #include <new>
 
@@ -128,6 +129,25 @@ __global__ void k_precompute(const Affine<F>* __restrict__ bases, size_t n, int 
         Affine<F> q = xyzz_to_affine<false>(acc);
         store_vec(table + (size_t)w * n + i, q);
     }
+}
+
+// Synthetic key: out[i] = [first + i + 1] * G (the benches' stand-in for CommitmentKey::setup, whose
+// hash_to_curve lives in the un-vendored halo2curves).  One thread per point: double-and-add on
+// the index, then normalise.
+template <class F>
+__global__ void k_index_multiples(Affine<F> g, uint64_t first, size_t n, Affine<F>* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s = first + i + 1;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (int bit = 63 - __clzll((long long)s); bit >= 0; bit--) {
+        acc = xyzz_double<false>(acc);
+        if ((s >> bit) & 1) {
+            XYZZ<F> gg = XYZZ<F>::from_affine(g);
+            xyzz_add<false>(acc, gg);
+        }
+    }
+    store_vec(out + i, xyzz_to_affine<false>(acc));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -610,7 +630,9 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     SB_KERNEL_CHECK();
     {
         size_t blocks = (p.chunks + 127) / 128;
+        profile_begin(st);
         k_accumulate<F><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+        profile_end(st, p.total);
         SB_KERNEL_CHECK();
     }
     k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(offsets, KB, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
@@ -812,6 +834,32 @@ int sb_msm(sb_ck_t ck, const uint64_t* scalars_mont, size_t n, uint64_t out_xy[8
     }
     const uint64_t* one[1] = {scalars_mont};
     return sb_msm_batch(ck, one, n, 1, out_xy);
+}
+
+int sb_index_multiples_device(int curve, const uint64_t gen_xy[8], uint64_t first, size_t n, void* d_out_xy, void* stream) {
+    if (!gen_xy || (!d_out_xy && n)) {
+        set_error("sb_index_multiples_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    if (!n) return SB_OK;
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (curve == CURVE_BN256) {
+        Affine<Fq> g;
+        memcpy(&g, gen_xy, 64);
+        k_index_multiples<Fq><<<blocks, 128, 0, st>>>(g, first, n, (Affine<Fq>*)d_out_xy);
+    } else if (curve == CURVE_GRUMPKIN) {
+        Affine<Fr> g;
+        memcpy(&g, gen_xy, 64);
+        k_index_multiples<Fr><<<blocks, 128, 0, st>>>(g, first, n, (Affine<Fr>*)d_out_xy);
+    } else {
+        set_error("sb_index_multiples_device: unknown curve %d", curve);
+        return SB_ERR_ARG;
+    }
+    SB_KERNEL_CHECK();
+    return SB_OK;
 }
 
 int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, void* d_out_xy, void* stream) {

@@ -1,6 +1,9 @@
 // runtime.cu -- device selection, error strings, scratch memory, and the on-device arithmetic self test.
 #include <string.h>
 
+#include <atomic>
+#include <vector>
+
 #include "common.cuh"
 #include "curve.cuh"
 
@@ -13,6 +16,33 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfileRec { cudaEvent_t e0, e1; uint64_t units; };
+static bool g_profile = false;
+static std::vector<ProfileRec> g_prof;
+static std::vector<ProfileRec> g_prof_pool;
+static ProfileRec g_prof_cur;
+bool profile_enabled() { return g_profile; }
+void profile_begin(cudaStream_t st) {
+    if (!g_profile) return;
+    if (!g_prof_pool.empty()) {
+        g_prof_cur = g_prof_pool.back();
+        g_prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&g_prof_cur.e0);
+        cudaEventCreate(&g_prof_cur.e1);
+    }
+    cudaEventRecord(g_prof_cur.e0, st);
+}
+void profile_end(cudaStream_t st, uint64_t units) {
+    if (!g_profile) return;
+    cudaEventRecord(g_prof_cur.e1, st);
+    g_prof_cur.units = units;
+    g_prof.push_back(g_prof_cur);
 }
 
 Runtime& runtime() {
@@ -113,6 +143,34 @@ extern "C" {
 
 const char* sb_last_error(void) { return g_err; }
 int sb_version(void) { return 1; }
+
+uint64_t sb_launch_count(void) { return g_launches.load(); }
+
+void sb_profile_enable(int on) { g_profile = on != 0; }
+
+/* Sum of the instrumented kernel's launch durations since the last call (synchronises the recorded events). */
+int sb_profile_collect(double* total_ms, uint64_t* total_units, uint64_t* launches) {
+    double ms = 0;
+    uint64_t units = 0, n = 0;
+    for (auto& rec : g_prof) {
+        cudaError_t e = cudaEventSynchronize(rec.e1);
+        float t = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, rec.e0, rec.e1);
+        if (e != cudaSuccess) {
+            set_error("sb_profile_collect: %s", cudaGetErrorString(e));
+            return SB_ERR_CUDA;
+        }
+        ms += t;
+        units += rec.units;
+        n++;
+        g_prof_pool.push_back(rec);
+    }
+    g_prof.clear();
+    if (total_ms) *total_ms = ms;
+    if (total_units) *total_units = units;
+    if (launches) *launches = n;
+    return SB_OK;
+}
 
 int sb_device_count(void) {
     int count = 0;

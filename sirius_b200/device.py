@@ -1,0 +1,129 @@
+"""Device-resident Sangria prover state: the accumulator witness W, the error vector E, the fixed
+columns and the commitment key stay in HBM across fold steps; per step only the fresh witness columns go host ->
+device and the 64-byte commitments come back (each must reach the host before the next challenge can be
+squeezed -- src/plonk/mod.rs:537-545, src/nifs/sangria/mod.rs:171-178).
+
+torch is used here for device memory, pinned host buffers and streams only; every computation is a call
+through the C ABI (`*_device` entry points).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .commitment import CommitmentKey
+from .sangria import PlonkStructure, _to_mont
+
+
+def _vp_array(ptrs: List[int]):
+    return (ctypes.c_void_p * max(1, len(ptrs)))(*ptrs)
+
+
+class DeviceSangriaSide:
+    """One curve of the cycle: relaxed accumulator (W, E) + the incoming trace's W, single witness round."""
+
+    def __init__(self, S: PlonkStructure, ck: CommitmentKey, stream):
+        import torch
+
+        self.torch = torch
+        self.S, self.ck, self.stream = S, ck, stream
+        self.n = 1 << S.k
+        self.A = S.num_advice_columns
+        self.d = S.degree
+        dev = torch.device("cuda", torch.cuda.current_device())
+        i64 = torch.int64
+        self.W_acc = torch.zeros((self.A * self.n, 4), dtype=i64, device=dev)
+        self.W_new = torch.zeros_like(self.W_acc)
+        self.W_in = torch.zeros_like(self.W_acc)
+        self.E_acc = torch.zeros((self.n, 4), dtype=i64, device=dev)
+        self.E_new = torch.zeros_like(self.E_acc)
+        self.T = torch.zeros((self.d, self.n, 4), dtype=i64, device=dev)
+        self.commit_W = torch.zeros(8, dtype=i64, device=dev)
+        self.commit_T = torch.zeros((self.d, 8), dtype=i64, device=dev)
+        self.h_commit_W = torch.zeros(8, dtype=i64).pin_memory()
+        self.h_commit_T = torch.zeros((self.d, 8), dtype=i64).pin_memory()
+        self.one = _to_mont([1], S.modulus)
+
+    # ---- data movement
+    def upload_incoming(self, host_W_pinned) -> int:
+        """H2D of the fresh witness round (pinned host tensor int64 [A*n,4]); returns bytes copied."""
+        with self.torch.cuda.stream(self.stream):
+            self.W_in.copy_(host_W_pinned, non_blocking=True)
+        return host_W_pinned.numel() * 8
+
+    def _cols(self, t):
+        base = t.data_ptr()
+        return _vp_array([base + j * self.n * 32 for j in range(self.A)])
+
+    # ---- PlonkStructure::run_sps_protocol's commit (src/plonk/mod.rs:441-445)
+    def commit_incoming(self) -> np.ndarray:
+        st = self.stream.cuda_stream
+        self.ck.commit_device(self.W_in.data_ptr(), self.A * self.n, self.commit_W.data_ptr(), 0, st)
+        with self.torch.cuda.stream(self.stream):
+            self.h_commit_W.copy_(self.commit_W, non_blocking=True)
+        self.stream.synchronize()  # the commitment is absorbed by the host-side random oracle
+        return self.h_commit_W.numpy().view(np.uint64).copy()
+
+    # ---- VanillaFS::prove (src/nifs/sangria/mod.rs:253-277) split at the challenge
+    def commit_cross_terms(self, U1_challenges: np.ndarray, U1_u: np.ndarray, U2_challenges: np.ndarray) -> np.ndarray:
+        lib = _lib.load()
+        st = self.stream.cuda_stream
+        c1 = np.ascontiguousarray(np.concatenate([U1_challenges.reshape(-1, 4), U1_u.reshape(1, 4)]), dtype=np.uint64)
+        c2 = np.ascontiguousarray(np.concatenate([U2_challenges.reshape(-1, 4), self.one]), dtype=np.uint64)
+        _lib.check(
+            lib.sb_cross_terms_device(
+                self.S._hom_prog._h, self.d, self.S._cols, self._cols(self.W_acc), self._cols(self.W_in), self.A,
+                c1.ctypes.data_as(_lib.u64p), c2.ctypes.data_as(_lib.u64p), c1.shape[0], ctypes.c_void_p(self.T.data_ptr()), ctypes.c_void_p(st),
+            )
+        )
+        self.ck.commit_batch_device(self.T.data_ptr(), self.n, self.n, self.d, self.commit_T.data_ptr(), 0, st)
+        with self.torch.cuda.stream(self.stream):
+            self.h_commit_T.copy_(self.commit_T, non_blocking=True)
+        self.stream.synchronize()  # cross-term commitments feed generate_challenge (:162-179)
+        return self.h_commit_T.numpy().view(np.uint64).copy()
+
+    def fold(self, r: np.ndarray) -> None:
+        """W <- W + r*W_in ; E <- E + sum r^j T_j   (accumulator.rs:363-404); buffers are swapped, not copied."""
+        lib = _lib.load()
+        st = self.stream.cuda_stream
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        f = self.S.field
+        _lib.check(lib.sb_axpy_fold_device(f, ctypes.c_void_p(self.W_acc.data_ptr()), ctypes.c_void_p(self.W_in.data_ptr()), r.ctypes.data_as(_lib.u64p),
+                                           ctypes.c_void_p(self.W_new.data_ptr()), self.A * self.n, ctypes.c_void_p(st)))
+        _lib.check(lib.sb_error_fold_device(f, ctypes.c_void_p(self.E_acc.data_ptr()), ctypes.c_void_p(self.T.data_ptr()), self.d, r.ctypes.data_as(_lib.u64p),
+                                            ctypes.c_void_p(self.E_new.data_ptr()), self.n, ctypes.c_void_p(st)))
+        self.W_acc, self.W_new = self.W_new, self.W_acc
+        self.E_acc, self.E_new = self.E_new, self.E_acc
+
+
+def synthetic_key(curve: int, n: int, window_bits: int = 0, stream=None) -> CommitmentKey:
+    """ck[i] = [i+1]G generated on the device (BASELINE.md section 3 synthetic bases)."""
+    import torch
+
+    from .curves import generator_limbs
+
+    lib = _lib.load()
+    d = torch.zeros((n, 8), dtype=torch.int64, device="cuda")
+    g = generator_limbs(curve)
+    st = stream.cuda_stream if stream is not None else 0
+    _lib.check(lib.sb_index_multiples_device(curve, g.ctypes.data_as(_lib.u64p), 0, n, ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(st or None)))
+    torch.cuda.synchronize()
+    ck = CommitmentKey.from_device(curve, d.data_ptr(), n, window_bits=window_bits, stream=st)
+    torch.cuda.synchronize()
+    del d
+    return ck
+
+
+def random_field_device(n: int, seed: int):
+    """n synthetic field elements directly in HBM: 252-bit uniform integers, read as Montgomery residues (every value
+    below the modulus is the Montgomery form of exactly one element, so this is a uniform draw over a 2^252 subset)."""
+    import torch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    t = torch.randint(-(2**63), 2**63 - 1, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+    t[:, 3] &= 0x0FFFFFFFFFFFFFFF
+    return t
