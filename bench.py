@@ -117,22 +117,24 @@ def build_side_gpu(side, rank, world, stream):
         fb += 2 * T + 5
         ab += T + 2
     cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_fixed=nfix, num_advice=nadv))
+    from sirius_b200 import sharding
+
     n = 1 << K_TABLE
-    n_loc = n // world
+    row0, n_loc = sharding.row_slice(rank, world, n)
     k_loc = n_loc.bit_length() - 1
-    row0 = rank * n_loc
     modulus = curves.SCALAR_FIELD[side["curve"]]
     # fixed columns: synthetic uniform, generated in HBM then registered (register copies from host memory)
     fixed = [device.random_field_device(n_loc, SEED + 1000 * side["curve"] + 10 * rank + j).cpu().numpy().view(np.uint64) for j in range(nfix)]
     S = SG.PlonkStructure(side["field"], modulus, k_loc, [], fixed, nadv, 0, cg)
+    if world > 1:
+        sharding.check_rotations_row_local(P.GraphEvaluator.new(cg.homogeneous, modulus).rotations)
     # commitment key restricted to this rank's rows: ck[col * n + row] for row in the slice, column-major
     lib = _lib.load()
-    ck_rows = min(1 << CK_LOG, nadv * n)
-    assert ck_rows == nadv * n or ck_rows >= nadv * n, "ck must cover W"
+    assert nadv * n <= (1 << CK_LOG), "the 2^21 key must cover W (only the prefix W needs is materialised)"
     d_bases = torch.zeros((nadv * n_loc, 8), dtype=torch.int64, device="cuda")
     g = curves.generator_limbs(side["curve"])
-    for col in range(nadv):
-        _lib.check(lib.sb_index_multiples_device(side["curve"], g.ctypes.data_as(_lib.u64p), col * n + row0, n_loc,
+    for col, (first, count) in enumerate(sharding.key_segments(nadv, n, rank, world)):
+        _lib.check(lib.sb_index_multiples_device(side["curve"], g.ctypes.data_as(_lib.u64p), first, count,
                                                  ctypes.c_void_p(d_bases.data_ptr() + col * n_loc * 64), ctypes.c_void_p(stream.cuda_stream)))
     stream.synchronize()
     ck = sirius_b200.CommitmentKey.from_device(side["curve"], d_bases.data_ptr(), nadv * n_loc, window_bits=16, stream=stream.cuda_stream)

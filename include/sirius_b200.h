@@ -110,11 +110,13 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
                     const int32_t* rotations, size_t n_rotations, sb_prog_t* out);
 void sb_expr_free(sb_prog_t prog);
 uint32_t sb_expr_num_slots(sb_prog_t prog);
+int sb_expr_field(sb_prog_t prog);
 
 /* Selector (1 byte per row, Vec<Vec<bool>>) and fixed (Vec<Vec<F>>) columns of a PlonkStructure, 2^log_rows rows. */
 int sb_columns_register(int field, uint32_t log_rows, const uint8_t* const* selectors, size_t num_selectors,
                         const uint64_t* const* fixed, size_t num_fixed, sb_columns_t* out);
 void sb_columns_release(sb_columns_t cols);
+uint32_t sb_columns_log_rows(sb_columns_t cols);
 
 /* GraphEvaluator::evaluate for every row (graph_evaluator.rs:361-388) with GetDataForEval::eval_column_var
  * column addressing (src/plonk/eval.rs:57-69): out[row] = expr(row).  W1 (and W2 for two-instance expressions,
@@ -145,6 +147,34 @@ int sb_axpy_fold(int field, const uint64_t* w1, const uint64_t* w2, const uint64
 int sb_axpy_fold_device(int field, const void* d_w1, const void* d_w2, const uint64_t r[4], void* d_out, size_t n, void* stream);
 int sb_error_fold(int field, const uint64_t* e, const uint64_t* const* T, uint32_t d, const uint64_t r[4], uint64_t* out, size_t n);
 int sb_error_fold_device(int field, const void* d_e, const void* d_T, uint32_t d, const uint64_t r[4], void* d_out, size_t n, void* stream);
+
+/* ---- Protogalaxy (src/nifs/protogalaxy) ------------------------------------------------------------ */
+
+#define SB_ROW_COMPAT 0  /* leaf i of a gate block evaluates row `i & 2^k` == row 0: the reference's behaviour (src/plonk/mod.rs:714) */
+#define SB_ROW_CORRECT 1 /* leaf i evaluates row `i % 2^k` */
+
+/* Leaves of the beta tree: leaves[b][g * 2^k + row] = gate_g evaluated on blend b, b < num_blends, where blend b
+ * is the Lagrange combination sum_j coef[b][j] * trace_j of `num_traces` witnesses (FoldedWitness::new,
+ * poly/folded_witness.rs:20-143, computed on the fly) with challenge vector challenges[b][..]; the rest of the
+ * 2^log_leaves entries is zero (src/plonk/mod.rs:709-711).  `gates` = one compiled GraphEvaluator per S.gates entry
+ * (get_evaluate_witness_fn, src/plonk/mod.rs:683-718).  d_cols_tables: host array [num_traces][num_fold_vars] of
+ * device column pointers.  A single trace with coef = [1] gives the leaves of compute_F / evaluate_e_from_trace. */
+int sb_pg_leaves_device(sb_prog_t const* gates, size_t num_gates, sb_columns_t cols, const void* const* d_cols_tables,
+                        size_t num_traces, size_t num_fold_vars, const uint64_t* coef, const uint64_t* challenges,
+                        size_t num_challenges, size_t num_blends, int row_mode, uint32_t log_leaves, void* d_leaves, void* stream);
+/* tree_reduce of compute_F (poly/mod.rs:100-185), compute_G (:330-413), evaluate_e_from_trace (mod.rs:586-639):
+ * out[p] = root of the binary tree over 2^log_n leaves with node(h) = left + right * multipliers[p][h].
+ * Point p reads leaves at d_leaves + p * leaf_stride elements (leaf_stride 0: all points share the leaves). */
+int sb_beta_tree_device(int field, const void* d_leaves, uint32_t log_n, size_t num_points, size_t leaf_stride,
+                        const uint64_t* multipliers, void* d_out, void* stream);
+/* Host front end (single witness round per trace): leaves + tree; point p uses blend point_blend[p]. */
+int sb_pg_tree(sb_prog_t const* gates, size_t num_gates, sb_columns_t cols, uint32_t num_advice, const uint64_t* const* traces_W,
+               size_t num_traces, const uint64_t* coef, const uint64_t* challenges, size_t num_challenges, size_t num_blends,
+               int row_mode, uint32_t log_leaves, const uint64_t* multipliers, size_t num_points, const uint32_t* point_blend,
+               uint64_t* out);
+/* ProtoGalaxy::fold_witness (mod.rs:176-210) / any Lagrange fold: out[i] = sum_j coef[j] * inputs[j][i]. */
+int sb_lincomb(int field, const uint64_t* const* inputs, const uint64_t* coef, size_t num_inputs, size_t n, uint64_t* out);
+int sb_lincomb_device(int field, const void* const* d_inputs, const uint64_t* coef, size_t num_inputs, size_t n, void* d_out, void* stream);
 
 /* ---- fft (src/fft.rs) ------------------------------------------------------------------------------ */
 

@@ -54,6 +54,13 @@ SIGNATURES = {
     "sb_axpy_fold_device": (ctypes.c_int, [ctypes.c_int, vp, vp, u64p, vp, ctypes.c_size_t, vp]),
     "sb_error_fold": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.POINTER(u64p), ctypes.c_uint32, u64p, u64p, ctypes.c_size_t]),
     "sb_error_fold_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_uint32, u64p, vp, ctypes.c_size_t, vp]),
+    "sb_expr_field": (ctypes.c_int, [vp]),
+    "sb_columns_log_rows": (ctypes.c_uint32, [vp]),
+    "sb_pg_leaves_device": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_size_t, vp, ctypes.POINTER(vp), ctypes.c_size_t, ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, vp, vp]),
+    "sb_beta_tree_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_size_t, u64p, vp, vp]),
+    "sb_pg_tree": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_size_t, vp, ctypes.c_uint32, ctypes.POINTER(u64p), ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), u64p]),
+    "sb_lincomb": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(u64p), u64p, ctypes.c_size_t, ctypes.c_size_t, u64p]),
+    "sb_lincomb_device": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp), u64p, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
     "sb_ntt": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint32, u64p, u64p]),
     "sb_ntt_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint32, u64p, u64p, vp]),
     "sb_coset_scale": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p, u64p]),

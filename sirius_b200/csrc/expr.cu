@@ -58,6 +58,11 @@ struct EvalArgs {
     const F* const* adv2;          // instance 2 (cross terms / two-instance expressions) or nullptr
     const F* challenges;           // single evaluation: challenge table; cross terms: [(d+1)][num_challenges]
     uint32_t num_challenges;
+    // Lagrange blend (Protogalaxy FoldedWitness, poly/folded_witness.rs:66-143, never materialised here):
+    // fold variable = sum_j coef[t*num_blend + j] * W_j, W_j's column table at blend_cols[j*num_fold_vars ..]
+    uint32_t num_blend;            // 0: off
+    const F* const* blend_cols;    // [num_blend][num_fold_vars] device column pointers
+    const F* blend_coef;           // [evaluations][num_blend]
 };
 
 template <class T>
@@ -106,6 +111,14 @@ SB_D F column_value(const EvalArgs<F>& A, uint32_t index, uint32_t row, uint32_t
         return ldg32(reinterpret_cast<const F*>(A.cols.fixed[index]) + row);
     }
     index -= A.cols.num_fixed;
+    if (A.num_blend) {
+        F acc = F::zero();
+        for (uint32_t j = 0; j < A.num_blend; j++) {
+            F w = ldg32(A.blend_cols[(size_t)j * A.num_fold_vars + index] + row);
+            acc = add(acc, mul(ldg32(A.blend_coef + (size_t)t * A.num_blend + j), w));
+        }
+        return acc;
+    }
     if (index >= A.num_fold_vars) {  // explicit second-instance variable (grouped / folded expressions)
         return ldg32(A.adv2[index - A.num_fold_vars] + row);
     }
@@ -158,12 +171,13 @@ SB_D F run_program(const EvalArgs<F>& A, uint4* sm, uint32_t row, uint32_t row_m
 
 template <class F>
 __global__ void __launch_bounds__(EXPR_THREADS)
-k_expr_eval(EvalArgs<F> A, F* __restrict__ out) {
+k_expr_eval(EvalArgs<F> A, uint32_t t, int row0_only, F* __restrict__ out) {
     extern __shared__ uint4 sm[];
     const uint32_t n = 1u << A.cols.log_rows;
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
-    F r = run_program(A, sm, row, n - 1, 0);
+    // row0_only reproduces the reference's `index & total_row` leaf addressing (src/plonk/mod.rs:714)
+    F r = run_program(A, sm, row0_only ? 0u : row, n - 1, t);
     stg32(out + row, r);
 }
 
@@ -357,8 +371,61 @@ static int eval_enqueue(sb_prog* prog, sb_columns* cols, const void* const* h_ad
         return SB_ERR_ARG;
     }
     SB_CUDA_TRY(cudaFuncSetAttribute(k_expr_eval<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_expr_eval<F><<<(n + threads - 1) / threads, threads, smem, st>>>(A, (F*)d_out);
+    A.num_blend = 0;
+    A.blend_cols = nullptr;
+    A.blend_coef = nullptr;
+    k_expr_eval<F><<<(n + threads - 1) / threads, threads, smem, st>>>(A, 0u, 0, (F*)d_out);
     SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+// Protogalaxy leaves: for every blend b (a Lagrange combination of `num_traces` witnesses + its folded challenge
+// vector) and every gate g, leaves[b][g * 2^k + row] = gate_g(row) ; padding up to 2^log_leaves is zero.
+template <class F>
+static int pg_leaves_enqueue(sb_prog* const* gates, size_t num_gates, sb_columns* cols, const void* const* h_cols_tables,
+                             size_t num_traces, size_t nfv, const uint64_t* coef, const uint64_t* challenges,
+                             size_t num_challenges, size_t num_blends, int row_mode_compat, uint32_t log_leaves, void* d_leaves,
+                             cudaStream_t st) {
+    const uint32_t n = 1u << cols->log_rows;
+    const size_t leaves = (size_t)1 << log_leaves;
+    if ((size_t)n * num_gates > leaves) {
+        set_error("sb_pg_leaves: 2^%u leaves cannot hold %zu gates x %u rows", log_leaves, num_gates, n);
+        return SB_ERR_ARG;
+    }
+    SB_CUDA_TRY(cudaMemsetAsync(d_leaves, 0, leaves * num_blends * 32, st));
+    const size_t ptr_bytes = align_up(sizeof(void*) * nfv * num_traces, 32);
+    const size_t coef_bytes = align_up(32 * num_blends * num_traces, 32);
+    const size_t ch_bytes = align_up(32 * num_blends * (num_challenges ? num_challenges : 1), 32);
+    for (size_t g = 0; g < num_gates; g++) {
+        sb_prog* prog = gates[g];
+        SB_TRY(validate_program(prog, cols, nfv, false, num_challenges));
+        SB_TRY(args_reserve(prog, ptr_bytes + coef_bytes + ch_bytes));
+        char* d = (char*)prog->d_args;
+        if (nfv) SB_CUDA_TRY(cudaMemcpyAsync(d, h_cols_tables, sizeof(void*) * nfv * num_traces, cudaMemcpyHostToDevice, st));
+        SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes, coef, 32 * num_blends * num_traces, cudaMemcpyHostToDevice, st));
+        if (num_challenges) SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes + coef_bytes, challenges, 32 * num_blends * num_challenges, cudaMemcpyHostToDevice, st));
+        EvalArgs<F> A;
+        SB_TRY(fill_args<F>(prog, cols, nullptr, nullptr, nfv, A));
+        A.adv1 = nullptr;
+        A.adv2 = nullptr;
+        A.challenges = (const F*)(d + ptr_bytes + coef_bytes);
+        A.num_challenges = (uint32_t)num_challenges;
+        A.num_blend = (uint32_t)num_traces;
+        A.blend_cols = (const F* const*)d;
+        A.blend_coef = (const F*)(d + ptr_bytes);
+        const uint32_t threads = n < (uint32_t)EXPR_THREADS ? n : EXPR_THREADS;
+        const size_t smem = (size_t)(prog->num_slots ? prog->num_slots : 1) * 32 * threads;
+        if (smem > 200 * 1024) {
+            set_error("expression needs %u live intermediates: too many for shared memory", prog->num_slots);
+            return SB_ERR_ARG;
+        }
+        SB_CUDA_TRY(cudaFuncSetAttribute(k_expr_eval<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        for (size_t b = 0; b < num_blends; b++) {
+            F* out = (F*)d_leaves + b * leaves + g * (size_t)n;
+            k_expr_eval<F><<<(n + threads - 1) / threads, threads, smem, st>>>(A, (uint32_t)b, row_mode_compat, out);
+            SB_KERNEL_CHECK();
+        }
+    }
     return SB_OK;
 }
 
@@ -404,6 +471,9 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
     A.adv2 = (const F* const*)(d + sizeof(void*) * nfv);
     A.challenges = (const F*)(d + ptr_bytes);
     A.num_challenges = (uint32_t)num_challenges;
+    A.num_blend = 0;
+    A.blend_cols = nullptr;
+    A.blend_coef = nullptr;
     const uint32_t n = 1u << cols->log_rows;
     const uint32_t threads = n < (uint32_t)EXPR_THREADS ? n : EXPR_THREADS;
     const size_t smem = (size_t)(prog->num_slots + m) * 32 * threads;
@@ -577,6 +647,8 @@ void sb_expr_free(sb_prog_t p) {
 }
 
 uint32_t sb_expr_num_slots(sb_prog_t p) { return p ? p->num_slots : 0; }
+int sb_expr_field(sb_prog_t p) { return p ? p->field : -1; }
+uint32_t sb_columns_log_rows(sb_columns_t c) { return c ? c->log_rows : 0; }
 
 int sb_columns_register(int field, uint32_t log_rows, const uint8_t* const* selectors, size_t num_selectors,
                         const uint64_t* const* fixed, size_t num_fixed, sb_columns_t* out) {
@@ -656,6 +728,24 @@ int sb_cross_terms_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, co
     if (prog->field == FIELD_FR)
         return cross_terms_enqueue<Fr>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st);
     return cross_terms_enqueue<Fq>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st);
+}
+
+int sb_pg_leaves_device(sb_prog_t const* gates, size_t num_gates, sb_columns_t cols, const void* const* d_cols_tables,
+                        size_t num_traces, size_t num_fold_vars, const uint64_t* coef, const uint64_t* challenges,
+                        size_t num_challenges, size_t num_blends, int row_mode, uint32_t log_leaves, void* d_leaves, void* stream) {
+    if (!gates || !num_gates || !cols || !d_leaves || !coef || (!d_cols_tables && num_fold_vars) || !num_traces || !num_blends ||
+        (!challenges && num_challenges)) {
+        set_error("sb_pg_leaves_device: bad argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    const int compat = row_mode == 0;
+    if (gates[0]->field == FIELD_FR)
+        return pg_leaves_enqueue<Fr>(gates, num_gates, cols, d_cols_tables, num_traces, num_fold_vars, coef, challenges, num_challenges, num_blends, compat, log_leaves, d_leaves, st);
+    return pg_leaves_enqueue<Fq>(gates, num_gates, cols, d_cols_tables, num_traces, num_fold_vars, coef, challenges, num_challenges, num_blends, compat, log_leaves, d_leaves, st);
 }
 
 // Host-memory front end used by the Rust shim: uploads the witness rounds, maps fold variables to columns as

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes
 from dataclasses import dataclass
-from typing import List, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -84,6 +84,7 @@ class PlonkStructure:
     num_advice_columns: int
     num_lookups: int
     custom_gates_lookup_compressed: CompressedGates
+    gates: Optional[List] = None         # S.gates: the individual gate Expressions (Protogalaxy evaluates them one by one)
 
     def __post_init__(self):
         lib = _lib.load()
@@ -97,6 +98,13 @@ class PlonkStructure:
         # GraphEvaluator::new(homogeneous) -- what the Rust shim compiles once per structure
         self._hom_prog = Program(self.field, GraphEvaluator.new(self.custom_gates_lookup_compressed.homogeneous, self.modulus))
 
+    def gate_programs(self):
+        """GraphEvaluator::new(gate) per gate (get_evaluate_witness_fn, src/plonk/mod.rs:697-701), compiled once."""
+        if getattr(self, "_gate_progs", None) is None:
+            assert self.gates, "PlonkStructure.gates not set"
+            self._gate_progs = [Program(self.field, GraphEvaluator.new(g, self.modulus)) for g in self.gates]
+        return self._gate_progs
+
     @property
     def degree(self) -> int:
         """number of cross terms = grouped().len() - 1 (src/plonk/mod.rs:399)"""
@@ -108,6 +116,8 @@ class PlonkStructure:
             self._cols = ctypes.c_void_p()
         if getattr(self, "_hom_prog", None) is not None:
             self._hom_prog.close()
+        for gp in getattr(self, "_gate_progs", None) or []:
+            gp.close()
 
 
 def _rounds(W: Sequence[np.ndarray]):
