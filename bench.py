@@ -257,8 +257,12 @@ def run_gpu(args):
         for _ in range(args.warmup):
             gpu_step(sides, extras, upload, combiner)
         barrier()
+        import ctypes
+
+        NT = 10
+        ms_arr, un_arr, ln_arr = (ctypes.c_double * NT)(), (ctypes.c_uint64 * NT)(), (ctypes.c_uint64 * NT)()
         lib.sb_profile_enable(1)
-        lib.sb_profile_collect(None, None, None)
+        lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
         launches0 = lib.sb_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -268,11 +272,10 @@ def run_gpu(args):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
-        import ctypes
-
-        acc_ms, acc_pts, acc_n = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_uint64()
-        _lib.check(lib.sb_profile_collect(ctypes.byref(acc_ms), ctypes.byref(acc_pts), ctypes.byref(acc_n)))
+        _lib.check(lib.sb_profile_collect(ms_arr, un_arr, ln_arr))
         lib.sb_profile_enable(0)
+        tags = ["decompose", "sort", "accumulate", "fixup", "reduce", "finalize", "cross_terms", "fold", "ntt", "protogalaxy"]
+        breakdown = {t: round(ms_arr[i] / args.steps, 4) for i, t in enumerate(tags) if ln_arr[i]}
         launches = lib.sb_launch_count() - launches0
         if world > 1:
             import torch.distributed as dist
@@ -280,13 +283,13 @@ def run_gpu(args):
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / args.steps, h2d // max(1, args.steps), launches // max(1, args.steps), (acc_ms.value, acc_pts.value, acc_n.value)
+        return ms / args.steps, h2d // max(1, args.steps), launches // max(1, args.steps), (ms_arr[2], un_arr[2], ln_arr[2]), breakdown
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, _, launches, prof = timed(upload=False)
-    ms_e2e, h2d_bytes, _, _ = timed(upload=True)
+    ms_dev, _, launches, prof, breakdown = timed(upload=False)
+    ms_e2e, h2d_bytes, _, _, _ = timed(upload=True)
     clocks = sampler.stop() if rank == 0 else None
 
     extra = {}
@@ -314,8 +317,15 @@ def run_gpu(args):
                 "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "launches": int(acc_n), "avg_launch_ms": round(acc_ms / acc_n, 4) if acc_n else None,
-                "note": "algorithmic 96 B/point; the kernel is integer-pipe bound (SURVEY F7), see DESIGN.md",
+                "note": "algorithmic 96 B/point; the kernel is integer-pipe bound (SURVEY F7): see int_pipe and DESIGN.md 4.2",
+                "int_pipe": {
+                    "achieved_gmadd_per_s": round(acc_pts * 16 / (acc_ms * 1e6), 3) if acc_ms else None,
+                    "peak_gmadd_per_s": 6.07,
+                    "frac": round(acc_pts * 16 / (acc_ms * 1e6) / 6.07, 4) if acc_ms else None,
+                    "peak_source": "profiles/r1_microbench.txt: serial XYZZ mixed additions on the full chip (IMAD.WIDE issue bound, 65.4 G Montgomery products/s)",
+                },
             },
+            "breakdown_ms_per_step": breakdown,
             "msm_points_per_step": points_per_step,
             "msm_mscalar_per_s_in_step": round(points_per_step / ms_dev / 1e3, 2),
             "extra": extra,

@@ -192,8 +192,12 @@ int sb_coset_scale_device(int field, void* d_a, size_t n, const uint64_t z[4], c
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------- */
 uint64_t sb_launch_count(void);  /* kernels launched by this library so far */
-void sb_profile_enable(int on);  /* CUDA events around the MSM bucket-accumulation kernel */
-int sb_profile_collect(double* total_ms, uint64_t* total_points, uint64_t* launches);
+#define SB_PROF_NUM_TAGS 10 /* decompose, sort, accumulate, fixup, reduce, finalize, cross_terms, fold, ntt, protogalaxy */
+void sb_profile_enable(int on);  /* CUDA events around each kernel group, on the launching stream */
+int sb_profile_collect(double* total_ms, uint64_t* total_units, uint64_t* launches); /* arrays of SB_PROF_NUM_TAGS */
+
+/* device micro-benchmarks of the arithmetic primitives (tools/microbench.py) */
+int sb_microbench(int which, int iters, int blocks, int threads, double* out_ms);
 
 /* ---- self test hooks used by tests/ (device arithmetic vs its portable twin) ----------------------- */
 int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul_ptx,

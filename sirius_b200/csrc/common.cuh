@@ -16,9 +16,19 @@ void count_launch();
 
 // Optional CUDA-event instrumentation of the dominant kernel (MSM bucket accumulation), used by bench.py to
 // report the roofline of that kernel from inside the timed region.
+enum ProfTag : int {
+    PROF_DECOMPOSE = 0, PROF_SORT = 1, PROF_ACCUMULATE = 2, PROF_FIXUP = 3, PROF_REDUCE = 4, PROF_FINALIZE = 5,
+    PROF_CROSS_TERMS = 6, PROF_FOLD = 7, PROF_NTT = 8, PROF_PG = 9, PROF_NUM_TAGS = 10
+};
 bool profile_enabled();
-void profile_begin(cudaStream_t st);
-void profile_end(cudaStream_t st, uint64_t units);
+int profile_begin(cudaStream_t st, int tag, uint64_t units);
+void profile_end(cudaStream_t st, int handle);
+struct ProfScope {  // CUDA events around the launches issued while the scope is alive (only when profiling is on)
+    cudaStream_t st;
+    int h;
+    ProfScope(cudaStream_t s, int tag, uint64_t units = 0) : st(s), h(profile_begin(s, tag, units)) {}
+    ~ProfScope() { profile_end(st, h); }
+};
 
 #define SB_CUDA_TRY(expr)                                                                         \
     do {                                                                                          \

@@ -45,6 +45,36 @@ struct alignas(16) XYZZ {  // identity: zz == 0
 template <class P>
 __device__ __noinline__ Fe<P> mul_outlined(Fe<P> a, Fe<P> b) { return mul(a, b); }
 #endif
+// Two independent products in one out-of-line body: ptxas interleaves the two carry chains, so a warp that is
+// alone on its scheduler (the reduction tree, the fix-up) gets ~2x the issue rate of back-to-back calls.
+template <class P>
+struct FePair { Fe<P> a, b; };
+#if defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ FePair<P> mul2_outlined(Fe<P> a0, Fe<P> b0, Fe<P> a1, Fe<P> b1) {
+    FePair<P> r;
+    r.a = mul(a0, b0);
+    r.b = mul(a1, b1);
+    return r;
+}
+#endif
+template <bool INL, class P>
+SB_HD void mul2x(Fe<P>& r0, const Fe<P>& a0, const Fe<P>& b0, Fe<P>& r1, const Fe<P>& a1, const Fe<P>& b1) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (INL) {
+        r0 = mul(a0, b0);
+        r1 = mul(a1, b1);
+    } else {
+        FePair<P> t = mul2_outlined(a0, b0, a1, b1);
+        r0 = t.a;
+        r1 = t.b;
+    }
+#else
+    r0 = mul(a0, b0);
+    r1 = mul(a1, b1);
+#endif
+}
+
 template <bool INL, class P>
 SB_HD Fe<P> mulx(const Fe<P>& a, const Fe<P>& b) {
 #if defined(__CUDA_ARCH__)
@@ -78,14 +108,14 @@ SB_HD XYZZ<F> xyzz_double(const XYZZ<F>& p) {
     if (p.is_identity() || p.y.is_zero()) return XYZZ<F>::identity();
     XYZZ<F> r;
     F u = dbl(p.y);
-    F v = mulx<INL>(u, u);
-    F w = mulx<INL>(u, v);
-    F s = mulx<INL>(p.x, v);
-    F xx = mulx<INL>(p.x, p.x);
+    F v, xx, w, s, mm, wy, t;
+    mul2x<INL>(v, u, u, xx, p.x, p.x);
+    mul2x<INL>(w, u, v, s, p.x, v);
     F m = add(dbl(xx), xx);
-    r.x = sub(mulx<INL>(m, m), dbl(s));
-    r.y = sub(mulx<INL>(m, sub(s, r.x)), mulx<INL>(w, p.y));
-    r.zz = mulx<INL>(v, p.zz);
+    mul2x<INL>(mm, m, m, wy, w, p.y);
+    r.x = sub(mm, dbl(s));
+    mul2x<INL>(t, m, sub(s, r.x), r.zz, v, p.zz);
+    r.y = sub(t, wy);
     r.zzz = mulx<INL>(w, p.zzz);
     return r;
 }
@@ -124,10 +154,9 @@ template <bool INL = true, class F>
 SB_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
     if (q.is_identity()) return;
     if (acc.is_identity()) { acc = q; return; }
-    F u1 = mulx<INL>(acc.x, q.zz);
-    F u2 = mulx<INL>(q.x, acc.zz);
-    F s1 = mulx<INL>(acc.y, q.zzz);
-    F s2 = mulx<INL>(q.y, acc.zzz);
+    F u1, u2, s1, s2;
+    mul2x<INL>(u1, acc.x, q.zz, u2, q.x, acc.zz);
+    mul2x<INL>(s1, acc.y, q.zzz, s2, q.y, acc.zzz);
     F p = sub(u2, u1);
     F r = sub(s2, s1);
     if (p.is_zero()) {
@@ -135,16 +164,26 @@ SB_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
         else acc = XYZZ<F>::identity();
         return;
     }
-    F pp = mulx<INL>(p, p);
-    F ppp = mulx<INL>(p, pp);
-    F qq = mulx<INL>(u1, pp);
-    F x3 = sub(sub(mulx<INL>(r, r), ppp), dbl(qq));
-    F y3 = sub(mulx<INL>(r, sub(qq, x3)), mulx<INL>(s1, ppp));
+    F pp, zz12, ppp, qq, rr, zzz12, t1, t2;
+    mul2x<INL>(pp, p, p, zz12, acc.zz, q.zz);
+    mul2x<INL>(ppp, p, pp, qq, u1, pp);
+    mul2x<INL>(rr, r, r, zzz12, acc.zzz, q.zzz);
+    F x3 = sub(sub(rr, ppp), dbl(qq));
+    mul2x<INL>(t1, r, sub(qq, x3), t2, s1, ppp);
     acc.x = x3;
-    acc.y = y3;
-    acc.zz = mulx<INL>(mulx<INL>(acc.zz, q.zz), pp);
-    acc.zzz = mulx<INL>(mulx<INL>(acc.zzz, q.zzz), ppp);
+    acc.y = sub(t1, t2);
+    mul2x<INL>(acc.zz, zz12, pp, acc.zzz, zzz12, ppp);
 }
+
+// Out-of-line entry points for the latency-bound kernels (bucket reduction tree, fix-up, combine): a warp that
+// runs alone executes each straight-line addition once, so inlined copies are instruction-fetch bound; one shared
+// copy of add/double (+ the shared products) stays resident in the instruction cache.
+#if defined(__CUDACC__)
+template <class F>
+__device__ __noinline__ void xyzz_add_call(XYZZ<F>& acc, const XYZZ<F>& q) { xyzz_add<false>(acc, q); }
+template <class F>
+__device__ __noinline__ void xyzz_double_call(XYZZ<F>& p) { p = xyzz_double<false>(p); }
+#endif
 
 template <bool INL = true, class F>
 SB_HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {

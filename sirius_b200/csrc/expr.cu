@@ -17,6 +17,7 @@
 // coalesced (consecutive rows -> consecutive 32-byte elements).
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -189,16 +190,13 @@ k_cross_terms(EvalArgs<F> A, uint32_t degree, const F* __restrict__ vinv, F* __r
     const uint32_t n = 1u << A.cols.log_rows;
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
-    // evaluations are parked in extra slots behind the program's own
-    for (uint32_t t = 0; t <= degree; t++) {
-        F e = run_program(A, sm, row, n - 1, t);
-        slot_store(sm, A.num_slots + t, blockDim.x, e);
-    }
+    F e[EXPR_MAX_DEGREE + 1];  // per-thread local array (written once, read `degree` times: stays in L1)
+    for (uint32_t t = 0; t <= degree; t++) e[t] = run_program(A, sm, row, n - 1, t);
     for (uint32_t j = 1; j <= degree; j++) {
         F acc = F::zero();
         for (uint32_t t = 0; t <= degree; t++) {
             F c = ldg32(vinv + j * (degree + 1) + t);
-            acc = add(acc, mul(c, slot_load<F>(sm, A.num_slots + t, blockDim.x)));
+            acc = add(acc, mul(c, e[t]));
         }
         stg32(out + (size_t)(j - 1) * n + row, acc);
     }
@@ -476,14 +474,17 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
     A.blend_coef = nullptr;
     const uint32_t n = 1u << cols->log_rows;
     const uint32_t threads = n < (uint32_t)EXPR_THREADS ? n : EXPR_THREADS;
-    const size_t smem = (size_t)(prog->num_slots + m) * 32 * threads;
+    const size_t smem = (size_t)(prog->num_slots ? prog->num_slots : 1) * 32 * threads;
     if (smem > 200 * 1024) {
         set_error("expression needs %u live intermediates: too many for shared memory", prog->num_slots);
         return SB_ERR_ARG;
     }
     SB_CUDA_TRY(cudaFuncSetAttribute(k_cross_terms<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_cross_terms<F><<<(n + threads - 1) / threads, threads, smem, st>>>(A, degree, (const F*)(d + ptr_bytes + ch_bytes), (F*)d_out);
-    SB_KERNEL_CHECK();
+    {
+        ProfScope ps(st, PROF_CROSS_TERMS, n);
+        k_cross_terms<F><<<(n + threads - 1) / threads, threads, smem, st>>>(A, degree, (const F*)(d + ptr_bytes + ch_bytes), (F*)d_out);
+        SB_KERNEL_CHECK();
+    }
     return SB_OK;
 }
 
@@ -566,53 +567,87 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
         SB_TRY(check_src(c.a_kind, c.a_index, c.a_rot, i));
         if (c.opcode <= OP_MUL) SB_TRY(check_src(c.b_kind, c.b_index, c.b_rot, i));
     }
+    // `Store(column | challenge | constant)` calculations (one per distinct leaf, graph_evaluator.rs:264-276) are
+    // not given a slot: their readers fetch the source directly (coalesced / broadcast loads).  This halves the
+    // live-slot count, i.e. doubles to quadruples the resident warps of the interpreter kernels.
+    struct Src { uint32_t kind, index, rot; };
+    std::vector<int> is_alias(n_calcs, 0);
+    std::vector<Src> alias_src(n_calcs);
+    for (size_t i = 0; i + 1 < n_calcs; i++) {  // the last calculation always materialises (it is the result)
+        const sb_calc& c = calcs[i];
+        if (c.opcode == OP_STORE && c.a_kind != VS_INTERMEDIATE) {
+            is_alias[c.target] = 1;
+            alias_src[c.target] = Src{c.a_kind, c.a_index, c.a_rot};
+        }
+    }
+    auto resolve = [&](uint32_t kind, uint32_t index, uint32_t rot) -> Src {
+        if (kind == VS_INTERMEDIATE && is_alias[index]) return alias_src[index];
+        return Src{kind, index, rot};
+    };
+    // recompute liveness on resolved operands
+    std::fill(last_use.begin(), last_use.end(), -1);
+    for (size_t i = 0; i < n_calcs; i++) {
+        const sb_calc& c = calcs[i];
+        if (is_alias[c.target] && i + 1 < n_calcs && c.opcode == OP_STORE && c.a_kind != VS_INTERMEDIATE) continue;
+        Src a = resolve(c.a_kind, c.a_index, c.a_rot);
+        if (a.kind == VS_INTERMEDIATE) last_use[a.index] = (long)i;
+        if (c.opcode <= OP_MUL) {
+            Src bsrc = resolve(c.b_kind, c.b_index, c.b_rot);
+            if (bsrc.kind == VS_INTERMEDIATE) last_use[bsrc.index] = (long)i;
+        }
+    }
     if (n_calcs) last_use[calcs[n_calcs - 1].target] = (long)n_calcs;  // the result stays live
     // slot assignment
     std::vector<uint32_t> slot_of(n_calcs, 0);
     std::vector<uint32_t> free_slots;
     uint32_t num_slots = 0;
-    std::vector<DevOp> ops(n_calcs);
+    std::vector<DevOp> ops;
+    ops.reserve(n_calcs);
     sb_prog* p = new (std::nothrow) sb_prog();
     if (!p) return SB_ERR_OOM;
     p->max_challenge = 0;
     p->uses_challenge = false;
-    auto enc = [&](uint32_t kind, uint32_t index, uint32_t rot) -> uint32_t {
-        if (kind == VS_INTERMEDIATE) return slot_of[index];
-        if (kind == VS_POLY || kind == VS_FIXED) {
-            if (kind == VS_POLY) p->poly_indices.push_back(index);
-            return index | (rot << 24);
+    auto enc = [&](const Src& v) -> uint32_t {
+        if (v.kind == VS_INTERMEDIATE) return slot_of[v.index];
+        if (v.kind == VS_POLY || v.kind == VS_FIXED) {
+            if (v.kind == VS_POLY) p->poly_indices.push_back(v.index);
+            return v.index | (v.rot << 24);
         }
-        if (kind == VS_CHALLENGE) {
+        if (v.kind == VS_CHALLENGE) {
             p->uses_challenge = true;
-            if (index > p->max_challenge) p->max_challenge = index;
+            if (v.index > p->max_challenge) p->max_challenge = v.index;
         }
-        return index;
+        return v.index;
     };
     for (size_t i = 0; i < n_calcs; i++) {
         const sb_calc& c = calcs[i];
+        if (is_alias[c.target] && i + 1 < n_calcs) continue;
         const bool binary = c.opcode <= OP_MUL;
+        Src a = resolve(c.a_kind, c.a_index, c.a_rot);
+        Src bsrc = binary ? resolve(c.b_kind, c.b_index, c.b_rot) : Src{0, 0, 0};
         DevOp o;
-        o.code = c.opcode | ((uint32_t)c.a_kind << 8) | ((binary ? (uint32_t)c.b_kind : 0u) << 16);
-        o.a = enc(c.a_kind, c.a_index, c.a_rot);
-        o.b = binary ? enc(c.b_kind, c.b_index, c.b_rot) : 0;
+        o.code = c.opcode | (a.kind << 8) | ((binary ? bsrc.kind : 0u) << 16);
+        o.a = enc(a);
+        o.b = binary ? enc(bsrc) : 0;
         // operands dying here release their slots before the destination is chosen
-        if (c.a_kind == VS_INTERMEDIATE && last_use[c.a_index] == (long)i) free_slots.push_back(slot_of[c.a_index]);
-        if (binary && c.b_kind == VS_INTERMEDIATE && last_use[c.b_index] == (long)i && !(c.a_kind == VS_INTERMEDIATE && c.a_index == c.b_index))
-            free_slots.push_back(slot_of[c.b_index]);
-        uint32_t s;
+        if (a.kind == VS_INTERMEDIATE && last_use[a.index] == (long)i) free_slots.push_back(slot_of[a.index]);
+        if (binary && bsrc.kind == VS_INTERMEDIATE && last_use[bsrc.index] == (long)i && !(a.kind == VS_INTERMEDIATE && a.index == bsrc.index))
+            free_slots.push_back(slot_of[bsrc.index]);
+        uint32_t sl;
         if (!free_slots.empty()) {
-            s = free_slots.back();
+            sl = free_slots.back();
             free_slots.pop_back();
         } else {
-            s = num_slots++;
+            sl = num_slots++;
         }
-        slot_of[c.target] = s;
-        o.dst = s;
-        ops[i] = o;
-        if (last_use[c.target] < 0) free_slots.push_back(s);  // never read (dead value)
+        slot_of[c.target] = sl;
+        o.dst = sl;
+        ops.push_back(o);
+        if (last_use[c.target] < 0) free_slots.push_back(sl);  // never read (dead value)
     }
+    const size_t n_ops = ops.size();
     p->field = field;
-    p->num_ops = (uint32_t)n_calcs;
+    p->num_ops = (uint32_t)n_ops;
     p->num_slots = num_slots;
     p->result_slot = n_calcs ? slot_of[calcs[n_calcs - 1].target] : 0;
     p->num_constants = (uint32_t)n_constants;
@@ -621,10 +656,10 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
     p->args_cap = 0;
     Runtime& rt = runtime();
     std::lock_guard<std::mutex> lk(rt.mu);
-    cudaError_t e = cudaMalloc(&p->d_ops, sizeof(DevOp) * (n_calcs ? n_calcs : 1));
+    cudaError_t e = cudaMalloc(&p->d_ops, sizeof(DevOp) * (n_ops ? n_ops : 1));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_constants, 32 * (n_constants ? n_constants : 1));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_rotations, 4 * (n_rotations ? n_rotations : 1));
-    if (e == cudaSuccess && n_calcs) e = cudaMemcpyAsync(p->d_ops, ops.data(), sizeof(DevOp) * n_calcs, cudaMemcpyHostToDevice, rt.stream);
+    if (e == cudaSuccess && n_ops) e = cudaMemcpyAsync(p->d_ops, ops.data(), sizeof(DevOp) * n_ops, cudaMemcpyHostToDevice, rt.stream);
     if (e == cudaSuccess && n_constants) e = cudaMemcpyAsync(p->d_constants, constants_mont, 32 * n_constants, cudaMemcpyHostToDevice, rt.stream);
     if (e == cudaSuccess && n_rotations) e = cudaMemcpyAsync(p->d_rotations, rotations, 4 * n_rotations, cudaMemcpyHostToDevice, rt.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
@@ -853,6 +888,7 @@ int sb_axpy_fold_device(int field, const void* d_w1, const void* d_w2, const uin
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     if (!n) return SB_OK;
     unsigned blocks = (unsigned)((n + 255) / 256);
+    ProfScope ps(st, PROF_FOLD, n);
     if (field == FIELD_FR) {
         Fr rr;
         memcpy(rr.v, r, 32);
@@ -884,6 +920,7 @@ int sb_error_fold_device(int field, const void* d_e, const void* d_T, uint32_t d
     if (!n) return SB_OK;
     SB_TRY(g_fold_consts.reserve(64 * 32));
     unsigned blocks = (unsigned)((n + 255) / 256);
+    ProfScope ps(st, PROF_FOLD, n);
     if (field == FIELD_FR) {
         Fr rr, pw[64];
         memcpy(rr.v, r, 32);

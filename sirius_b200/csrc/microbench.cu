@@ -1,0 +1,121 @@
+// microbench.cu -- ground-truth latency / throughput of the field and group primitives on the device.
+// Used from tools/microbench.py; results go into DESIGN.md (integer-pipe roofline of the MSM).
+#include <vector>
+#include "common.cuh"
+#include "curve.cuh"
+
+namespace sb {
+
+template <class F>
+__global__ void k_mb_mul_chain(F* io, int iters) {  // dependent products: latency (1 warp) or throughput (full grid)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    F x = io[2 * i], y = io[2 * i + 1];
+    for (int k = 0; k < iters; k++) {
+        x = mul(x, y);
+        y = mul(y, x);
+    }
+    io[2 * i] = add(x, y);
+}
+template <class F>
+__global__ void k_mb_mul_chain4(F* io, int iters) {  // four independent chains per thread (ILP)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    F x = io[2 * i], y = io[2 * i + 1], z = add(x, y), w = sub(x, y);
+    for (int k = 0; k < iters; k++) {
+        x = mul(x, x);
+        y = mul(y, y);
+        z = mul(z, z);
+        w = mul(w, w);
+    }
+    io[2 * i] = add(add(x, y), add(z, w));
+}
+template <class F>
+__global__ void k_mb_mul_outlined(F* io, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    F x = io[2 * i], y = io[2 * i + 1];
+    for (int k = 0; k < iters; k++) {
+        x = mul_outlined(x, y);
+        y = mul_outlined(y, x);
+    }
+    io[2 * i] = add(x, y);
+}
+template <class F>
+__global__ void k_mb_add_call(XYZZ<F>* io, int iters) {  // serial full additions through the out-of-line entry
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ<F> a = io[2 * i], b = io[2 * i + 1];
+    for (int k = 0; k < iters; k++) xyzz_add_call(a, b);
+    io[2 * i] = a;
+}
+template <class F>
+__global__ void k_mb_add_inline(XYZZ<F>* io, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ<F> a = io[2 * i], b = io[2 * i + 1];
+    for (int k = 0; k < iters; k++) xyzz_add<true>(a, b);
+    io[2 * i] = a;
+}
+template <class F>
+__global__ void k_mb_madd(XYZZ<F>* io, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ<F> a = io[2 * i];
+    Affine<F> q;
+    q.x = io[2 * i + 1].x;
+    q.y = io[2 * i + 1].y;
+    for (int k = 0; k < iters; k++) xyzz_madd(a, q, (k & 1) != 0);
+    io[2 * i] = a;
+}
+__global__ void k_mb_imad_wide(uint32_t* io, int iters) {  // raw IMAD.WIDE.U32 issue rate, 8 independent accumulators
+    uint32_t a = io[threadIdx.x], b = io[threadIdx.x + 32];
+    unsigned long long acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = j;
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = (unsigned long long)a * (b + j) + acc[j];
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += acc[j];
+    io[threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32);
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int sb_microbench(int which, int iters, int blocks, int threads, double* out_ms) {
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    size_t n = (size_t)blocks * threads;
+    char* d = nullptr;
+    SB_CUDA_TRY(cudaMalloc(&d, n * 256 + 1024));
+    // inputs: a valid-looking nonzero pattern (values < p: top limb small)
+    std::vector<uint32_t> h(n * 64 + 256);
+    for (size_t i = 0; i < h.size(); i++) h[i] = (uint32_t)(i * 2654435761u + 12345u) & ((i % 8 == 7) ? 0x0fffffffu : 0xffffffffu);
+    SB_CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(e0, rt.stream);
+        switch (which) {
+            case 0: k_mb_mul_chain<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
+            case 1: k_mb_mul_chain4<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
+            case 2: k_mb_mul_outlined<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
+            case 3: k_mb_add_call<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
+            case 4: k_mb_add_inline<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
+            case 5: k_mb_madd<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
+            case 6: k_mb_imad_wide<<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            default: cudaFree(d); set_error("sb_microbench: unknown test %d", which); return SB_ERR_ARG;
+        }
+        cudaEventRecord(e1, rt.stream);
+        SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *out_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    SB_CUDA_TRY(cudaGetLastError());
+    return SB_OK;
+}

@@ -18,6 +18,7 @@
 //
 // Roofline: the work is ~W mixed additions per scalar (8M+2S 254-bit Montgomery products each) -- integer-pipe
 // bound; algorithmic HBM traffic is 96 B/point.
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -109,7 +110,7 @@ SB_D XYZZ<F> warp_sum(XYZZ<F> v) {
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
         XYZZ<F> t = shfl_xor_point(v, d);
-        xyzz_add<false>(v, t);
+        xyzz_add_call(v, t);
     }
     return v;
 }
@@ -125,7 +126,7 @@ __global__ void k_precompute(const Affine<F>* __restrict__ bases, size_t n, int 
     store_vec(table + i, p);
     XYZZ<F> acc = XYZZ<F>::from_affine(p);
     for (int w = 1; w < W; w++) {
-        for (int j = 0; j < c; j++) acc = xyzz_double<false>(acc);
+        for (int j = 0; j < c; j++) xyzz_double_call(acc);
         Affine<F> q = xyzz_to_affine<false>(acc);
         store_vec(table + (size_t)w * n + i, q);
     }
@@ -141,10 +142,10 @@ __global__ void k_index_multiples(Affine<F> g, uint64_t first, size_t n, Affine<
     uint64_t s = first + i + 1;
     XYZZ<F> acc = XYZZ<F>::identity();
     for (int bit = 63 - __clzll((long long)s); bit >= 0; bit--) {
-        acc = xyzz_double<false>(acc);
+        xyzz_double_call(acc);
         if ((s >> bit) & 1) {
             XYZZ<F> gg = XYZZ<F>::from_affine(g);
-            xyzz_add<false>(acc, gg);
+            xyzz_add_call(acc, gg);
         }
     }
     store_vec(out + i, xyzz_to_affine<false>(acc));
@@ -299,8 +300,8 @@ __global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t
 // Thread t owns sorted entries [t*LS, (t+1)*LS), LS = 2^ls_log.  A bucket lying entirely inside the chunk is
 // written to buckets[]; a piece of a bucket that continues into a neighbouring chunk goes to PH[t] (piece
 // starts at the chunk start) or PT[t] (piece ends at the chunk end) and is finished by k_fixup.
-template <class F>
-__global__ void __launch_bounds__(128)
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ ekey, const uint32_t* __restrict__ eidx,
              const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* __restrict__ buckets,
              XYZZ<F>* __restrict__ PH, XYZZ<F>* __restrict__ PT) {
@@ -369,7 +370,7 @@ k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* 
 #pragma unroll 1
     for (uint32_t p = 1; p < np; p++) {
         XYZZ<F> q = load_vec(PH + t0 + p);
-        xyzz_add<false>(acc, q);
+        xyzz_add_call(acc, q);
     }
     store_vec(buckets + b, acc);
 }
@@ -389,7 +390,7 @@ k_fixup_heavy(const uint32_t* __restrict__ offsets, int ls_log, XYZZ<F>* __restr
         XYZZ<F> acc = XYZZ<F>::identity();
         for (uint32_t p = threadIdx.x; p < np; p += HEAVY_THREADS) {
             XYZZ<F> q = (p == 0 && (o & ((1u << ls_log) - 1))) ? load_vec(PT + t0) : load_vec(PH + t0 + p);
-            xyzz_add<false>(acc, q);
+            xyzz_add_call(acc, q);
         }
         sh[threadIdx.x] = acc;
         __syncthreads();
@@ -397,7 +398,7 @@ k_fixup_heavy(const uint32_t* __restrict__ offsets, int ls_log, XYZZ<F>* __restr
             if ((int)threadIdx.x < d) {
                 XYZZ<F> x = sh[threadIdx.x];
                 XYZZ<F> y = sh[threadIdx.x + d];
-                xyzz_add<false>(x, y);
+                xyzz_add_call(x, y);
                 sh[threadIdx.x] = x;
             }
             __syncthreads();
@@ -419,14 +420,14 @@ SB_D void warp_combine(XYZZ<F> S, XYZZ<F> Wt, int log_child_len, int lane, XYZZ<
 #pragma unroll 1
     for (int d = 1; d < 32; d <<= 1) {
         XYZZ<F> t = shfl_down_point(suf, d);
-        if (lane + d < 32) xyzz_add<false>(suf, t);
+        if (lane + d < 32) xyzz_add_call(suf, t);
     }
     outS = shfl_point(suf, 0);
     XYZZ<F> js = (lane >= 1) ? suf : XYZZ<F>::identity();
     js = warp_sum(js);
 #pragma unroll 1
-    for (int k = 0; k < log_child_len; k++) js = xyzz_double<false>(js);
-    xyzz_add<false>(sumW, js);
+    for (int k = 0; k < log_child_len; k++) xyzz_double_call(js);
+    xyzz_add_call(sumW, js);
     outWt = sumW;
 }
 
@@ -444,9 +445,9 @@ k_reduce_level0(const XYZZ<F>* __restrict__ buckets_all, uint32_t K, Node<F>* __
         uint64_t b = first + j;
         if (b < K) {
             XYZZ<F> q = load_vec(buckets + b);
-            xyzz_add<false>(run, q);
+            xyzz_add_call(run, q);
         }
-        xyzz_add<false>(acc, run);
+        xyzz_add_call(acc, run);
     }
     XYZZ<F> S, Wt;
     int log_l0 = 0;
@@ -509,7 +510,7 @@ __global__ void k_combine(const XYZZ<F>* __restrict__ parts, int count, Affine<F
     XYZZ<F> acc = XYZZ<F>::identity();
     for (int i = 0; i < count; i++) {
         XYZZ<F> q = load_vec(parts + i);
-        xyzz_add<false>(acc, q);
+        xyzz_add_call(acc, q);
     }
     store_vec(out_xy, xyzz_to_affine<false>(acc));
 }
@@ -617,9 +618,13 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     const uint32_t K = p.K, KB = p.KB;
     uint32_t* heavy_count = counts + KB;
 
-    SB_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)KB + 1) * 4, st));
-    k_decompose<S><<<(total + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, total, stride, K, ck->c, ck->W, dig, counts);
-    SB_KERNEL_CHECK();
+    {
+        ProfScope ps(st, PROF_DECOMPOSE, p.total);
+        SB_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)KB + 1) * 4, st));
+        k_decompose<S><<<(total + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, total, stride, K, ck->c, ck->W, dig, counts);
+        SB_KERNEL_CHECK();
+    }
+    ProfScope* sort_scope = new ProfScope(st, PROF_SORT, p.nW);
     k_scan_tile_sums<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles);
     SB_KERNEL_CHECK();
     k_scan_tiles<<<1, 1024, 0, st>>>(tiles, p.tiles);
@@ -627,18 +632,33 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     k_scan_apply<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets, cursor);
     SB_KERNEL_CHECK();
     k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, ck->W, cursor, ekey, eidx);
+    delete sort_scope;
     SB_KERNEL_CHECK();
     {
         size_t blocks = (p.chunks + 127) / 128;
-        profile_begin(st);
-        k_accumulate<F><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
-        profile_end(st, p.total);
+        static const int minb = []() {
+            const char* e = getenv("SB_ACC_MINB");
+            return e ? atoi(e) : 4;
+        }();
+        ProfScope ps(st, PROF_ACCUMULATE, p.total);
+        if (minb == 5)
+            k_accumulate<F, 5><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+        else if (minb == 6)
+            k_accumulate<F, 6><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+        else if (minb == 3)
+            k_accumulate<F, 3><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+        else
+            k_accumulate<F, 4><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         SB_KERNEL_CHECK();
     }
-    k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(offsets, KB, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
-    SB_KERNEL_CHECK();
-    k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(offsets, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
-    SB_KERNEL_CHECK();
+    {
+        ProfScope ps(st, PROF_FIXUP, KB);
+        k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(offsets, KB, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
+        SB_KERNEL_CHECK();
+        k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(offsets, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
+        SB_KERNEL_CHECK();
+    }
+    ProfScope* red_scope = new ProfScope(st, PROF_REDUCE, KB);
     {
         uint32_t lanes = (K + RED_L0 - 1) / RED_L0;
         lanes = (lanes + 31) / 32 * 32;
@@ -659,8 +679,12 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         log_len += 5;
         std::swap(cur, nxt);
     }
-    k_finalize<F><<<p.batch, 32, 0, st>>>(cur, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
-    SB_KERNEL_CHECK();
+    delete red_scope;
+    {
+        ProfScope ps(st, PROF_FINALIZE, p.batch);
+        k_finalize<F><<<p.batch, 32, 0, st>>>(cur, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
+        SB_KERNEL_CHECK();
+    }
     return SB_OK;
 }
 

@@ -21,28 +21,30 @@ void set_error(const char* fmt, ...) {
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct ProfileRec { cudaEvent_t e0, e1; uint64_t units; };
+struct ProfileRec { cudaEvent_t e0, e1; uint64_t units; int tag; };
 static bool g_profile = false;
 static std::vector<ProfileRec> g_prof;
 static std::vector<ProfileRec> g_prof_pool;
-static ProfileRec g_prof_cur;
 bool profile_enabled() { return g_profile; }
-void profile_begin(cudaStream_t st) {
-    if (!g_profile) return;
+int profile_begin(cudaStream_t st, int tag, uint64_t units) {
+    if (!g_profile) return -1;
+    ProfileRec rec;
     if (!g_prof_pool.empty()) {
-        g_prof_cur = g_prof_pool.back();
+        rec = g_prof_pool.back();
         g_prof_pool.pop_back();
     } else {
-        cudaEventCreate(&g_prof_cur.e0);
-        cudaEventCreate(&g_prof_cur.e1);
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
     }
-    cudaEventRecord(g_prof_cur.e0, st);
+    rec.units = units;
+    rec.tag = tag;
+    cudaEventRecord(rec.e0, st);
+    g_prof.push_back(rec);
+    return (int)g_prof.size() - 1;
 }
-void profile_end(cudaStream_t st, uint64_t units) {
-    if (!g_profile) return;
-    cudaEventRecord(g_prof_cur.e1, st);
-    g_prof_cur.units = units;
-    g_prof.push_back(g_prof_cur);
+void profile_end(cudaStream_t st, int handle) {
+    if (handle < 0 || handle >= (int)g_prof.size()) return;
+    cudaEventRecord(g_prof[handle].e1, st);
 }
 
 Runtime& runtime() {
@@ -148,27 +150,28 @@ uint64_t sb_launch_count(void) { return g_launches.load(); }
 
 void sb_profile_enable(int on) { g_profile = on != 0; }
 
-/* Sum of the instrumented kernel's launch durations since the last call (synchronises the recorded events). */
+/* Per-tag sums of the instrumented launch groups since the last call (synchronises the recorded events).
+ * Arrays of SB_PROF_NUM_TAGS entries each; any may be NULL. */
 int sb_profile_collect(double* total_ms, uint64_t* total_units, uint64_t* launches) {
-    double ms = 0;
-    uint64_t units = 0, n = 0;
+    for (int t = 0; t < PROF_NUM_TAGS; t++) {
+        if (total_ms) total_ms[t] = 0;
+        if (total_units) total_units[t] = 0;
+        if (launches) launches[t] = 0;
+    }
     for (auto& rec : g_prof) {
         cudaError_t e = cudaEventSynchronize(rec.e1);
-        float t = 0;
-        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, rec.e0, rec.e1);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, rec.e0, rec.e1);
         if (e != cudaSuccess) {
             set_error("sb_profile_collect: %s", cudaGetErrorString(e));
             return SB_ERR_CUDA;
         }
-        ms += t;
-        units += rec.units;
-        n++;
+        if (total_ms) total_ms[rec.tag] += ms;
+        if (total_units) total_units[rec.tag] += rec.units;
+        if (launches) launches[rec.tag] += 1;
         g_prof_pool.push_back(rec);
     }
     g_prof.clear();
-    if (total_ms) *total_ms = ms;
-    if (total_units) *total_units = units;
-    if (launches) *launches = n;
     return SB_OK;
 }
 
