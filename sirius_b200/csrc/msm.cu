@@ -9,7 +9,7 @@
 //            bucket sums: fixed-size chunks of the sorted entries, one chunk per thread, mixed XYZZ adds
 //                         (skew-proof: a bucket of any size is split across as many threads as it needs)
 //                                                                                k_accumulate, k_fixup
-//            sum_b (b+1) * B_b by a warp-shuffle suffix-scan tree                k_reduce_level0 / k_reduce_level
+//            sum_b (b+1) * B_b: row/column sums, octal digit sums, quad-lane tail  k_rowcol_sums / k_weighted_digits / k_reduce_final
 //            XYZZ -> affine                                                      k_finalize
 //
 // Because every window's base multiple is precomputed, all W windows share ONE set of 2^(c-1) buckets and
@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "curve.cuh"
+#include "quad.cuh"
 
 namespace sb {
 
@@ -32,7 +33,6 @@ constexpr int LS_MIN_LOG = 4;   // sorted entries per accumulate chunk (one thre
 constexpr int LS_MAX_LOG = 8;
 constexpr int FIX_SEQ = 32;     // buckets split in <= FIX_SEQ pieces are summed by one thread, larger ones by a block
 constexpr int HEAVY_THREADS = 256;
-constexpr int RED_L0 = 4;       // buckets per lane at level 0 of the bucket reduction
 constexpr int SCAN_ITEMS = 16;  // items per thread in the scan kernels
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
@@ -346,7 +346,7 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ e
 
 // One thread per bucket: empty buckets are set to the identity; a bucket split over 2..FIX_SEQ chunks is summed
 // from its pieces here; a bucket split over more chunks (skewed scalars: many equal digits) is queued for
-// k_fixup_heavy.
+// k_fixup_heavy.  (Throughput-bound for batched commits: plain lanes, not quad-lane groups -- measured.)
 template <class F>
 __global__ void __launch_bounds__(128)
 k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* __restrict__ buckets,
@@ -409,75 +409,152 @@ k_fixup_heavy(const uint32_t* __restrict__ offsets, int ls_log, XYZZ<F>* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// sum_b (b+1) B_b : warp-shuffle suffix-scan tree
+// sum_b (b+1) B_b : row/column sums, then octal digit sums of the two short vectors
 // ------------------------------------------------------------------------------------------------
-// A warp turns 32 children (S_j, Wt_j), each covering `child_len` consecutive buckets, into their parent:
-//   S = sum_j S_j,   Wt = sum_j Wt_j + child_len * sum_j j*S_j,   sum_j j*S_j = sum_{j>=1} Suffix_j.
+// With b = r * C + q (C = 2^lc columns, R = K / C rows):
+//     sum_b (b+1) B_b = C * sum_r r * Row_r  +  sum_q (q+1) * Col_q,      Row_r = sum_q B_{r,q},  Col_q = sum_r B_{r,q}.
+// Stage 1 (k_rowcol_sums) does the 2K plain additions with ordinary lanes (it is throughput-bound for batched
+// commits): one warp per row / per column, a short serial run per lane and a 5-step shuffle tree.
+// Stage 2 (k_weighted_digits) reduces a short vector E_0..E_{n-1} with weights (j + w0) by octal digit sums:
+//     sum_j j * E_j = sum_i 8^i sum_{v=1..7} v * D[i][v],   D[i][v] = sum_{j: digit_i(j) = v} E_j   (plain sums, one warp each)
+// and finishes with quad-lane additions (quad.cuh): 7-term weighted sums, Horner over the digit positions.
+// Stage 3 (k_reduce_final) combines  C * X + Y  and normalises to affine.
 template <class F>
-SB_D void warp_combine(XYZZ<F> S, XYZZ<F> Wt, int log_child_len, int lane, XYZZ<F>& outS, XYZZ<F>& outWt) {
-    XYZZ<F> sumW = warp_sum(Wt);
-    XYZZ<F> suf = S;
+SB_D XYZZ<F> warp_sum_call(XYZZ<F> v) {  // all lanes end with the warp total (scalar additions)
 #pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {
-        XYZZ<F> t = shfl_down_point(suf, d);
-        if (lane + d < 32) xyzz_add_call(suf, t);
+    for (int d = 16; d >= 1; d >>= 1) {
+        XYZZ<F> t = shfl_xor_point(v, d);
+        xyzz_add_call(v, t);
     }
-    outS = shfl_point(suf, 0);
-    XYZZ<F> js = (lane >= 1) ? suf : XYZZ<F>::identity();
-    js = warp_sum(js);
-#pragma unroll 1
-    for (int k = 0; k < log_child_len; k++) xyzz_double_call(js);
-    xyzz_add_call(sumW, js);
-    outWt = sumW;
+    return v;
 }
 
+// vec[batch][0..R) = row sums, vec[batch][R..R+C) = column sums
 template <class F>
 __global__ void __launch_bounds__(128)
-k_reduce_level0(const XYZZ<F>* __restrict__ buckets_all, uint32_t K, Node<F>* __restrict__ out_all, uint32_t num_out) {
+k_rowcol_sums(const XYZZ<F>* __restrict__ buckets_all, int log_k, int lc, XYZZ<F>* __restrict__ vec_all) {
+    const uint32_t K = 1u << log_k, C = 1u << lc, R = K >> lc;
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= R + C) return;
     const XYZZ<F>* buckets = buckets_all + (size_t)blockIdx.y * K;
-    Node<F>* out = out_all + (size_t)blockIdx.y * num_out;
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    XYZZ<F> run = XYZZ<F>::identity(), acc = XYZZ<F>::identity();
-    const uint64_t first = (uint64_t)g * RED_L0;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (w < R) {  // row w: C consecutive buckets
+        const uint32_t per = (C + 31) >> 5;
 #pragma unroll 1
-    for (int j = RED_L0 - 1; j >= 0; j--) {
-        uint64_t b = first + j;
-        if (b < K) {
-            XYZZ<F> q = load_vec(buckets + b);
-            xyzz_add_call(run, q);
+        for (uint32_t t = 0; t < per; t++) {
+            const uint32_t q = (uint32_t)lane * per + t;
+            if (q < C) {
+                XYZZ<F> x = load_vec(buckets + (size_t)w * C + q);
+                xyzz_add_call(acc, x);
+            }
         }
-        xyzz_add_call(acc, run);
+    } else {      // column w - R: R buckets, stride C
+        const uint32_t col = w - R;
+        const uint32_t per = (R + 31) >> 5;
+#pragma unroll 1
+        for (uint32_t t = 0; t < per; t++) {
+            const uint32_t r = (uint32_t)lane * per + t;
+            if (r < R) {
+                XYZZ<F> x = load_vec(buckets + (size_t)r * C + col);
+                xyzz_add_call(acc, x);
+            }
+        }
     }
-    XYZZ<F> S, Wt;
-    int log_l0 = 0;
-    while ((1 << log_l0) < RED_L0) log_l0++;
-    warp_combine(run, acc, log_l0, lane, S, Wt);
-    if (lane == 0 && (g >> 5) < num_out) {
-        Node<F>* o = out + (g >> 5);
-        store_vec(&o->S, S);
-        store_vec(&o->Wt, Wt);
+    acc = warp_sum_call(acc);
+    if (lane == 0) store_vec(vec_all + (size_t)blockIdx.y * (R + C) + w, acc);
+}
+
+// grid (2, batch): blockIdx.x = 0 -> X = sum_r r * Row_r (weights from 0), 1 -> Y = sum_q (q+1) * Col_q.
+// 24 warps: warp (pos, v) sums the entries whose octal digit `pos` equals v; then warps 0..2 do the 7-term
+// weighted sums and warp 0 the Horner step, all with quad-lane additions.
+constexpr int WD_THREADS = 768;
+template <class F>
+__global__ void __launch_bounds__(WD_THREADS)
+k_weighted_digits(const XYZZ<F>* __restrict__ vec_all, int log_k, int lc, XYZZ<F>* __restrict__ xy_all) {
+    __shared__ XYZZ<F> D[3][8];
+    __shared__ XYZZ<F> Xp[3];
+    __shared__ XYZZ<F> S0;
+    const uint32_t K = 1u << log_k, C = 1u << lc, R = K >> lc;
+    const int which = blockIdx.x;
+    const uint32_t n = which == 0 ? R : C;
+    const int log_n = which == 0 ? (log_k - lc) : lc;
+    const XYZZ<F>* E = vec_all + (size_t)blockIdx.y * (R + C) + (which == 0 ? 0 : R);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int npos = (log_n + 2) / 3 > 0 ? (log_n + 2) / 3 : 1;   // <= 3 for n <= 512 (K <= 2^18); larger n: see loop
+    // digit sums (scalar lanes).  For npos > 3 (very wide windows) the warps loop over the extra positions.
+    XYZZ<F> horner = XYZZ<F>::identity();
+    for (int pos_base = ((npos - 1) / 3) * 3; pos_base >= 0; pos_base -= 3) {
+        const int pos = pos_base + warp / 8, v = warp & 7;
+        XYZZ<F> acc = XYZZ<F>::identity();
+        if (pos < npos) {
+            const int bits = (log_n - 3 * pos) < 3 ? (log_n - 3 * pos) : 3;
+            if (v < (1 << bits)) {
+                const uint32_t cnt = n >> bits;
+                const uint32_t low_mask = (1u << (3 * pos)) - 1;
+#pragma unroll 1
+                for (uint32_t j = lane; j < cnt; j += 32) {
+                    const uint32_t idx = ((j >> (3 * pos)) << (3 * pos + bits)) | ((uint32_t)v << (3 * pos)) | (j & low_mask);
+                    XYZZ<F> x = load_vec(E + idx);
+                    xyzz_add_call(acc, x);
+                }
+            }
+        }
+        acc = warp_sum_call(acc);
+        if (lane == 0) D[warp / 8][v] = acc;
+        __syncthreads();
+        if (warp < 3) {  // position pos_base + warp: sum_v v * D[v] by suffix sums over the 8 groups
+            const int g = lane >> 2;
+            XYZZ<F> d = D[warp][g];
+            if (pos_base == 0 && warp == 0) {
+                XYZZ<F> tot = warp_group_sum(d);
+                if (lane == 0) S0 = tot;
+            }
+            XYZZ<F> suf = d;
+#pragma unroll 1
+            for (int dist = 1; dist < 8; dist <<= 1) {
+                XYZZ<F> t = group_shfl_down(suf, dist);
+                if (g + dist < 8) quad_add(suf, t);
+            }
+            XYZZ<F> term = (g >= 1) ? suf : XYZZ<F>::identity();
+            term = warp_group_sum(term);
+            if (lane == 0) Xp[warp] = term;
+        }
+        __syncthreads();
+        if (warp == 0) {  // horner = 8^3 * horner + 64 * X2 + 8 * X1 + X0   (positions pos_base .. pos_base + 2)
+            for (int i = 2; i >= 0; i--) {
+                quad_double(horner);
+                quad_double(horner);
+                quad_double(horner);
+                if (pos_base + i < npos) {
+                    XYZZ<F> q = Xp[i];
+                    quad_add(horner, q);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        if (which == 1) {  // weights q + 1
+            XYZZ<F> s0 = S0;
+            quad_add(horner, s0);
+        }
+        if (lane == 0) store_vec(xy_all + (size_t)blockIdx.y * 2 + which, horner);
     }
 }
 
+// root = C * X + Y ; out = affine(root)
 template <class F>
-__global__ void __launch_bounds__(128)
-k_reduce_level(const Node<F>* __restrict__ in_all, uint32_t count, int log_child_len, Node<F>* __restrict__ out_all, uint32_t num_out) {
-    const Node<F>* in = in_all + (size_t)blockIdx.y * count;
-    Node<F>* out = out_all + (size_t)blockIdx.y * num_out;
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    XYZZ<F> s = XYZZ<F>::identity(), w = XYZZ<F>::identity();
-    if (g < count) {
-        s = load_vec(&in[g].S);
-        w = load_vec(&in[g].Wt);
-    }
-    XYZZ<F> S, Wt;
-    warp_combine(s, w, log_child_len, lane, S, Wt);
-    if (lane == 0 && (g >> 5) < num_out) {
-        Node<F>* o = out + (g >> 5);
-        store_vec(&o->S, S);
-        store_vec(&o->Wt, Wt);
+__global__ void k_reduce_final(const XYZZ<F>* __restrict__ xy_all, int lc, uint32_t batch, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
+    const uint32_t b = blockIdx.x;
+    if (b >= batch) return;
+    XYZZ<F> acc = load_vec(xy_all + (size_t)b * 2);
+    for (int k = 0; k < lc; k++) quad_double(acc);
+    XYZZ<F> y = load_vec(xy_all + (size_t)b * 2 + 1);
+    quad_add(acc, y);
+    if (threadIdx.x == 0) {
+        if (out_xyzz) store_vec(out_xyzz + b, acc);
+        if (out_xy) store_vec(out_xy + b, xyzz_to_affine<false>(acc));
     }
 }
 
@@ -571,7 +648,7 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     }
     p.chunks = (p.nW + ((size_t)1 << p.ls_log) - 1) >> p.ls_log;
     p.tiles = (p.KB + SCAN_TILE - 1) / SCAN_TILE;
-    p.nodes0 = (p.K + 32 * RED_L0 - 1) / (32 * RED_L0);
+    p.nodes0 = 64;  // digit-sum partials: npos(<=8) * 8 values * nsplit(<=8) XYZZ = 512 * 128 B = 256 Node-sized slots
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -589,8 +666,11 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     p.off_ph = take(p.chunks * 128);
     p.off_pt = take(p.chunks * 128);
     p.off_heavy = take((p.chunks / FIX_SEQ + 2) * 4);
-    p.off_nodes_a = take((size_t)p.nodes0 * batch * 256);
-    p.off_nodes_b = take(((size_t)p.nodes0 / 32 + 1) * batch * 256);
+    {
+        const int log_k = ck->c - 1, lc = (log_k + 1) / 2;
+        p.off_nodes_a = take((((size_t)1 << lc) + ((size_t)p.K >> lc)) * batch * 128);  // row + column sums
+        p.off_nodes_b = take((size_t)batch * 2 * 128);                                   // X, Y
+    }
     p.off_out_xy = take(64 * batch);
     p.off_out_xyzz = take(128 * batch);
     p.off_scalars = take(stage_scalars ? p.total * 32 : 0);
@@ -613,8 +693,6 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     auto* PH = (XYZZ<F>*)(ws + p.off_ph);
     auto* PT = (XYZZ<F>*)(ws + p.off_pt);
     auto* heavy_list = (uint32_t*)(ws + p.off_heavy);
-    auto* nodes_a = (Node<F>*)(ws + p.off_nodes_a);
-    auto* nodes_b = (Node<F>*)(ws + p.off_nodes_b);
     const uint32_t K = p.K, KB = p.KB;
     uint32_t* heavy_count = counts + KB;
 
@@ -658,32 +736,26 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(offsets, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
     }
-    ProfScope* red_scope = new ProfScope(st, PROF_REDUCE, KB);
     {
-        uint32_t lanes = (K + RED_L0 - 1) / RED_L0;
-        lanes = (lanes + 31) / 32 * 32;
-        dim3 grid((lanes + 127) / 128, p.batch);
-        k_reduce_level0<F><<<grid, 128, 0, st>>>(buckets, K, nodes_a, p.nodes0);
-        SB_KERNEL_CHECK();
-    }
-    uint32_t count = p.nodes0;
-    int log_len = 5;
-    for (int l = RED_L0; l > 1; l >>= 1) log_len++;
-    Node<F>*cur = nodes_a, *nxt = nodes_b;
-    while (count > 1) {
-        uint32_t lanes = (count + 31) / 32 * 32;
-        dim3 grid((lanes + 127) / 128, p.batch);
-        k_reduce_level<F><<<grid, 128, 0, st>>>(cur, count, log_len, nxt, (count + 31) / 32);
-        SB_KERNEL_CHECK();
-        count = (count + 31) / 32;
-        log_len += 5;
-        std::swap(cur, nxt);
-    }
-    delete red_scope;
-    {
-        ProfScope ps(st, PROF_FINALIZE, p.batch);
-        k_finalize<F><<<p.batch, 32, 0, st>>>(cur, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
-        SB_KERNEL_CHECK();
+        const int log_k = ck->c - 1;
+        const int lc = (log_k + 1) / 2;
+        const uint32_t C = 1u << lc, R = K >> lc;
+        auto* vec = (XYZZ<F>*)(ws + p.off_nodes_a);   // [batch][R + C]
+        auto* xy = (XYZZ<F>*)(ws + p.off_nodes_b);    // [batch][2]
+        {
+            ProfScope ps(st, PROF_REDUCE, KB);
+            dim3 g1((R + C + 3) / 4, p.batch);
+            k_rowcol_sums<F><<<g1, 128, 0, st>>>(buckets, log_k, lc, vec);
+            SB_KERNEL_CHECK();
+            dim3 g2(2, p.batch);
+            k_weighted_digits<F><<<g2, WD_THREADS, 0, st>>>(vec, log_k, lc, xy);
+            SB_KERNEL_CHECK();
+        }
+        {
+            ProfScope pf(st, PROF_FINALIZE, p.batch);
+            k_reduce_final<F><<<p.batch, 4, 0, st>>>(xy, lc, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
+            SB_KERNEL_CHECK();
+        }
     }
     return SB_OK;
 }
