@@ -176,11 +176,9 @@ class Combiner:
         gathered = torch.zeros((self.world, batch, 16), dtype=torch.int64, device="cuda")
         with torch.cuda.stream(self.stream):
             dist.all_gather_into_tensor(gathered, part)
-            per = gathered.permute(1, 0, 2).contiguous()  # [batch][world][16]
         out = torch.zeros((batch, 8), dtype=torch.int64, device="cuda")
-        for b in range(batch):
-            _lib.check(lib.sb_msm_combine_device(sess.ck.curve, ctypes.c_void_p(per.data_ptr() + b * self.world * 128), self.world,
-                                                 ctypes.c_void_p(out.data_ptr() + b * 64), ctypes.c_void_p(self.stream.cuda_stream)))
+        _lib.check(lib.sb_msm_combine_batch_device(sess.ck.curve, ctypes.c_void_p(gathered.data_ptr()), self.world, batch, batch,
+                                                   ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(self.stream.cuda_stream)))
         with torch.cuda.stream(self.stream):
             h_out.copy_(out.view(h_out.shape), non_blocking=True)
         self.stream.synchronize()

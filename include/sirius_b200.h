@@ -99,6 +99,9 @@ int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t
                         void* d_out_xyzz, void* stream);
 /* Multi-GPU combine: sum `count` XYZZ partials (device, 128 B each) and normalise to affine. */
 int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, void* d_out_xy, void* stream);
+/* Batched form: out[b] = affine(sum_g partials[g * stride + b]), g < count ranks, b < batch commitments -- reads
+ * the all-gather output [rank][batch] in place. */
+int sb_msm_combine_batch_device(int curve, const void* d_partials_xyzz, int count, size_t batch, size_t stride, void* d_out_xy, void* stream);
 
 /* Synthetic commitment key used by the benches: d_out[i] = [first + i + 1] * G, affine. */
 int sb_index_multiples_device(int curve, const uint64_t gen_xy[8], uint64_t first, size_t n, void* d_out_xy, void* stream);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "sb_msm_batch": (ctypes.c_int, [vp, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p]),
     "sb_msm_batch_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp]),
     "sb_index_multiples_device": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint64, ctypes.c_size_t, vp, vp]),
+    "sb_msm_combine_batch_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
     "sb_msm_combine_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
     "sb_expr_compile": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32), ctypes.c_size_t, ctypes.POINTER(vp)]),
     "sb_expr_free": (None, [vp]),

@@ -182,22 +182,31 @@ k_expr_eval(EvalArgs<F> A, uint32_t t, int row0_only, F* __restrict__ out) {
     stg32(out + row, r);
 }
 
-// out[(j-1)*n + row] = T_j(row), j = 1..degree;  vinv is the (degree+1)^2 inverse Vandermonde on points 0..degree
+// out[(j-1)*n + row] = T_j(row), j = 1..degree;  vinv is the (degree+1)^2 inverse Vandermonde on points 0..degree.
+// One thread per (row, evaluation point t): a block holds rows_per_block rows x (degree+1) points, the evaluations
+// meet in shared memory and thread (row, t) then produces T_{t+1}.  (d+1) times the parallelism of a thread per row,
+// which matters when the rows are sharded over several GPUs; column loads stay coalesced (the d+1 threads of a row
+// read the same address).
 template <class F>
 __global__ void __launch_bounds__(EXPR_THREADS)
-k_cross_terms(EvalArgs<F> A, uint32_t degree, const F* __restrict__ vinv, F* __restrict__ out) {
+k_cross_terms(EvalArgs<F> A, uint32_t degree, uint32_t rows_per_block, const F* __restrict__ vinv, F* __restrict__ out) {
     extern __shared__ uint4 sm[];
     const uint32_t n = 1u << A.cols.log_rows;
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n) return;
-    F e[EXPR_MAX_DEGREE + 1];  // per-thread local array (written once, read `degree` times: stays in L1)
-    for (uint32_t t = 0; t <= degree; t++) e[t] = run_program(A, sm, row, n - 1, t);
-    for (uint32_t j = 1; j <= degree; j++) {
+    const uint32_t m = degree + 1;
+    const uint32_t r_in = threadIdx.x / m, t = threadIdx.x - r_in * m;
+    const uint32_t row = blockIdx.x * rows_per_block + r_in;
+    const bool live = r_in < rows_per_block && row < n;
+    // exchange area behind the slot file: [rows_per_block][m] evaluations
+    F* exch = reinterpret_cast<F*>(sm + (size_t)(A.num_slots ? A.num_slots : 1) * 2 * blockDim.x);
+    if (live) {
+        F e = run_program(A, sm, row, n - 1, t);
+        exch[r_in * m + t] = e;
+    }
+    __syncthreads();
+    if (live && t + 1 <= degree) {
+        const uint32_t j = t + 1;
         F acc = F::zero();
-        for (uint32_t t = 0; t <= degree; t++) {
-            F c = ldg32(vinv + j * (degree + 1) + t);
-            acc = add(acc, mul(c, e[t]));
-        }
+        for (uint32_t s = 0; s <= degree; s++) acc = add(acc, mul(ldg32(vinv + j * m + s), exch[r_in * m + s]));
         stg32(out + (size_t)(j - 1) * n + row, acc);
     }
 }
@@ -473,8 +482,10 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
     A.blend_cols = nullptr;
     A.blend_coef = nullptr;
     const uint32_t n = 1u << cols->log_rows;
-    const uint32_t threads = n < (uint32_t)EXPR_THREADS ? n : EXPR_THREADS;
-    const size_t smem = (size_t)(prog->num_slots ? prog->num_slots : 1) * 32 * threads;
+    uint32_t rows_per_block = (uint32_t)EXPR_THREADS / m;
+    if (rows_per_block > n) rows_per_block = n;
+    const uint32_t threads = (rows_per_block * m + 31) / 32 * 32;
+    const size_t smem = (size_t)(prog->num_slots ? prog->num_slots : 1) * 32 * threads + (size_t)rows_per_block * m * 32;
     if (smem > 200 * 1024) {
         set_error("expression needs %u live intermediates: too many for shared memory", prog->num_slots);
         return SB_ERR_ARG;
@@ -482,7 +493,7 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
     SB_CUDA_TRY(cudaFuncSetAttribute(k_cross_terms<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
         ProfScope ps(st, PROF_CROSS_TERMS, n);
-        k_cross_terms<F><<<(n + threads - 1) / threads, threads, smem, st>>>(A, degree, (const F*)(d + ptr_bytes + ch_bytes), (F*)d_out);
+        k_cross_terms<F><<<(n + rows_per_block - 1) / rows_per_block, threads, smem, st>>>(A, degree, rows_per_block, (const F*)(d + ptr_bytes + ch_bytes), (F*)d_out);
         SB_KERNEL_CHECK();
     }
     return SB_OK;

@@ -98,6 +98,19 @@ class PlonkStructure:
         # GraphEvaluator::new(homogeneous) -- what the Rust shim compiles once per structure
         self._hom_prog = Program(self.field, GraphEvaluator.new(self.custom_gates_lookup_compressed.homogeneous, self.modulus))
 
+    def is_sat(self, ck: CommitmentKey, U_challenges, U_W_commitments, W: Sequence[np.ndarray]) -> None:
+        """PlonkStructure::is_sat (src/plonk/mod.rs:304-361) without the host-side sps_verify / log-derivative parts:
+        the compressed gate expression vanishes on every row and the witness rounds re-open."""
+        if getattr(self, "_compressed_prog", None) is None:
+            self._compressed_prog = Program(self.field, GraphEvaluator.new(self.custom_gates_lookup_compressed.compressed, self.modulus))
+        got = evaluate_rows(self, self._compressed_prog, W, np.asarray(U_challenges, dtype=np.uint64).reshape(-1, 4))
+        mismatch = int(np.count_nonzero(np.any(got != 0, axis=1)))
+        if mismatch:
+            raise EvaluationMismatch(mismatch, 1 << self.k)
+        bad = sum(1 for Ci, Wi in zip(U_W_commitments, W) if not np.array_equal(ck.commit(Wi), np.asarray(Ci, dtype=np.uint64).reshape(8)))
+        if bad:
+            raise CommitmentMismatch(bad)
+
     def gate_programs(self):
         """GraphEvaluator::new(gate) per gate (get_evaluate_witness_fn, src/plonk/mod.rs:697-701), compiled once."""
         if getattr(self, "_gate_progs", None) is None:
@@ -118,6 +131,8 @@ class PlonkStructure:
             self._hom_prog.close()
         for gp in getattr(self, "_gate_progs", None) or []:
             gp.close()
+        if getattr(self, "_compressed_prog", None) is not None:
+            self._compressed_prog.close()
 
 
 def _rounds(W: Sequence[np.ndarray]):
@@ -127,7 +142,64 @@ def _rounds(W: Sequence[np.ndarray]):
     return arrs, ptrs, lens
 
 
+class EvaluationMismatch(Exception):
+    """plonk::Error::EvaluationMismatch { mismatch_count, total_row } (src/plonk/mod.rs, used by the deciders)."""
+
+    def __init__(self, mismatch_count: int, total_row: int):
+        super().__init__(f"(Relaxed) plonk relation not satisfied: mismatch_count {mismatch_count}, total_row {total_row}")
+        self.mismatch_count, self.total_row = mismatch_count, total_row
+
+
+class CommitmentMismatch(Exception):
+    """plonk::Error::CommitmentMismatch { mismatch_count }"""
+
+    def __init__(self, mismatch_count: int):
+        super().__init__(f"commitment of witness mismatch: {mismatch_count}")
+        self.mismatch_count = mismatch_count
+
+
+class ECommitmentMismatch(Exception):
+    """VerifyError::ECommitmentMismatch (src/nifs/sangria/mod.rs:319-320)"""
+
+
+def evaluate_rows(S: "PlonkStructure", prog: Program, W: Sequence[np.ndarray], challenges: np.ndarray, W2: Optional[Sequence[np.ndarray]] = None) -> np.ndarray:
+    """GraphEvaluator::evaluate for every row (sb_expr_eval): uint64 [2^k,4]."""
+    lib = _lib.load()
+    a1, p1, l1 = _rounds(W)
+    ch = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((1 << S.k, 4), dtype=np.uint64)
+    if W2 is not None:
+        a2, p2, l2 = _rounds(W2)
+        _lib.check(lib.sb_expr_eval(prog._h, S._cols, S.num_advice_columns, S.num_lookups, p1, l1, len(a1), p2, l2, len(a2),
+                                    ch.ctypes.data_as(_lib.u64p), ch.shape[0], out.ctypes.data_as(_lib.u64p)))
+    else:
+        _lib.check(lib.sb_expr_eval(prog._h, S._cols, S.num_advice_columns, S.num_lookups, p1, l1, len(a1), None, None, 0,
+                                    ch.ctypes.data_as(_lib.u64p), ch.shape[0], out.ctypes.data_as(_lib.u64p)))
+    return out
+
+
 class VanillaFS:
+    @staticmethod
+    def is_sat_accumulation(S: "PlonkStructure", U_challenges, U_u, W: Sequence[np.ndarray], E: np.ndarray) -> None:
+        """src/nifs/sangria/mod.rs:334-383: homogeneous gate polynomial on (W, challenges ++ [u]) must equal E row by
+        row.  (The log-derivative check of lookup arguments stays on the Rust side: lookups are out of scope.)"""
+        if S.num_lookups:
+            raise NotImplementedError("is_sat_log_derivative (lookup arguments) is outside the GPU hot path")
+        ch = np.concatenate([np.asarray(U_challenges, dtype=np.uint64).reshape(-1, 4), np.asarray(U_u, dtype=np.uint64).reshape(1, 4)])
+        got = evaluate_rows(S, S._hom_prog, W, ch)
+        mismatch = int(np.count_nonzero(np.any(got != np.asarray(E, dtype=np.uint64).reshape(-1, 4), axis=1)))
+        if mismatch:
+            raise EvaluationMismatch(mismatch, 1 << S.k)
+
+    @staticmethod
+    def is_sat_witness_commit(ck: CommitmentKey, W_commitments, W: Sequence[np.ndarray], E: np.ndarray, E_commitment) -> None:
+        """src/nifs/sangria/mod.rs:455-474: every W round and E re-open to their commitments."""
+        bad = sum(1 for Ci, Wi in zip(W_commitments, W) if not np.array_equal(ck.commit(Wi), np.asarray(Ci, dtype=np.uint64).reshape(8)))
+        if bad:
+            raise CommitmentMismatch(bad)
+        if not np.array_equal(ck.commit(E), np.asarray(E_commitment, dtype=np.uint64).reshape(8)):
+            raise ECommitmentMismatch()
+
     @staticmethod
     def commit_cross_terms(ck: CommitmentKey, S: PlonkStructure, U1_challenges, U1_u, W1: Sequence[np.ndarray], U2_challenges,
                            W2: Sequence[np.ndarray]):

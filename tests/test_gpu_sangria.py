@@ -169,3 +169,46 @@ def test_witness_fold(sb, oracle, field):
         lib.so_error_fold(field, e1.ctypes.data_as(u64p), ptrs, ctypes.c_size_t(d), r.ctypes.data_as(u64p), exp_e.ctypes.data_as(u64p), ctypes.c_size_t(ne))
         assert np.array_equal(got.W[0], exp_w)
         assert np.array_equal(got.E, exp_e)
+
+
+@pytest.mark.parametrize("field,curve", [(R.FIELD_FR, R.CURVE_BN256), (R.FIELD_FQ, R.CURVE_GRUMPKIN)])
+def test_prove_then_is_sat(sb, oracle, field, curve):
+    """The reference's end-to-end nifs structure (src/nifs/sangria/tests.rs:185-235): fold an accumulator with an
+    incoming trace, then the deciders accept the result (E opens to the evaluated relation, commitments re-open);
+    a single corrupted cell is reported."""
+    from sirius_b200 import sangria as SG
+
+    m = R.MODULUS[field]
+    k, T_list = 8, [5, 3]
+    n = 1 << k
+    S, co, fixed, sels, nadv = _build(sb, oracle, field, k, T_list, 91)
+    nch = co.ctx.num_challenges - 1
+    W1, W2 = oracle.random_field(field, 1, nadv * n), oracle.random_field(field, 2, nadv * n)
+    c1, c2, u1 = oracle.random_field(field, 3, nch), oracle.random_field(field, 4, nch), oracle.random_field(field, 5, 1)
+    r = oracle.random_field(field, 6, 1).reshape(4)
+    # a satisfied relaxed accumulator: E1 := P_hom(W1; c1, u1), taken from the ORACLE evaluator
+    hom = E.GraphEvaluator(co.homogeneous, m)
+    adv1 = [W1[i * n:(i + 1) * n] for i in range(nadv)]
+    E1 = E.c_graph_evaluate(field, hom, sels, fixed, adv1, np.concatenate([c1, u1]), k)
+    bases = oracle.running_bases(curve, nadv * n)
+    ck = sb.CommitmentKey(curve, bases)
+    SG.VanillaFS.is_sat_accumulation(S, c1, u1, [W1], E1)
+    T, commits = SG.VanillaFS.commit_cross_terms(ck, S, c1, u1, [W1], c2, [W2])
+    folded = SG.RelaxedPlonkWitness(field, [W1], E1).fold([W2], T, r)
+    # folded instance scalars: challenges + r * challenges2, u + r (accumulator.rs:228-235)
+    cf = oracle.field_binop("add", field, c1, oracle.field_binop("mul", field, np.tile(r, (nch, 1)), c2))
+    uf = oracle.field_binop("add", field, u1, r.reshape(1, 4))
+    SG.VanillaFS.is_sat_accumulation(S, cf, uf, folded.W, folded.E)
+    # commitments of the folded witness re-open: C(W') == C(W1) + r C(W2) is the verifier's view; here the prover's
+    cW, cE = ck.commit(folded.W[0]), ck.commit(folded.E)
+    SG.VanillaFS.is_sat_witness_commit(ck, [cW], folded.W, folded.E, cE)
+    assert np.array_equal(cW, oracle.msm(curve, folded.W[0], bases))
+    bad = folded.E.copy()
+    bad[5, 0] ^= np.uint64(1)
+    with pytest.raises(SG.EvaluationMismatch) as ei:
+        SG.VanillaFS.is_sat_accumulation(S, cf, uf, folded.W, bad)
+    assert ei.value.mismatch_count == 1 and ei.value.total_row == n
+    with pytest.raises(SG.ECommitmentMismatch):
+        SG.VanillaFS.is_sat_witness_commit(ck, [cW], folded.W, bad, cE)
+    S.close()
+    ck.close()
