@@ -384,6 +384,20 @@ def gpu_side_metrics(stream):
 _CPU_STATE = {}
 
 
+def cpu_threads() -> int:
+    """Host threads for the CPU arm: the physical cores (the restatement, like rayon-based halo2, gets slower when
+    it is spread over SMT siblings: 9.2 s on 128 logical vs 4.7 s on 64 physical cores of the round-1 box)."""
+    try:
+        import psutil
+
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
 def cpu_setup():
     """The same shapes for the CPU restatement (oracle/): test infrastructure, used only as the timed baseline."""
     if _CPU_STATE:
@@ -438,9 +452,9 @@ def cpu_step():
     def prove(s):
         f, curve, nadv = s["side"]["field"], s["side"]["curve"], s["nadv"]
         adv = [s["W1"][i * n:(i + 1) * n] for i in range(nadv)] + [s["W2"][i * n:(i + 1) * n] for i in range(nadv)]
-        T = [np.zeros((n, 4), dtype=np.uint64) if ev is None else E.c_graph_evaluate(f, ev, [], s["fixed"], adv, s["ch"], K_TABLE, threads=0) for ev in s["evs"]]
+        T = [np.zeros((n, 4), dtype=np.uint64) if ev is None else E.c_graph_evaluate(f, ev, [], s["fixed"], adv, s["ch"], K_TABLE, threads=cpu_threads()) for ev in s["evs"]]
         for t in T:
-            oracle.msm(curve, t, s["bases"], threads=0)
+            oracle.msm(curve, t, s["bases"], threads=cpu_threads())
         outw = np.zeros_like(s["W1"])
         lib.so_axpy(f, s["W1"].ctypes.data_as(u64p), s["W2"].ctypes.data_as(u64p), s["r"].ctypes.data_as(u64p), outw.ctypes.data_as(u64p), ctypes.c_size_t(nadv * n))
         ptrs = (u64p * len(T))(*[t.ctypes.data_as(u64p) for t in T])
@@ -448,7 +462,7 @@ def cpu_step():
         lib.so_error_fold(f, s["E1"].ctypes.data_as(u64p), ptrs, ctypes.c_size_t(len(T)), s["r"].ctypes.data_as(u64p), oute.ctypes.data_as(u64p), ctypes.c_size_t(n))
 
     def commit_w(s):
-        oracle.msm(s["side"]["curve"], s["W2"], s["bases"], threads=0)
+        oracle.msm(s["side"]["curve"], s["W2"], s["bases"], threads=cpu_threads())
 
     prove(st["secondary"])
     commit_w(st["primary"])
@@ -464,7 +478,7 @@ def cpu_step_baseline(steps):
     for _ in range(steps):
         cpu_step()
     ms = (time.perf_counter() - t0) * 1e3 / steps
-    return {"value": round(ms, 2), "unit": "ms", "cores": oracle.num_threads(), "kind": "port",
+    return {"value": round(ms, 2), "unit": "ms", "cores": cpu_threads(), "kind": "port",
             "sample": f"{steps} full fold_step hot path(s) of the same workload (CPU restatement of the reference: halo2-style chunked Pippenger, "
                       "literal GroupedPoly/GraphEvaluator cross terms, OpenMP on all host cores)"}
 
@@ -483,7 +497,7 @@ def run_reference(args):
     for _ in range(args.steps):
         cpu_step()
     ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    base = {"value": round(ms, 2), "unit": "ms", "cores": oracle.num_threads(), "kind": "port",
+    base = {"value": round(ms, 2), "unit": "ms", "cores": cpu_threads(), "kind": "port",
             "sample": "full fold_step hot path per step (CPU restatement of the reference; the Rust crate cannot be built here: no cargo/rustc)"}
     line = {
         "impl": "reference", "metric": METRIC, "value": round(ms, 2), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1),
