@@ -62,6 +62,60 @@ __global__ void k_mb_madd(XYZZ<F>* io, int iters) {
     for (int k = 0; k < iters; k++) xyzz_madd(a, q, (k & 1) != 0);
     io[2 * i] = a;
 }
+// Timing experiment only (wrong results): the product with 16 of its 128 IMAD.WIDE removed and ~100 extra
+// carry-chain additions, to price a Karatsuba product (48 + 64 wide multiplies + more additions) before writing it.
+template <class P>
+SB_D Fe<P> mul_fake112(const Fe<P>& a, const Fe<P>& b) {
+    uint32_t A[9], B[9];
+    const uint32_t b0 = b.v[0];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { A[k] = a.v[k & 7] ^ b0; B[k] = b.v[k & 7] + k; }
+    {
+        uint32_t m = A[0] * P::INV;
+        chain_odd(B, P::P1, P::P3, P::P5, P::P7, m);
+        chain_even(A, P::P0, P::P2, P::P4, P::P6, m);
+    }
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        {
+            const uint32_t bi = b.v[i];
+            fold_shift_chain_odd(B, A, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+            if (i < 4) chain_even(B, a.v[0], a.v[2], a.v[4], a.v[6], bi);
+            uint32_t m = B[0] * P::INV;
+            chain_odd(A, P::P1, P::P3, P::P5, P::P7, m);
+            chain_even(B, P::P0, P::P2, P::P4, P::P6, m);
+        }
+        if (i + 1 < 8) {
+            const uint32_t bi = b.v[i + 1];
+            fold_shift_chain_odd(A, B, a.v[1], a.v[3], a.v[5], a.v[7], bi);
+            if (i < 4) chain_even(A, a.v[0], a.v[2], a.v[4], a.v[6], bi);
+            uint32_t m = A[0] * P::INV;
+            chain_odd(B, P::P1, P::P3, P::P5, P::P7, m);
+            chain_even(A, P::P0, P::P2, P::P4, P::P6, m);
+        }
+    }
+    // ~100 extra additions on the ALU pipe (12 dependent 8-limb carry chains)
+    Fe<P> r, t;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { r.v[k] = B[k + 1] + A[k]; t.v[k] = A[k + 1]; }
+#pragma unroll
+    for (int rep = 0; rep < 6; rep++) {
+        r = add_ptx(r, t);
+        t = sub_ptx(t, r);
+    }
+    return r;
+}
+template <class F>
+__global__ void k_mb_mul_fake(F* io, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    F x = io[2 * i], y = io[2 * i + 1];
+    for (int k = 0; k < iters; k++) {
+        x = mul_fake112(x, y);
+        y = mul_fake112(y, x);
+    }
+    io[2 * i] = add(x, y);
+}
+
 __global__ void k_mb_imad_wide(uint32_t* io, int iters) {  // raw IMAD.WIDE.U32 issue rate, 8 independent accumulators
     uint32_t a = io[threadIdx.x], b = io[threadIdx.x + 32];
     unsigned long long acc[8];
@@ -105,6 +159,7 @@ extern "C" int sb_microbench(int which, int iters, int blocks, int threads, doub
             case 4: k_mb_add_inline<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 5: k_mb_madd<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 6: k_mb_imad_wide<<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 7: k_mb_mul_fake<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
             default: cudaFree(d); set_error("sb_microbench: unknown test %d", which); return SB_ERR_ARG;
         }
         cudaEventRecord(e1, rt.stream);
