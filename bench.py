@@ -156,27 +156,35 @@ def build_side_gpu(side, rank, world, stream):
 
 
 class Combiner:
-    """N > 1: all-gather the XYZZ partial sums of a commitment and add them."""
+    """N > 1: all-gather the XYZZ partial sums of a commitment group and add them."""
 
     def __init__(self, world, stream):
         import torch
 
         self.world, self.stream, self.torch = world, stream, torch
+        self.bufs = {}
+
+    def _buffers(self, batch):
+        torch = self.torch
+        if batch not in self.bufs:
+            self.bufs[batch] = (torch.zeros((batch, 16), dtype=torch.int64, device="cuda"),
+                                torch.zeros((self.world, batch, 16), dtype=torch.int64, device="cuda"),
+                                torch.zeros((batch, 8), dtype=torch.int64, device="cuda"))
+        return self.bufs[batch]
 
     def commit(self, sess, d_scalars, n, batch, h_out):
         import ctypes
+
         import torch
         import torch.distributed as dist
 
         from sirius_b200 import _lib
 
         lib = _lib.load()
-        part = torch.zeros((batch, 16), dtype=torch.int64, device="cuda")
+        part, gathered, out = self._buffers(batch)
         sess.ck.commit_batch_device(d_scalars, n, n, batch, 0, part.data_ptr(), self.stream.cuda_stream)
-        gathered = torch.zeros((self.world, batch, 16), dtype=torch.int64, device="cuda")
         with torch.cuda.stream(self.stream):
             dist.all_gather_into_tensor(gathered, part)
-        out = torch.zeros((batch, 8), dtype=torch.int64, device="cuda")
         _lib.check(lib.sb_msm_combine_batch_device(sess.ck.curve, ctypes.c_void_p(gathered.data_ptr()), self.world, batch, batch,
                                                    ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(self.stream.cuda_stream)))
         with torch.cuda.stream(self.stream):
@@ -200,8 +208,7 @@ def gpu_step(sides, extras, upload, combiner):
             from sirius_b200 import _lib
 
             lib = _lib.load()
-            c1 = np.ascontiguousarray(np.concatenate([ex["c1"].reshape(-1, 4), ex["u1"].reshape(1, 4)]), dtype=np.uint64)
-            c2 = np.ascontiguousarray(np.concatenate([ex["c2"].reshape(-1, 4), sess.one]), dtype=np.uint64)
+            c1, c2 = sess.challenge_vectors(ex["c1"], ex["u1"], ex["c2"])
             _lib.check(lib.sb_cross_terms_device(sess.S._hom_prog._h, sess.d, sess.S._cols, sess._cols(sess.W_acc), sess._cols(sess.W_in), sess.A,
                                                  c1.ctypes.data_as(_lib.u64p), c2.ctypes.data_as(_lib.u64p), c1.shape[0],
                                                  ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(sess.stream.cuda_stream)))

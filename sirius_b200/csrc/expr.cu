@@ -246,6 +246,8 @@ struct sb_prog {
     void* d_rotations;
     void* d_args;  // per-call tables: column pointer arrays, challenge table, Vandermonde inverse, r powers
     size_t args_cap;
+    uint32_t vinv_degree;  // inverse Vandermonde on 0..degree, built once per (program, degree)
+    void* d_vinv;
     std::vector<uint32_t> poly_indices;  // distinct column indices the program reads (for validation)
     uint32_t max_challenge;
     bool uses_challenge;
@@ -449,7 +451,17 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
     const size_t ptr_bytes = align_up(sizeof(void*) * nfv * 2, 32);
     const size_t ch_bytes = (size_t)32 * m * (num_challenges ? num_challenges : 1);
     const size_t vinv_bytes = (size_t)32 * m * m;
-    SB_TRY(args_reserve(prog, ptr_bytes + ch_bytes + vinv_bytes));
+    SB_TRY(args_reserve(prog, ptr_bytes + ch_bytes));
+    if (prog->vinv_degree != degree || !prog->d_vinv) {
+        std::vector<F> vinv;
+        host_vandermonde_inverse<F>(degree, vinv);
+        if (prog->d_vinv) cudaFree(prog->d_vinv);
+        prog->d_vinv = nullptr;
+        SB_CUDA_TRY(cudaMalloc(&prog->d_vinv, vinv_bytes));
+        SB_CUDA_TRY(cudaMemcpyAsync(prog->d_vinv, vinv.data(), vinv_bytes, cudaMemcpyHostToDevice, st));
+        SB_CUDA_TRY(cudaStreamSynchronize(st));
+        prog->vinv_degree = degree;
+    }
     char* d = (char*)prog->d_args;
     // challenge table: c1 + t*c2 for t = 0..degree, built on the host with the portable field code
     std::vector<F> table((size_t)m * (num_challenges ? num_challenges : 1));
@@ -463,14 +475,11 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
             cur = add_portable(cur, c2);
         }
     }
-    std::vector<F> vinv;
-    host_vandermonde_inverse<F>(degree, vinv);
     if (nfv) {
         SB_CUDA_TRY(cudaMemcpyAsync(d, h_adv1, sizeof(void*) * nfv, cudaMemcpyHostToDevice, st));
         SB_CUDA_TRY(cudaMemcpyAsync(d + sizeof(void*) * nfv, h_adv2, sizeof(void*) * nfv, cudaMemcpyHostToDevice, st));
     }
     if (num_challenges) SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes, table.data(), 32 * table.size(), cudaMemcpyHostToDevice, st));
-    SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes + ch_bytes, vinv.data(), vinv_bytes, cudaMemcpyHostToDevice, st));
     // the staging vectors die at return: pageable cudaMemcpyAsync has already copied them out
     EvalArgs<F> A;
     SB_TRY(fill_args<F>(prog, cols, h_adv1, h_adv2, nfv, A));
@@ -493,7 +502,7 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
     SB_CUDA_TRY(cudaFuncSetAttribute(k_cross_terms<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
         ProfScope ps(st, PROF_CROSS_TERMS, n);
-        k_cross_terms<F><<<(n + rows_per_block - 1) / rows_per_block, threads, smem, st>>>(A, degree, rows_per_block, (const F*)(d + ptr_bytes + ch_bytes), (F*)d_out);
+        k_cross_terms<F><<<(n + rows_per_block - 1) / rows_per_block, threads, smem, st>>>(A, degree, rows_per_block, (const F*)prog->d_vinv, (F*)d_out);
         SB_KERNEL_CHECK();
     }
     return SB_OK;
@@ -664,6 +673,8 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
     p->num_constants = (uint32_t)n_constants;
     p->num_rotations = (uint32_t)n_rotations;
     p->d_ops = p->d_constants = p->d_rotations = p->d_args = nullptr;
+    p->vinv_degree = 0;
+    p->d_vinv = nullptr;
     p->args_cap = 0;
     Runtime& rt = runtime();
     std::lock_guard<std::mutex> lk(rt.mu);
@@ -689,6 +700,7 @@ void sb_expr_free(sb_prog_t p) {
     if (p->d_constants) cudaFree(p->d_constants);
     if (p->d_rotations) cudaFree(p->d_rotations);
     if (p->d_args) cudaFree(p->d_args);
+    if (p->d_vinv) cudaFree(p->d_vinv);
     delete p;
 }
 

@@ -46,6 +46,7 @@ class DeviceSangriaSide:
         self.h_commit_W = torch.zeros(8, dtype=i64).pin_memory()
         self.h_commit_T = torch.zeros((self.d, 8), dtype=i64).pin_memory()
         self.one = _to_mont([1], S.modulus)
+        self._ch_cache = {}   # id-keyed cache of the concatenated challenge vectors (host-side glue, built once)
 
     # ---- data movement
     def upload_incoming(self, host_W_pinned) -> int:
@@ -56,7 +57,13 @@ class DeviceSangriaSide:
 
     def _cols(self, t):
         base = t.data_ptr()
-        return _vp_array([base + j * self.n * 32 for j in range(self.A)])
+        hit = getattr(self, "_cols_cache", None)
+        if hit is None:
+            hit = self._cols_cache = {}
+        arr = hit.get(base)
+        if arr is None:
+            arr = hit[base] = _vp_array([base + j * self.n * 32 for j in range(self.A)])
+        return arr
 
     # ---- PlonkStructure::run_sps_protocol's commit (src/plonk/mod.rs:441-445)
     def commit_incoming(self) -> np.ndarray:
@@ -71,8 +78,7 @@ class DeviceSangriaSide:
     def commit_cross_terms(self, U1_challenges: np.ndarray, U1_u: np.ndarray, U2_challenges: np.ndarray) -> np.ndarray:
         lib = _lib.load()
         st = self.stream.cuda_stream
-        c1 = np.ascontiguousarray(np.concatenate([U1_challenges.reshape(-1, 4), U1_u.reshape(1, 4)]), dtype=np.uint64)
-        c2 = np.ascontiguousarray(np.concatenate([U2_challenges.reshape(-1, 4), self.one]), dtype=np.uint64)
+        c1, c2 = self.challenge_vectors(U1_challenges, U1_u, U2_challenges)
         _lib.check(
             lib.sb_cross_terms_device(
                 self.S._hom_prog._h, self.d, self.S._cols, self._cols(self.W_acc), self._cols(self.W_in), self.A,
@@ -84,6 +90,18 @@ class DeviceSangriaSide:
             self.h_commit_T.copy_(self.commit_T, non_blocking=True)
         self.stream.synchronize()  # cross-term commitments feed generate_challenge (:162-179)
         return self.h_commit_T.numpy().view(np.uint64).copy()
+
+    def challenge_vectors(self, U1_challenges, U1_u, U2_challenges):
+        """[U1.challenges.., U1.u] and [U2.challenges.., 1] (src/nifs/sangria/mod.rs:113-118)."""
+        key = (U1_challenges.tobytes(), U1_u.tobytes(), U2_challenges.tobytes())
+        hit = self._ch_cache.get(key)
+        if hit is None:
+            c1 = np.ascontiguousarray(np.concatenate([U1_challenges.reshape(-1, 4), U1_u.reshape(1, 4)]), dtype=np.uint64)
+            c2 = np.ascontiguousarray(np.concatenate([U2_challenges.reshape(-1, 4), self.one]), dtype=np.uint64)
+            if len(self._ch_cache) > 64:
+                self._ch_cache.clear()
+            hit = self._ch_cache[key] = (c1, c2)
+        return hit
 
     def fold(self, r: np.ndarray) -> None:
         """W <- W + r*W_in ; E <- E + sum r^j T_j   (accumulator.rs:363-404); buffers are swapped, not copied."""
