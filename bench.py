@@ -139,7 +139,7 @@ def build_side_gpu(side, rank, world, stream):
     stream.synchronize()
     # window width: 16 bits at 2^17 rows; one bit less per halving of the local rows keeps the bucket work
     # (2^(c-1) buckets per commitment) in proportion to the local points
-    window_bits = {1: 16, 2: 15, 4: 14, 8: 13}.get(world, 13)
+    window_bits = int(os.environ.get("SB_BENCH_WINDOW", "0")) or {1: 16, 2: 15, 4: 14, 8: 13}.get(world, 13)
     ck = sirius_b200.CommitmentKey.from_device(side["curve"], d_bases.data_ptr(), nadv * n_loc, window_bits=window_bits, stream=stream.cuda_stream)
     stream.synchronize()
     del d_bases

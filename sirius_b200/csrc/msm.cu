@@ -610,13 +610,20 @@ namespace sb {
 
 static Scratch g_ws;
 
+// Window width per key size, measured on B200 (profiles/r1_window_tuning.txt).  Only widths at which the window
+// count W = floor(254/c)+1 drops are worth having (c = 13, 15, 16, 17, 19, 20): a wider window with the same W only
+// doubles the buckets.
 static int default_window_bits(size_t n) {
     int lg = 0;
     while (((size_t)1 << lg) < n) lg++;
-    int c = lg - 5;
-    if (c < 8) c = 8;
-    if (c > 20) c = 20;
-    return c;
+    if (lg <= 12) return 10;
+    if (lg <= 14) return 11;
+    if (lg <= 16) return 13;
+    if (lg <= 17) return 15;
+    if (lg <= 19) return 16;
+    if (lg <= 22) return 17;
+    if (lg <= 23) return 19;
+    return 20;
 }
 
 struct MsmPlan {
