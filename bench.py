@@ -137,10 +137,12 @@ def build_side_gpu(side, rank, world, stream):
         _lib.check(lib.sb_index_multiples_device(side["curve"], g.ctypes.data_as(_lib.u64p), first, count,
                                                  ctypes.c_void_p(d_bases.data_ptr() + col * n_loc * 64), ctypes.c_void_p(stream.cuda_stream)))
     stream.synchronize()
-    # window width: 16 bits at 2^17 rows; one bit less per halving of the local rows keeps the bucket work
-    # (2^(c-1) buckets per commitment) in proportion to the local points
-    window_bits = int(os.environ.get("SB_BENCH_WINDOW", "0")) or {1: 16, 2: 15, 4: 14, 8: 13}.get(world, 13)
-    ck = sirius_b200.CommitmentKey.from_device(side["curve"], d_bases.data_ptr(), nadv * n_loc, window_bits=window_bits, stream=stream.cuda_stream)
+    # several window widths per key: each commit picks the cheapest one for its size (the W commits want wide
+    # windows, the batched cross-term commits of 2^17/world scalars narrow ones)
+    windows = [int(x) for x in os.environ.get("SB_BENCH_WINDOWS", "16,13,15,17").split(",")]
+    ck = sirius_b200.CommitmentKey.from_device(side["curve"], d_bases.data_ptr(), nadv * n_loc, window_bits=windows[0], stream=stream.cuda_stream)
+    for wb in windows[1:]:
+        ck.add_window(wb, stream.cuda_stream)
     stream.synchronize()
     del d_bases
     sess = device.DeviceSangriaSide(S, ck, stream)

@@ -82,6 +82,9 @@ int sb_ck_register(int curve, const uint64_t* bases_xy, size_t n, int window_bit
 /* Same, the generators already being in device memory. */
 int sb_ck_register_device(int curve, const void* d_bases_xy, size_t n, int window_bits, void* stream, sb_ck_t* out);
 void sb_ck_release(sb_ck_t ck);
+/* Register one more window width for this key; every commit picks the cheapest registered width for its size
+ * (large commits want wide windows, the small batched cross-term commits narrow ones). */
+int sb_ck_add_window(sb_ck_t ck, int window_bits, void* stream);
 size_t sb_ck_len(sb_ck_t ck);
 int sb_ck_window_bits(sb_ck_t ck);
 

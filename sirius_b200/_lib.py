@@ -33,6 +33,7 @@ SIGNATURES = {
     "sb_ck_register": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(vp)]),
     "sb_ck_register_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_int, vp, ctypes.POINTER(vp)]),
     "sb_ck_release": (None, [vp]),
+    "sb_ck_add_window": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "sb_ck_len": (ctypes.c_size_t, [vp]),
     "sb_ck_window_bits": (ctypes.c_int, [vp]),
     "sb_msm": (ctypes.c_int, [vp, u64p, ctypes.c_size_t, u64p]),

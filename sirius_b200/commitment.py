@@ -57,6 +57,10 @@ class CommitmentKey:
     def is_empty(self) -> bool:
         return self.len() == 0
 
+    def add_window(self, window_bits: int, stream: int = 0) -> None:
+        """Register a further window width; commits pick the cheapest registered width per call."""
+        _lib.check(_lib.load().sb_ck_add_window(self._h, int(window_bits), ctypes.c_void_p(stream or None)))
+
     @property
     def window_bits(self) -> int:
         return int(_lib.load().sb_ck_window_bits(self._h))

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <vector>
 #include <new>
 
 #include "common.cuh"
@@ -598,12 +599,18 @@ __global__ void k_combine(const XYZZ<F>* __restrict__ parts, int count, size_t s
 // ------------------------------------------------------------------------------------------------
 }  // namespace sb
 
-struct sb_ck {
-    int curve;
-    size_t n;
+struct sb_ck_table {
     int c, W;
     uint32_t K;
     void* table;  // Affine[W][n]
+};
+struct sb_ck {
+    int curve;
+    size_t n;
+    int c, W;      // primary table (also tables[0])
+    uint32_t K;
+    void* table;
+    std::vector<sb_ck_table> tables;  // every registered window width; the commit picks the cheapest per call
 };
 
 namespace sb {
@@ -627,6 +634,8 @@ static int default_window_bits(size_t n) {
 }
 
 struct MsmPlan {
+    int c, W;            // window width / count of the table chosen for this call
+    const void* table;
     size_t n, total, nW, chunks;
     uint32_t batch, K, KB, tiles, nodes0;
     int ls_log;
@@ -639,9 +648,21 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     p.n = n;
     p.batch = (uint32_t)batch;
     p.total = n * batch;
-    p.nW = p.total * (size_t)ck->W;
-    p.K = ck->K;
-    const uint64_t kb = (uint64_t)ck->K * batch;
+    {   // cheapest registered window width: ~W mixed additions per scalar + ~12 addition-equivalents per bucket
+        // (fix-up, row/column sums and their latency), fitted to profiles/r1_window_tuning.txt
+        const sb_ck_table* best = nullptr;
+        double best_cost = 0;
+        for (const sb_ck_table& t : ck->tables) {
+            double cost = (double)p.total * t.W + 12.0 * (double)batch * t.K;
+            if (!best || cost < best_cost) { best = &t; best_cost = cost; }
+        }
+        p.c = best->c;
+        p.W = best->W;
+        p.K = best->K;
+        p.table = best->table;
+    }
+    p.nW = p.total * (size_t)p.W;
+    const uint64_t kb = (uint64_t)p.K * batch;
     if (p.nW >= (1ull << 31) || kb > (1ull << 25)) {
         set_error("sb_msm: batch too large (n*W*batch = %zu, buckets = %llu)", p.nW, (unsigned long long)kb);
         return SB_ERR_ARG;
@@ -678,7 +699,7 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     p.off_pt = take(p.chunks * 128);
     p.off_heavy = take((p.chunks / FIX_SEQ + 2) * 4);
     {
-        const int log_k = ck->c - 1, lc = (log_k + 1) / 2;
+        const int log_k = p.c - 1, lc = (log_k + 1) / 2;
         p.off_nodes_a = take((((size_t)1 << lc) + ((size_t)p.K >> lc)) * batch * 128);  // row + column sums
         p.off_nodes_b = take((size_t)batch * 2 * 128);                                   // X, Y
     }
@@ -710,7 +731,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     {
         ProfScope ps(st, PROF_DECOMPOSE, p.total);
         SB_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)KB + 1) * 4, st));
-        k_decompose<S><<<(total + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, total, stride, K, ck->c, ck->W, dig, counts);
+        k_decompose<S><<<(total + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, total, stride, K, p.c, p.W, dig, counts);
         SB_KERNEL_CHECK();
     }
     ProfScope* sort_scope = new ProfScope(st, PROF_SORT, p.nW);
@@ -720,7 +741,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     SB_KERNEL_CHECK();
     k_scan_apply<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets, cursor);
     SB_KERNEL_CHECK();
-    k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, ck->W, cursor, ekey, eidx);
+    k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, cursor, ekey, eidx);
     delete sort_scope;
     SB_KERNEL_CHECK();
     {
@@ -731,13 +752,13 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         }();
         ProfScope ps(st, PROF_ACCUMULATE, p.total);
         if (minb == 5)
-            k_accumulate<F, 5><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 5><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else if (minb == 6)
-            k_accumulate<F, 6><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 6><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else if (minb == 3)
-            k_accumulate<F, 3><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 3><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else
-            k_accumulate<F, 4><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)ck->table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 4><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         SB_KERNEL_CHECK();
     }
     {
@@ -748,7 +769,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         SB_KERNEL_CHECK();
     }
     {
-        const int log_k = ck->c - 1;
+        const int log_k = p.c - 1;
         const int lc = (log_k + 1) / 2;
         const uint32_t C = 1u << lc, R = K >> lc;
         auto* vec = (XYZZ<F>*)(ws + p.off_nodes_a);   // [batch][R + C]
@@ -784,48 +805,64 @@ static int msm_dispatch(const sb_ck* ck, const MsmPlan& p, char* ws, const void*
     return msm_enqueue<Fr, Fq>(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st);
 }
 
+static int ck_add_table(sb_ck* ck, const void* d_bases, int c, cudaStream_t st) {
+    if (c < 2 || c > 24) {
+        set_error("sb_ck: window_bits %d out of range [2,24]", c);
+        return SB_ERR_ARG;
+    }
+    for (const sb_ck_table& t : ck->tables)
+        if (t.c == c) return SB_OK;
+    const int W = 254 / c + 1;
+    const size_t n = ck->n;
+    if ((uint64_t)n * (uint64_t)W >= (1ull << 31)) {
+        set_error("sb_ck: n*W = %zu*%d does not fit the 31-bit table index", n, W);
+        return SB_ERR_ARG;
+    }
+    sb_ck_table t;
+    t.c = c;
+    t.W = W;
+    t.K = 1u << (c - 1);
+    t.table = nullptr;
+    if (n) {
+        cudaError_t e = cudaMalloc(&t.table, n * (size_t)W * 64);
+        if (e != cudaSuccess) {
+            set_error("sb_ck: cudaMalloc(%zu) failed: %s", n * (size_t)W * 64, cudaGetErrorString(e));
+            return SB_ERR_OOM;
+        }
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        if (ck->curve == CURVE_BN256) k_precompute<Fq><<<blocks, 128, 0, st>>>((const Affine<Fq>*)d_bases, n, c, W, (Affine<Fq>*)t.table);
+        else k_precompute<Fr><<<blocks, 128, 0, st>>>((const Affine<Fr>*)d_bases, n, c, W, (Affine<Fr>*)t.table);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
+        if (e2 != cudaSuccess) {
+            set_error("sb_ck: precompute failed: %s", cudaGetErrorString(e2));
+            cudaFree(t.table);
+            return SB_ERR_CUDA;
+        }
+    }
+    ck->tables.push_back(t);
+    return SB_OK;
+}
+
 static int ck_build(int curve, const void* d_bases, size_t n, int window_bits, cudaStream_t st, sb_ck_t* out) {
     if (curve != CURVE_BN256 && curve != CURVE_GRUMPKIN) {
         set_error("sb_ck_register: unknown curve %d", curve);
         return SB_ERR_ARG;
     }
     int c = window_bits > 0 ? window_bits : default_window_bits(n);
-    if (c < 2 || c > 24) {
-        set_error("sb_ck_register: window_bits %d out of range [2,24]", c);
-        return SB_ERR_ARG;
-    }
-    int W = 254 / c + 1;
-    if ((uint64_t)n * (uint64_t)W >= (1ull << 31)) {
-        set_error("sb_ck_register: n*W = %zu*%d does not fit the 31-bit table index", n, W);
-        return SB_ERR_ARG;
-    }
     sb_ck* ck = new (std::nothrow) sb_ck();
     if (!ck) return SB_ERR_OOM;
     ck->curve = curve;
     ck->n = n;
-    ck->c = c;
-    ck->W = W;
-    ck->K = 1u << (c - 1);
-    ck->table = nullptr;
-    if (n) {
-        cudaError_t e = cudaMalloc(&ck->table, n * (size_t)W * 64);
-        if (e != cudaSuccess) {
-            set_error("sb_ck_register: cudaMalloc(%zu) failed: %s", n * (size_t)W * 64, cudaGetErrorString(e));
-            delete ck;
-            return SB_ERR_OOM;
-        }
-        unsigned blocks = (unsigned)((n + 127) / 128);
-        if (curve == CURVE_BN256) k_precompute<Fq><<<blocks, 128, 0, st>>>((const Affine<Fq>*)d_bases, n, c, W, (Affine<Fq>*)ck->table);
-        else k_precompute<Fr><<<blocks, 128, 0, st>>>((const Affine<Fr>*)d_bases, n, c, W, (Affine<Fr>*)ck->table);
-        cudaError_t e2 = cudaGetLastError();
-        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(st);
-        if (e2 != cudaSuccess) {
-            set_error("sb_ck_register: precompute failed: %s", cudaGetErrorString(e2));
-            cudaFree(ck->table);
-            delete ck;
-            return SB_ERR_CUDA;
-        }
+    int rc = ck_add_table(ck, d_bases, c, st);
+    if (rc != SB_OK) {
+        delete ck;
+        return rc;
     }
+    ck->c = ck->tables[0].c;
+    ck->W = ck->tables[0].W;
+    ck->K = ck->tables[0].K;
+    ck->table = ck->tables[0].table;
     *out = ck;
     return SB_OK;
 }
@@ -872,8 +909,22 @@ int sb_ck_register_device(int curve, const void* d_bases_xy, size_t n, int windo
 
 void sb_ck_release(sb_ck_t ck) {
     if (!ck) return;
-    if (ck->table) cudaFree(ck->table);
+    for (sb_ck_table& t : ck->tables)
+        if (t.table) cudaFree(t.table);
     delete ck;
+}
+
+/* A further window width for the same key: table 0 holds the generators themselves (window 0 of any table), so
+ * additional tables are derived on the device.  Commits then use whichever registered width is cheapest. */
+int sb_ck_add_window(sb_ck_t ck, int window_bits, void* stream) {
+    if (!ck || ck->tables.empty()) {
+        set_error("sb_ck_add_window: bad key");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    return ck_add_table(ck, ck->tables[0].table, window_bits, stream ? (cudaStream_t)stream : rt.stream);
 }
 
 size_t sb_ck_len(sb_ck_t ck) { return ck ? ck->n : 0; }

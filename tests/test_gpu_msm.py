@@ -121,6 +121,25 @@ def test_msm_batch(sb, oracle, curve):
     ck.close()
 
 
+def test_msm_multiple_window_tables(sb, oracle):
+    """a key with several registered window widths: every commit picks one per call, results never change"""
+    curve = R.CURVE_GRUMPKIN
+    n = 1 << 14
+    bases = oracle.running_bases(curve, n)
+    ck = sb.CommitmentKey(curve, bases, window_bits=8)
+    s = _scalars(oracle, curve, n, 5, "uniform")
+    ref_full, ref_small = oracle.msm(curve, s, bases), oracle.msm(curve, s[:300], bases)
+    assert np.array_equal(ck.commit(s), ref_full)
+    for wb in (13, 11, 16):
+        ck.add_window(wb)
+        assert np.array_equal(ck.commit(s), ref_full)
+        assert np.array_equal(ck.commit(s[:300]), ref_small)
+        got = ck.commit_batch([s, s[::-1].copy(), s])
+        assert np.array_equal(got[0], ref_full) and np.array_equal(got[2], ref_full)
+        assert np.array_equal(got[1], oracle.msm(curve, s[::-1].copy(), bases))
+    ck.close()
+
+
 def test_msm_too_long_input(sb, oracle):
     bases = oracle.running_bases(R.CURVE_BN256, 8)
     ck = sb.CommitmentKey(R.CURVE_BN256, bases)
