@@ -364,7 +364,7 @@ def gpu_side_metrics(stream):
 
     out = {}
     n = 1 << 20
-    ck = device.synthetic_key(0, n, window_bits=16, stream=stream)
+    ck = device.synthetic_key(0, n, stream=stream)
     s = device.random_field_device(n, SEED + 77)
     o = torch.zeros(8, dtype=torch.int64, device="cuda")
     for _ in range(3):

@@ -277,9 +277,10 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ counts, uint32_t K, co
     }
 }
 
-// entry (bucket key, table index | sign<<31) placed at its bucket's next free slot
+// entry (table index | sign<<31) placed at its bucket's next free slot; the bucket of a sorted position is
+// recovered from `offsets` (k_chunk_heads + a walk in k_accumulate), so no key array is written
 __global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t total, uint32_t K, uint32_t n_ck, int W,
-                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ ekey, uint32_t* __restrict__ eidx) {
+                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ eidx) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const uint32_t batch = i / n;
@@ -289,7 +290,6 @@ __global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t
         if (d) {
             uint32_t b = batch * K + (d & 0x7fffffffu) - 1;
             uint32_t pos = atomicAdd(&cursor[b], 1u);
-            ekey[pos] = b;
             eidx[pos] = ((uint32_t)w * n_ck + pt) | (d & 0x80000000u);
         }
     }
@@ -298,12 +298,23 @@ __global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t
 // ------------------------------------------------------------------------------------------------
 // bucket sums
 // ------------------------------------------------------------------------------------------------
+// chunk_head[t] = bucket that contains sorted position t*LS (one thread per bucket, writes one entry per chunk start
+// inside its range: #chunks writes in total instead of one key per entry)
+__global__ void k_chunk_heads(const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, uint32_t* __restrict__ chunk_head) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= KB) return;
+    const uint32_t o = offsets[b], o2 = offsets[b + 1];
+    if (o2 == o) return;
+    const uint32_t LS = 1u << ls_log;
+    for (uint32_t t = (o + LS - 1) >> ls_log; ((uint64_t)t << ls_log) < o2; t++) chunk_head[t] = b;
+}
+
 // Thread t owns sorted entries [t*LS, (t+1)*LS), LS = 2^ls_log.  A bucket lying entirely inside the chunk is
 // written to buckets[]; a piece of a bucket that continues into a neighbouring chunk goes to PH[t] (piece
 // starts at the chunk start) or PT[t] (piece ends at the chunk end) and is finished by k_fixup.
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ ekey, const uint32_t* __restrict__ eidx,
+k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ chunk_head, const uint32_t* __restrict__ eidx,
              const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* __restrict__ buckets,
              XYZZ<F>* __restrict__ PH, XYZZ<F>* __restrict__ PT) {
     const uint32_t M = offsets[KB];
@@ -314,7 +325,8 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ e
     const uint32_t LS = 1u << ls_log;
     const uint32_t end = (M - start < LS) ? M : start + LS;
 
-    uint32_t cur = ekey[start];
+    uint32_t cur = chunk_head[t];               // offsets[cur] <= start < offsets[cur + 1]
+    uint32_t cur_end = offsets[cur + 1];
     uint32_t seg_start = start;
     XYZZ<F> acc = XYZZ<F>::identity();
     uint32_t e = eidx[start];
@@ -322,23 +334,27 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ e
 #pragma unroll 1
     for (uint32_t pos = start; pos < end; pos++) {
         // prefetch the next entry's base while this one is being added
-        uint32_t k_next = cur, e_next = 0;
+        uint32_t e_next = 0;
         Affine<F> base_next;
         if (pos + 1 < end) {
-            k_next = ekey[pos + 1];
             e_next = eidx[pos + 1];
             base_next = load_vec_nc(table + (e_next & 0x7fffffffu));
         }
         xyzz_madd(acc, base, (e >> 31) != 0);
-        if (pos + 1 == end || k_next != cur) {
+        if (pos + 1 == end || pos + 1 == cur_end) {
             const uint32_t seg_end = pos + 1;
-            const uint32_t o = offsets[cur], o2 = offsets[cur + 1];
-            if (o == seg_start && o2 == seg_end) store_vec(buckets + cur, acc);
+            const uint32_t o = offsets[cur];
+            if (o == seg_start && cur_end == seg_end) store_vec(buckets + cur, acc);
             else if (seg_start == start) store_vec(PH + t, acc);
             else store_vec(PT + t, acc);
             acc = XYZZ<F>::identity();
             seg_start = seg_end;
-            cur = k_next;
+            if (seg_end < end) {                 // next non-empty bucket
+                do {
+                    cur++;
+                    cur_end = offsets[cur + 1];
+                } while (cur_end <= seg_end);
+            }
         }
         e = e_next;
         base = base_next;
@@ -419,7 +435,7 @@ k_fixup_heavy(const uint32_t* __restrict__ offsets, int ls_log, XYZZ<F>* __restr
 // Stage 2 (k_weighted_digits) reduces a short vector E_0..E_{n-1} with weights (j + w0) by octal digit sums:
 //     sum_j j * E_j = sum_i 8^i sum_{v=1..7} v * D[i][v],   D[i][v] = sum_{j: digit_i(j) = v} E_j   (plain sums, one warp each)
 // and finishes with quad-lane additions (quad.cuh): 7-term weighted sums, Horner over the digit positions.
-// Stage 3 (k_reduce_final) combines  C * X + Y  and normalises to affine.
+// Stage 3 (k_reduce_final) adds the two parts and normalises to affine.
 template <class F>
 SB_D XYZZ<F> warp_sum_call(XYZZ<F> v) {  // all lanes end with the warp total (scalar additions)
 #pragma unroll 1
@@ -539,18 +555,19 @@ k_weighted_digits(const XYZZ<F>* __restrict__ vec_all, int log_k, int lc, XYZZ<F
         if (which == 1) {  // weights q + 1
             XYZZ<F> s0 = S0;
             quad_add(horner, s0);
+        } else {           // the row part carries the factor C = 2^lc (done here, beside the column block)
+            for (int k = 0; k < lc; k++) quad_double(horner);
         }
         if (lane == 0) store_vec(xy_all + (size_t)blockIdx.y * 2 + which, horner);
     }
 }
 
-// root = C * X + Y ; out = affine(root)
+// root = C*X + Y (both already weighted) ; out = affine(root)
 template <class F>
-__global__ void k_reduce_final(const XYZZ<F>* __restrict__ xy_all, int lc, uint32_t batch, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
+__global__ void k_reduce_final(const XYZZ<F>* __restrict__ xy_all, uint32_t batch, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
     const uint32_t b = blockIdx.x;
     if (b >= batch) return;
     XYZZ<F> acc = load_vec(xy_all + (size_t)b * 2);
-    for (int k = 0; k < lc; k++) quad_double(acc);
     XYZZ<F> y = load_vec(xy_all + (size_t)b * 2 + 1);
     quad_add(acc, y);
     if (threadIdx.x == 0) {
@@ -692,7 +709,7 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     p.off_offsets = take(((size_t)p.KB + 1) * 4);
     p.off_cursor = take((size_t)p.KB * 4);
     p.off_tiles = take(8192 * 4);
-    p.off_ekey = take(p.nW * 4);
+    p.off_ekey = take((p.chunks + 1) * 4);  // chunk heads
     p.off_eidx = take(p.nW * 4);
     p.off_buckets = take((size_t)p.KB * 128);
     p.off_ph = take(p.chunks * 128);
@@ -719,7 +736,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     auto* offsets = (uint32_t*)(ws + p.off_offsets);
     auto* cursor = (uint32_t*)(ws + p.off_cursor);
     auto* tiles = (uint32_t*)(ws + p.off_tiles);
-    auto* ekey = (uint32_t*)(ws + p.off_ekey);
+    auto* chunk_head = (uint32_t*)(ws + p.off_ekey);
     auto* eidx = (uint32_t*)(ws + p.off_eidx);
     auto* buckets = (XYZZ<F>*)(ws + p.off_buckets);
     auto* PH = (XYZZ<F>*)(ws + p.off_ph);
@@ -741,7 +758,9 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     SB_KERNEL_CHECK();
     k_scan_apply<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets, cursor);
     SB_KERNEL_CHECK();
-    k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, cursor, ekey, eidx);
+    k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, cursor, eidx);
+    SB_KERNEL_CHECK();
+    k_chunk_heads<<<(KB + 255) / 256, 256, 0, st>>>(offsets, KB, p.ls_log, chunk_head);
     delete sort_scope;
     SB_KERNEL_CHECK();
     {
@@ -752,13 +771,13 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         }();
         ProfScope ps(st, PROF_ACCUMULATE, p.total);
         if (minb == 5)
-            k_accumulate<F, 5><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 5><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else if (minb == 6)
-            k_accumulate<F, 6><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 6><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else if (minb == 3)
-            k_accumulate<F, 3><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 3><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else
-            k_accumulate<F, 4><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, ekey, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 4><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         SB_KERNEL_CHECK();
     }
     {
@@ -785,7 +804,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         }
         {
             ProfScope pf(st, PROF_FINALIZE, p.batch);
-            k_reduce_final<F><<<p.batch, 4, 0, st>>>(xy, lc, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
+            k_reduce_final<F><<<p.batch, 4, 0, st>>>(xy, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
             SB_KERNEL_CHECK();
         }
     }
