@@ -140,6 +140,17 @@ def test_msm_multiple_window_tables(sb, oracle):
     ck.close()
 
 
+def test_msm_public_bn256_vector(sb):
+    """commit([2], [(1,2)]) on the GPU equals the public alt_bn128 doubling vector (tests/golden/bn256_g1_kat.json)"""
+    import json, os
+
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bn256_g1_kat.json")))
+    exp = tuple(int(v) for v in kat["two_G_dec"])
+    ck = sb.CommitmentKey(R.CURVE_BN256, R.points_to_limbs([tuple(kat["G"])], R.CURVE_BN256))
+    assert R.limbs_to_points(ck.commit(R.to_mont_limbs([2], R.FR)), R.CURVE_BN256) == [exp]
+    ck.close()
+
+
 def test_msm_too_long_input(sb, oracle):
     bases = oracle.running_bases(R.CURVE_BN256, 8)
     ck = sb.CommitmentKey(R.CURVE_BN256, bases)

@@ -126,3 +126,24 @@ def test_msm_cancellation_gives_identity(oracle):
     s = R.to_mont_limbs([5, R.FR - 5], R.FR)
     out = oracle.msm(curve, s, b)
     assert not out.any()  # identity encoded (0,0)
+
+
+def test_bn256_public_doubling_vector(oracle):
+    """An external anchor for the bn256 group law (the reference itself has no known-answer test for commit):
+    2*(1,2) from the public alt_bn128 / EIP-196 vectors, and the group order r*(1,2) = identity."""
+    import json, os
+
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bn256_g1_kat.json")))
+    G = tuple(kat["G"])
+    exp = tuple(int(v) for v in kat["two_G_dec"])
+    assert R.ec_add(G, G, R.CURVE_BN256) == exp
+    b = R.points_to_limbs([G], R.CURVE_BN256)
+    two = R.to_mont_limbs([2], R.FR)
+    assert R.limbs_to_points(oracle.msm(R.CURVE_BN256, two, b), R.CURVE_BN256) == [exp]
+    assert R.limbs_to_points(oracle.msm_naive(R.CURVE_BN256, two, b), R.CURVE_BN256) == [exp]
+    # (r-1)*G == -G  <=>  r*G == identity, on both curves of the cycle
+    for curve in (R.CURVE_BN256, R.CURVE_GRUMPKIN):
+        g = R.CURVE_GEN[curve]
+        m1 = R.to_mont_limbs([R.CURVE_SCALAR[curve] - 1], R.CURVE_SCALAR[curve])
+        got = oracle.msm(curve, m1, R.points_to_limbs([g], curve))
+        assert R.limbs_to_points(got, curve) == [R.ec_neg(g, curve)]
