@@ -769,7 +769,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
             const char* e = getenv("SB_ACC_MINB");
             return e ? atoi(e) : 4;
         }();
-        ProfScope ps(st, PROF_ACCUMULATE, p.total);
+        ProfScope ps(st, PROF_ACCUMULATE, p.nW);  // units: mixed additions (upper bound: zero digits are skipped)
         if (minb == 5)
             k_accumulate<F, 5><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else if (minb == 6)
