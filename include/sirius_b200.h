@@ -13,6 +13,8 @@
  *     is in host memory.  "_device" entry points take device pointers on the current device and enqueue on
  *     the given CUDA stream (cudaStream_t passed as void*; NULL = the library's stream), returning without
  *     synchronising.
+ *   - "_device" entry points of one family share a grow-only device workspace: enqueue them on ONE stream (or
+ *     synchronise between streams); calls are serialised on an internal mutex at enqueue time only.
  *   - There is no CPU fallback: without a CUDA device every call fails with SB_ERR_CUDA.
  */
 #ifndef SIRIUS_B200_H

@@ -38,11 +38,6 @@ constexpr int SCAN_ITEMS = 16;  // items per thread in the scan kernels
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
 
-template <class F>
-struct alignas(16) Node {  // subtree summary for sum_b (b+1) B_b : S = sum B_b, Wt = sum (b - first + 1) B_b
-    XYZZ<F> S, Wt;
-};
-
 // ------------------------------------------------------------------------------------------------
 // 128-bit global loads/stores of field-sized objects
 // ------------------------------------------------------------------------------------------------
@@ -79,24 +74,6 @@ SB_D void store_vec(T* p, const T& v) {
 // warp helpers on XYZZ points
 // ------------------------------------------------------------------------------------------------
 template <class F>
-SB_D XYZZ<F> shfl_point(const XYZZ<F>& v, int src_lane) {
-    XYZZ<F> r;
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
-    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-    for (int i = 0; i < 32; i++) d[i] = __shfl_sync(0xffffffffu, s[i], src_lane);
-    return r;
-}
-template <class F>
-SB_D XYZZ<F> shfl_down_point(const XYZZ<F>& v, int delta) {
-    XYZZ<F> r;
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
-    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-    for (int i = 0; i < 32; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
-    return r;
-}
-template <class F>
 SB_D XYZZ<F> shfl_xor_point(const XYZZ<F>& v, int mask) {
     XYZZ<F> r;
     const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
@@ -105,17 +82,6 @@ SB_D XYZZ<F> shfl_xor_point(const XYZZ<F>& v, int mask) {
     for (int i = 0; i < 32; i++) d[i] = __shfl_xor_sync(0xffffffffu, s[i], mask);
     return r;
 }
-// all lanes end with the sum over the warp
-template <class F>
-SB_D XYZZ<F> warp_sum(XYZZ<F> v) {
-#pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {
-        XYZZ<F> t = shfl_xor_point(v, d);
-        xyzz_add_call(v, t);
-    }
-    return v;
-}
-
 // ------------------------------------------------------------------------------------------------
 // register-time: table of window multiples
 // ------------------------------------------------------------------------------------------------
@@ -576,16 +542,6 @@ __global__ void k_reduce_final(const XYZZ<F>* __restrict__ xy_all, uint32_t batc
     }
 }
 
-// one thread per batch entry (one warp each, so the serial inversions run on different schedulers)
-template <class F>
-__global__ void k_finalize(const Node<F>* __restrict__ roots, uint32_t batch, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
-    const uint32_t b = blockIdx.x;
-    if (threadIdx.x != 0 || b >= batch) return;
-    XYZZ<F> r = load_vec(&roots[b].Wt);
-    if (out_xyzz) store_vec(out_xyzz + b, r);
-    if (out_xy) store_vec(out_xy + b, xyzz_to_affine<false>(r));
-}
-
 template <class F>
 __global__ void k_identity_out(uint32_t batch, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
     const uint32_t b = blockIdx.x;
@@ -654,7 +610,7 @@ struct MsmPlan {
     int c, W;            // window width / count of the table chosen for this call
     const void* table;
     size_t n, total, nW, chunks;
-    uint32_t batch, K, KB, tiles, nodes0;
+    uint32_t batch, K, KB, tiles;
     int ls_log;
     size_t off_dig, off_counts, off_offsets, off_cursor, off_tiles, off_ekey, off_eidx, off_buckets, off_ph, off_pt,
         off_heavy, off_nodes_a, off_nodes_b, off_out_xy, off_out_xyzz, off_scalars, total_bytes;
@@ -697,7 +653,6 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     }
     p.chunks = (p.nW + ((size_t)1 << p.ls_log) - 1) >> p.ls_log;
     p.tiles = (p.KB + SCAN_TILE - 1) / SCAN_TILE;
-    p.nodes0 = 64;  // digit-sum partials: npos(<=8) * 8 values * nsplit(<=8) XYZZ = 512 * 128 B = 256 Node-sized slots
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;

@@ -1,0 +1,106 @@
+"""CPU pinning of the Protogalaxy oracle (oracle/pg_ref.py) by the identities the reference's own tests use
+(src/nifs/protogalaxy/poly/mod.rs:639-853: cmp_with_direct_eval_of_F / _of_G, zero_f / zero_g) and by the
+Lagrange known-answer vector.  Both leaf-row modes."""
+import pytest
+
+from oracle import expr_ref as E
+from oracle import pg_ref as PG
+from oracle import pyref as R
+
+M = R.FR
+
+
+def _structure(k, T, seed, satisfied=False):
+    rng = R.Xoshiro256ss(seed)
+    n = 1 << k
+    nfix, nadv = 2 * T + 5, T + 2
+    gates = [E.main_gate_expression(T, 0, 0, 0, nfix)]
+    if satisfied:  # all-zero fixed columns: the gate vanishes on any witness
+        fixed = [[0] * n for _ in range(nfix)]
+    else:
+        fixed = [[rng.field(M) for _ in range(n)] for _ in range(nfix)]
+    S = PG.PGStructure(k, [], fixed, nadv, 0, gates)
+    return S, rng, nadv, n
+
+
+def _pow_weights(count, c):
+    t = count.bit_length() - 1
+    out = []
+    for i in range(count):
+        w = 1
+        for h in range(t):
+            if (i >> h) & 1:
+                w = w * c[h] % M
+        out.append(w)
+    return out
+
+
+@pytest.mark.parametrize("mode", ["compat", "correct"])
+def test_F_equals_direct_sum(mode):
+    S, rng, nadv, n = _structure(3, 2, 1)
+    W = [[rng.field(M) for _ in range(nadv * n)]]
+    ctx = PG.PolyContext(S, 1)
+    t = ctx.betas_count()
+    betas, delta = [rng.field(M) for _ in range(t)], rng.field(M)
+    F = PG.compute_F(ctx, betas, delta, W, [], mode)
+    assert len(F) == ctx.fft_points_count_F()
+    f = PG.evaluate_witness_fn(S, W, [], mode)
+    leaves = [f(i) for i in range(ctx.count)]
+    deltas = [delta]
+    for _ in range(t - 1):
+        deltas.append(deltas[-1] ** 2 % M)
+    for X in (0, 1, rng.field(M)):
+        c = [(b + X * d) % M for b, d in zip(betas, deltas)]
+        assert PG.poly_eval(F, X) == sum(w * v for w, v in zip(_pow_weights(ctx.count, c), leaves)) % M
+    # e is the same tree with the betas themselves
+    assert PG.evaluate_e(S, W, [], betas, mode) == sum(w * v for w, v in zip(_pow_weights(ctx.count, betas), leaves)) % M
+
+
+@pytest.mark.parametrize("mode", ["compat", "correct"])
+def test_G_equals_direct_sum_and_K_divides(mode):
+    S, rng, nadv, n = _structure(2, 2, 2)
+    Ws = [[[rng.field(M) for _ in range(nadv * n)]] for _ in range(2)]
+    ctx = PG.PolyContext(S, 1)
+    t = ctx.betas_count()
+    bs = [rng.field(M) for _ in range(t)]
+    G = PG.compute_G(ctx, bs, Ws[0], [], [Ws[1]], [[]], mode)
+    assert len(G) == ctx.fft_points_count_G
+    w = _pow_weights(ctx.count, bs)
+    for X in (3, rng.field(M)):
+        L = R.eval_lagrange_polys(ctx.lagrange_domain(), X)
+        folded = [[sum(L[j] * Ws[j][0][i] for j in range(2)) % M for i in range(nadv * n)]]
+        f = PG.evaluate_witness_fn(S, folded, [], mode)
+        assert PG.poly_eval(G, X) == sum(wi * f(i) for i, wi in enumerate(w)) % M
+    # K interpolates (G - F(alpha) L0) / Z on the coset zeta*H (compute_K_from_G, poly/mod.rs:475-509)
+    F_alpha = rng.field(M)
+    K = PG.compute_K_from_G(ctx, list(G), F_alpha)
+    logK = ctx.fft_log_domain_size_K()
+    assert len(K) == 1 << logK
+    back = R.coset_fft(K)
+    for i, w in enumerate(R.iter_cyclic_subgroup(logK)):
+        if i % 37:
+            continue
+        X = R.FR_ZETA * w % M
+        L0 = R.eval_lagrange_polys(ctx.lagrange_domain(), X)[0]
+        Z = (pow(X, ctx.instances_to_fold, M) - 1) % M
+        assert (F_alpha * L0 + Z * back[i]) % M == PG.poly_eval(G, X)
+
+
+def test_zero_F_and_G_on_satisfied_structure():
+    # reference zero_f / zero_g: a satisfied trace gives the zero polynomials
+    S, rng, nadv, n = _structure(2, 2, 3, satisfied=True)
+    Ws = [[[rng.field(M) for _ in range(nadv * n)]] for _ in range(2)]
+    ctx = PG.PolyContext(S, 1)
+    t = ctx.betas_count()
+    betas = [rng.field(M) for _ in range(t)]
+    assert PG.compute_F(ctx, betas, rng.field(M), Ws[0], []) == [0] * ctx.fft_points_count_F()
+    assert PG.compute_G(ctx, betas, Ws[0], [], [Ws[1]], [[]]) == [0] * ctx.fft_points_count_G
+
+
+def test_poly_context_quirk_F5():
+    # fft_log_domain_size_K returns a point COUNT used as a log: L=1, degree-5 gate -> 2^8 points
+    S, _, _, _ = _structure(2, 2, 4)
+    ctx = PG.PolyContext(S, 1)
+    assert ctx.fft_points_count_G == 8 and ctx.fft_log_domain_size_K() == 8
+    ctx3 = PG.PolyContext(S, 3)
+    assert ctx3.fft_points_count_G == 16 and ctx3.fft_log_domain_size_K() == 16
