@@ -56,23 +56,44 @@ __global__ void k_powers(F g, uint32_t count, F* __restrict__ out) {
     st16(out + i, acc);
 }
 
+// shared-memory element store in two 16-byte planes: consecutive threads hit consecutive 16-byte words, so the
+// butterflies with stride >= 8 elements are bank-conflict free (an array of 32-byte elements is 2-way conflicted
+// on every 128-bit access)
+template <class F>
+SB_D F sm_load(const uint4* lo, const uint4* hi, uint32_t idx) {
+    F r;
+    uint4* d = reinterpret_cast<uint4*>(&r);
+    d[0] = lo[idx];
+    d[1] = hi[idx];
+    return r;
+}
+template <class F>
+SB_D void sm_store(uint4* lo, uint4* hi, uint32_t idx, const F& v) {
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    lo[idx] = s[0];
+    hi[idx] = s[1];
+}
+
 template <class F>
 __global__ void k_ntt_pass(const F* __restrict__ in, F* __restrict__ out, uint32_t logN, uint32_t logR, uint32_t logNs,
                            uint32_t log_tj, const F* __restrict__ inner_tw, const F* __restrict__ tw_lo,
                            const F* __restrict__ tw_hi, F scale, int has_scale) {
     extern __shared__ uint4 smem_raw[];
-    F* data = reinterpret_cast<F*>(smem_raw);
     const uint32_t R = 1u << logR, halfR = R >> 1;
-    F* itw = data + ((size_t)R << log_tj);
+    const uint32_t total = R << log_tj;           // data elements in the block
+    uint4* d_lo = smem_raw;
+    uint4* d_hi = smem_raw + total;
+    uint4* t_lo = smem_raw + 2 * total;           // inner twiddles, R/2 elements
+    uint4* t_hi = t_lo + halfR;
 
     const uint32_t tj = threadIdx.x >> (logR - 1);  // which transform of this block
     const uint32_t t = threadIdx.x & (halfR - 1);
     const uint32_t j = (blockIdx.x << log_tj) + tj;
     const uint32_t col_stride_log = logN - logR;
     const uint32_t Ns_mask = (1u << logNs) - 1;
-    F* my = data + ((size_t)tj << logR);
+    const uint32_t my = tj << logR;                // base index of this transform
 
-    for (uint32_t k = threadIdx.x; k < halfR; k += blockDim.x) st16(itw + k, ld16(inner_tw + k));
+    for (uint32_t k = threadIdx.x; k < halfR; k += blockDim.x) sm_store(t_lo, t_hi, k, ld16(inner_tw + k));
 
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -87,19 +108,19 @@ __global__ void k_ntt_pass(const F* __restrict__ in, F* __restrict__ out, uint32
             }
         }
         const uint32_t br = __brev(r) >> (32 - logR);
-        st16(my + br, v);
+        sm_store(d_lo, d_hi, my + br, v);
     }
     __syncthreads();
 
     for (uint32_t s = 0; s < logR; s++) {
         const uint32_t half = 1u << s;
         const uint32_t i = t & (half - 1);
-        const uint32_t p = ((t >> s) << (s + 1)) + i;
-        F x = ld16(my + p);
-        F y = ld16(my + p + half);
-        if (i) y = mul(y, ld16(itw + (i << (logR - 1 - s))));
-        st16(my + p, add(x, y));
-        st16(my + p + half, sub(x, y));
+        const uint32_t p = my + ((t >> s) << (s + 1)) + i;
+        F x = sm_load<F>(d_lo, d_hi, p);
+        F y = sm_load<F>(d_lo, d_hi, p + half);
+        if (i) y = mul(y, sm_load<F>(t_lo, t_hi, i << (logR - 1 - s)));
+        sm_store(d_lo, d_hi, p, add(x, y));
+        sm_store(d_lo, d_hi, p + half, sub(x, y));
         __syncthreads();
     }
 
@@ -107,7 +128,7 @@ __global__ void k_ntt_pass(const F* __restrict__ in, F* __restrict__ out, uint32
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const uint32_t r = t + h * halfR;
-        F v = ld16(my + r);
+        F v = sm_load<F>(d_lo, d_hi, my + r);
         if (has_scale) v = mul(v, scale);
         st16(out + j0 + ((size_t)r << logNs), v);
     }
