@@ -108,6 +108,11 @@ int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, voi
  * the all-gather output [rank][batch] in place. */
 int sb_msm_combine_batch_device(int curve, const void* d_partials_xyzz, int count, size_t batch, size_t stride, void* d_out_xy, void* stream);
 
+/* Validation of a key read from the reference's cache file (raw memory dump of [C], src/commitment.rs:99-128): counts
+ * the points that are neither the identity (0,0) nor on y^2 = x^3 + b, as load_or_setup_cache does (:148-157). */
+int sb_points_on_curve(int curve, const uint64_t* points_xy, size_t n, uint64_t* bad_count);
+int sb_points_on_curve_device(int curve, const void* d_points_xy, size_t n, void* d_bad_count_u64, void* stream);
+
 /* Synthetic commitment key used by the benches: d_out[i] = [first + i + 1] * G, affine. */
 int sb_index_multiples_device(int curve, const uint64_t gen_xy[8], uint64_t first, size_t n, void* d_out_xy, void* stream);
 
@@ -183,6 +188,11 @@ int sb_pg_tree(sb_prog_t const* gates, size_t num_gates, sb_columns_t cols, uint
 /* ProtoGalaxy::fold_witness (mod.rs:176-210) / any Lagrange fold: out[i] = sum_j coef[j] * inputs[j][i]. */
 int sb_lincomb(int field, const uint64_t* const* inputs, const uint64_t* coef, size_t num_inputs, size_t n, uint64_t* out);
 int sb_lincomb_device(int field, const void* const* d_inputs, const uint64_t* coef, size_t num_inputs, size_t n, void* d_out, void* stream);
+
+/* ---- batched inversion (building block of the SPS lookup columns, src/plonk/lookup.rs:213-365, and of
+ * util::batch_invert_assigned, src/util/mod.rs:128-153): out[i] = in[i]^-1, zeros stay zero (ff::BatchInvert). */
+int sb_batch_invert(int field, const uint64_t* in, uint64_t* out, size_t n);
+int sb_batch_invert_device(int field, const void* d_in, void* d_out, size_t n, void* stream);
 
 /* ---- fft (src/fft.rs) ------------------------------------------------------------------------------ */
 

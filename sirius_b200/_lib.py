@@ -40,6 +40,8 @@ SIGNATURES = {
     "sb_msm_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, vp, vp, vp]),
     "sb_msm_batch": (ctypes.c_int, [vp, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p]),
     "sb_msm_batch_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp]),
+    "sb_points_on_curve": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p]),
+    "sb_points_on_curve_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, vp, vp]),
     "sb_index_multiples_device": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint64, ctypes.c_size_t, vp, vp]),
     "sb_msm_combine_batch_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
     "sb_msm_combine_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_int, vp, vp]),
@@ -63,6 +65,8 @@ SIGNATURES = {
     "sb_pg_tree": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_size_t, vp, ctypes.c_uint32, ctypes.POINTER(u64p), ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32), u64p]),
     "sb_lincomb": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(u64p), u64p, ctypes.c_size_t, ctypes.c_size_t, u64p]),
     "sb_lincomb_device": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp), u64p, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
+    "sb_batch_invert": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t]),
+    "sb_batch_invert_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
     "sb_ntt": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint32, u64p, u64p]),
     "sb_ntt_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint32, u64p, u64p, vp]),
     "sb_coset_scale": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p, u64p]),

@@ -70,6 +70,47 @@ class CommitmentKey:
         """C::identity(), encoded (0,0)."""
         return np.zeros(8, dtype=np.uint64)
 
+    # -- key cache files (src/commitment.rs:99-170): the raw memory of [C], 64 bytes per point ---------------
+    def save_to_file(self, file_path: str) -> None:
+        """`CommitmentKey::save_to_file`: the generators' bytes as they sit in memory."""
+        if self._host is None:
+            raise ValueError("this key was registered from device memory; no host copy to dump")
+        with open(file_path, "wb") as f:
+            f.write(self._host.tobytes())
+
+    @classmethod
+    def load_from_file(cls, curve: int, file_path: str, k: int, window_bits: int = 0) -> "CommitmentKey":
+        """`CommitmentKey::load_from_file`: exactly 2^k points are read (`read_exact`)."""
+        want = (1 << k) * 64
+        with open(file_path, "rb") as f:
+            buf = f.read(want)
+        if len(buf) != want:
+            raise EOFError("failed to fill whole buffer")  # io::ErrorKind::UnexpectedEof
+        return cls(curve, np.frombuffer(buf, dtype=np.uint64).reshape(-1, 8).copy(), window_bits)
+
+    @classmethod
+    def load_or_setup_cache(cls, curve: int, cache_folder: str, label: str, k: int, setup=None) -> "CommitmentKey":
+        """`CommitmentKey::load_or_setup_cache`: {cache_folder}/{label}/{k}.bin, validated point by point on the
+        device.  Key generation (`setup`: Shake256 + hash_to_curve of the un-vendored halo2curves) is
+        not part of the GPU hot path: pass `setup(k, label) -> uint64[2^k, 8]` to create a missing file."""
+        import os
+
+        path = os.path.join(cache_folder, label, f"{k}.bin")
+        if os.path.exists(path):
+            key = cls.load_from_file(curve, path, k)
+            bad = np.zeros(1, dtype=np.uint64)
+            _lib.check(_lib.load().sb_points_on_curve(curve, key._host.ctypes.data_as(_lib.u64p), key._host.shape[0], bad.ctypes.data_as(_lib.u64p)))
+            if int(bad[0]):
+                key.close()
+                raise ValueError("Wrong file in cache, some ptr out of curve")  # io::ErrorKind::InvalidData
+            return key
+        if setup is None:
+            raise NotImplementedError("CommitmentKey::setup needs halo2curves' hash_to_curve (un-vendored); supply `setup`")
+        key = cls(curve, setup(k, label))
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        key.save_to_file(path)
+        return key
+
     def commit(self, v) -> np.ndarray:
         """sum_i v[i] * ck[i] as an affine point (uint64[8]); raises TooLongInput like the Rust Err."""
         s = _as_u64(v, 4)

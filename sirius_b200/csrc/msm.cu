@@ -118,6 +118,34 @@ __global__ void k_index_multiples(Affine<F> g, uint64_t first, size_t n, Affine<
     store_vec(out + i, xyzz_to_affine<false>(acc));
 }
 
+// is_on_curve for every point of a key file (reference src/commitment.rs:148-157: `p.is_on_curve()` over the
+// loaded cache; halo2curves accepts the identity (0,0)).  bad_count += number of points off y^2 = x^3 + b.
+template <class F>
+__global__ void k_on_curve(const Affine<F>* __restrict__ pts, size_t n, int b_small, int b_negative, unsigned long long* bad_count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = load_vec_nc(pts + i);
+    if (p.is_identity()) return;
+    F bb = F::zero();
+    bb.v[0] = (uint32_t)b_small;
+    bb = to_mont(bb);
+    if (b_negative) bb = neg(bb);
+    // coordinates must be canonical (< p) for the comparison to mean anything: reduce-once keeps valid inputs unchanged
+    F lhs = sqr(p.y);
+    F rhs = add(mul(sqr(p.x), p.x), bb);
+    bool canonical = true;
+    {
+        uint32_t t[8];
+        for (int k = 0; k < 8; k++) t[k] = p.x.v[k];
+        reduce_once_portable<typename F::Params>(t);
+        for (int k = 0; k < 8; k++) canonical &= (t[k] == p.x.v[k]);
+        for (int k = 0; k < 8; k++) t[k] = p.y.v[k];
+        reduce_once_portable<typename F::Params>(t);
+        for (int k = 0; k < 8; k++) canonical &= (t[k] == p.y.v[k]);
+    }
+    if (!canonical || lhs != rhs) atomicAdd(bad_count, 1ull);
+}
+
 // ------------------------------------------------------------------------------------------------
 // commit-time: digits, counting sort
 // ------------------------------------------------------------------------------------------------
@@ -966,6 +994,49 @@ int sb_msm(sb_ck_t ck, const uint64_t* scalars_mont, size_t n, uint64_t out_xy[8
     }
     const uint64_t* one[1] = {scalars_mont};
     return sb_msm_batch(ck, one, n, 1, out_xy);
+}
+
+int sb_points_on_curve_device(int curve, const void* d_points_xy, size_t n, void* d_bad_count_u64, void* stream) {
+    if ((!d_points_xy && n) || !d_bad_count_u64) {
+        set_error("sb_points_on_curve_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    SB_CUDA_TRY(cudaMemsetAsync(d_bad_count_u64, 0, 8, st));
+    if (!n) return SB_OK;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (curve == CURVE_BN256) k_on_curve<Fq><<<blocks, 256, 0, st>>>((const Affine<Fq>*)d_points_xy, n, 3, 0, (unsigned long long*)d_bad_count_u64);
+    else if (curve == CURVE_GRUMPKIN) k_on_curve<Fr><<<blocks, 256, 0, st>>>((const Affine<Fr>*)d_points_xy, n, 17, 1, (unsigned long long*)d_bad_count_u64);
+    else {
+        set_error("sb_points_on_curve_device: unknown curve %d", curve);
+        return SB_ERR_ARG;
+    }
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+int sb_points_on_curve(int curve, const uint64_t* points_xy, size_t n, uint64_t* bad_count) {
+    if ((!points_xy && n) || !bad_count) {
+        set_error("sb_points_on_curve: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    void* d = nullptr;
+    SB_CUDA_TRY(cudaMalloc(&d, n * 64 + 64));
+    int rc = SB_OK;
+    cudaError_t e = cudaMemcpyAsync((char*)d + 64, points_xy, n * 64, cudaMemcpyHostToDevice, rt.stream);
+    if (e == cudaSuccess) rc = sb_points_on_curve_device(curve, (char*)d + 64, n, d, rt.stream);
+    if (e == cudaSuccess && rc == SB_OK) e = cudaMemcpyAsync(bad_count, d, 8, cudaMemcpyDeviceToHost, rt.stream);
+    if (e == cudaSuccess && rc == SB_OK) e = cudaStreamSynchronize(rt.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        set_error("sb_points_on_curve: %s", cudaGetErrorString(e));
+        return SB_ERR_CUDA;
+    }
+    return rc;
 }
 
 int sb_index_multiples_device(int curve, const uint64_t gen_xy[8], uint64_t first, size_t n, void* d_out_xy, void* stream) {

@@ -151,6 +151,49 @@ def test_msm_public_bn256_vector(sb):
     ck.close()
 
 
+def test_key_cache_file_roundtrip_and_validation(sb, oracle, tmp_path):
+    """reference commitment::file_tests::consistency (src/commitment.rs:197-213) + the on-curve check of
+    load_or_setup_cache (:148-157), here done on the device"""
+    for curve in (R.CURVE_BN256, R.CURVE_GRUMPKIN):
+        k = 6
+        bases = oracle.running_bases(curve, 1 << k)
+        bases[5] = 0  # the identity is a valid key entry
+        made = []
+        ck = sb.CommitmentKey.load_or_setup_cache(curve, str(tmp_path), f"lbl{curve}", k, setup=lambda kk, lbl: (made.append(kk), bases)[1])
+        assert made == [k]
+        ck2 = sb.CommitmentKey.load_or_setup_cache(curve, str(tmp_path), f"lbl{curve}", k)  # now read back from the file
+        assert np.array_equal(ck2._host, bases)
+        s = oracle.random_field(0 if curve == R.CURVE_BN256 else 1, 3, 1 << k)
+        assert np.array_equal(ck2.commit(s), ck.commit(s))
+        # corrupt one coordinate: the loader must refuse the file
+        path = tmp_path / f"lbl{curve}" / f"{k}.bin"
+        raw = bytearray(path.read_bytes())
+        raw[64 * 9 + 3] ^= 0x5A
+        path.write_bytes(bytes(raw))
+        with pytest.raises(ValueError, match="out of curve"):
+            sb.CommitmentKey.load_or_setup_cache(curve, str(tmp_path), f"lbl{curve}", k)
+        with pytest.raises(EOFError):
+            sb.CommitmentKey.load_from_file(curve, str(path), k + 1)
+        ck.close()
+        ck2.close()
+
+
+@pytest.mark.parametrize("field", [R.FIELD_FR, R.FIELD_FQ])
+def test_batch_invert(sb, oracle, field):
+    """ff::BatchInvert semantics (zeros stay zero) vs the oracle's Fermat inversion"""
+    from sirius_b200 import _lib
+
+    for n in (1, 15, 16, 17, 1000, 1 << 15):
+        a = oracle.random_field(field, 9 + n, n)
+        a[::7] = 0
+        out = np.zeros_like(a)
+        _lib.check(_lib.load().sb_batch_invert(field, p(a), p(out), n))
+        nz = ~np.all(a == 0, axis=1)
+        assert not out[~nz].any()
+        if nz.any():
+            assert np.array_equal(out[nz], oracle.field_inv(field, a[nz]))
+
+
 def test_msm_too_long_input(sb, oracle):
     bases = oracle.running_bases(R.CURVE_BN256, 8)
     ck = sb.CommitmentKey(R.CURVE_BN256, bases)
