@@ -3,6 +3,7 @@
 #include <vector>
 #include "common.cuh"
 #include "curve.cuh"
+#include "quad.cuh"
 
 namespace sb {
 
@@ -116,6 +117,35 @@ __global__ void k_mb_mul_fake(F* io, int iters) {
     io[2 * i] = add(x, y);
 }
 
+template <class F>
+__global__ void k_mb_quad_add(XYZZ<F>* io, int iters) {  // serial quad-lane additions (operands replicated per group)
+    size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    XYZZ<F> a = io[2 * g], b = io[2 * g + 1];
+    for (int k = 0; k < iters; k++) quad_add(a, b);
+    if ((threadIdx.x & 3) == 0) io[2 * g] = a;
+}
+template <class F>
+__global__ void k_mb_quad_double(XYZZ<F>* io, int iters) {
+    size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    XYZZ<F> a = io[2 * g];
+    for (int k = 0; k < iters; k++) quad_double(a);
+    if ((threadIdx.x & 3) == 0) io[2 * g] = a;
+}
+template <class F>
+__global__ void k_mb_double_call(XYZZ<F>* io, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ<F> a = io[2 * i];
+    for (int k = 0; k < iters; k++) xyzz_double_call(a);
+    io[2 * i] = a;
+}
+template <class F>
+__global__ void k_mb_inv(F* io, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    F a = io[2 * i];
+    for (int k = 0; k < iters; k++) a = inv_binary(a);
+    io[2 * i] = a;
+}
+
 __global__ void k_mb_imad_wide(uint32_t* io, int iters) {  // raw IMAD.WIDE.U32 issue rate, 8 independent accumulators
     uint32_t a = io[threadIdx.x], b = io[threadIdx.x + 32];
     unsigned long long acc[8];
@@ -160,6 +190,10 @@ extern "C" int sb_microbench(int which, int iters, int blocks, int threads, doub
             case 5: k_mb_madd<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 6: k_mb_imad_wide<<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
             case 7: k_mb_mul_fake<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
+            case 8: k_mb_quad_add<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
+            case 9: k_mb_quad_double<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
+            case 10: k_mb_double_call<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
+            case 11: k_mb_inv<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
             default: cudaFree(d); set_error("sb_microbench: unknown test %d", which); return SB_ERR_ARG;
         }
         cudaEventRecord(e1, rt.stream);

@@ -1,11 +1,16 @@
 // quad.cuh -- XYZZ addition / doubling executed by a group of 4 consecutive lanes.
 //
-// The tail of every commitment (bucket fix-up, the weighted bucket sum) is a short chain of dependent XYZZ
-// additions on a nearly idle chip; a single lane needs 14 dependent Montgomery products (~13.2k cycles measured,
-// profiles/r1_microbench.txt) per addition.  Here the 14 products of one addition are issued in 4 rounds of up to
-// 4 independent products, one per lane of the group, and broadcast inside the group with shuffles: ~3.3x shorter
-// dependent chain.  Operands and results are REPLICATED in the 4 lanes; shuffles use the group's own 4-lane mask,
-// so different groups of a warp may diverge freely.
+// The tail of every commitment (weighted bucket sum, final combine) is a short chain of dependent XYZZ additions on
+// a nearly idle chip; a single lane needs 14 dependent Montgomery products (13.3k cycles measured) per addition.
+// Here the 14 products of one addition are issued in 4 rounds of up to 4 independent products, one per lane of the
+// group, and broadcast inside the group with shuffles.  Operands and results are REPLICATED in the 4 lanes;
+// shuffles use the group's own 4-lane mask, so different groups of a warp may diverge freely.
+//
+// Measured (profiles/r1_microbench3.txt): 12.8k cycles per quad-lane addition vs 13.3k for the single-lane one --
+// the 120 partial-mask shuffles and the role selects cost what the shorter product chain saves.  The form is kept
+// for the last, serial stage of the weighted bucket sum (it is correct, tested, and no slower); the real gain of
+// that stage came from needing fewer dependent operations (digit sums instead of scan levels), and making these
+// primitives pay off (full-mask shuffles, fewer broadcasts) is a round-2 item.
 #pragma once
 #include "curve.cuh"
 
