@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <memory>
 #include <vector>
 #include <new>
 
@@ -734,7 +735,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         k_decompose<S><<<(total + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, total, stride, K, p.c, p.W, dig, counts);
         SB_KERNEL_CHECK();
     }
-    ProfScope* sort_scope = new ProfScope(st, PROF_SORT, p.nW);
+    std::unique_ptr<ProfScope> sort_scope(new ProfScope(st, PROF_SORT, p.nW));
     k_scan_tile_sums<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles);
     SB_KERNEL_CHECK();
     k_scan_tiles<<<1, 1024, 0, st>>>(tiles, p.tiles);
@@ -744,7 +745,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, cursor, eidx);
     SB_KERNEL_CHECK();
     k_chunk_heads<<<(KB + 255) / 256, 256, 0, st>>>(offsets, KB, p.ls_log, chunk_head);
-    delete sort_scope;
+    sort_scope.reset();
     SB_KERNEL_CHECK();
     {
         size_t blocks = (p.chunks + 127) / 128;

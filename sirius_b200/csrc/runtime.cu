@@ -98,7 +98,8 @@ int Scratch::reserve(size_t bytes) {
     if (bytes <= cap) return SB_OK;
     Runtime& rt = runtime();
     if (ptr) {
-        cudaStreamSynchronize(rt.stream);
+        (void)rt;
+        cudaDeviceSynchronize();  // earlier work on ANY stream may still read the old buffer
         cudaFree(ptr);
         ptr = nullptr;
         cap = 0;

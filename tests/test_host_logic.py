@@ -86,3 +86,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "sirius_oracle" not in src, f
+
+
+def test_header_is_plain_c():
+    """the boundary is a C ABI: the header must compile as C with no torch/CUDA types in the signatures"""
+    import subprocess, tempfile
+
+    hdr = os.path.join(ROOT, "include", "sirius_b200.h")
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write(f'#include "{hdr}"\nint main(void) {{ return sb_version() == 0; }}\n')
+        path = f.name
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", path])
+    os.unlink(path)
+    src = open(hdr).read()
+    assert "torch" not in src and "cudaStream_t" not in src and "at::" not in src
