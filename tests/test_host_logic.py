@@ -98,5 +98,8 @@ def test_header_is_plain_c():
         path = f.name
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", path])
     os.unlink(path)
-    src = open(hdr).read()
+    import re
+
+    src = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)  # declarations only; comments may name the types
+    src = re.sub(r"//[^\n]*", "", src)
     assert "torch" not in src and "cudaStream_t" not in src and "at::" not in src
