@@ -41,6 +41,7 @@ extern "C" {
 
 typedef struct sb_ck* sb_ck_t;           /* device-resident CommitmentKey (src/commitment.rs:29-32) */
 typedef struct sb_prog* sb_prog_t;       /* uploaded GraphEvaluator program (src/polynomial/graph_evaluator.rs:164-180) */
+typedef struct sb_sparse* sb_sparse_t;   /* device-resident SparseMatrix (src/polynomial/sparse.rs:5), rows in CSR order */
 typedef struct sb_columns* sb_columns_t; /* device-resident selectors + fixed columns of a PlonkStructure (src/plonk/mod.rs:132-133) */
 
 /* ValueSource (graph_evaluator.rs:57-68) and Calculation (graph_evaluator.rs:72-89) discriminants */
@@ -193,6 +194,52 @@ int sb_lincomb_device(int field, const void* const* d_inputs, const uint64_t* co
  * util::batch_invert_assigned, src/util/mod.rs:128-153): out[i] = in[i]^-1, zeros stay zero (ff::BatchInvert). */
 int sb_batch_invert(int field, const uint64_t* in, uint64_t* out, size_t n);
 int sb_batch_invert_device(int field, const void* d_in, void* d_out, size_t n, void* stream);
+
+/* ---- SPS lookup columns (src/plonk/lookup.rs:213-365), run between two commits of run_sps_protocol_{2,3}
+ * (src/plonk/mod.rs:501-660).  l_i / t_i themselves come from sb_expr_eval on the compressed lookup / table
+ * expressions (LookupEvalDomain, src/plonk/eval.rs:84-131: one witness round holding the advice columns,
+ * num_lookup = 0, challenges = [r]). */
+
+/* Arguments::evaluate_m (lookup.rs:270-298): m[i] = F::from_u128(#{j : l[j] == t[i]}) on the first row of t holding
+ * that value and 0 on every later repeat.  n_t <= 2^30. */
+int sb_lookup_multiplicity(int field, const uint64_t* l, size_t n_l, const uint64_t* t, size_t n_t, uint64_t* m);
+int sb_lookup_multiplicity_device(int field, const void* d_l, size_t n_l, const void* d_t, size_t n_t, void* d_m, void* stream);
+/* Arguments::evaluate_h_g (lookup.rs:300-312): h[i] = (l[i]+r)^-1, g[i] = m[i] * (t[i]+r)^-1, with
+ * Option::from(invert()).unwrap_or(ZERO) for a zero denominator. */
+int sb_lookup_inverses(int field, const uint64_t* l, const uint64_t* t, const uint64_t* m, const uint64_t r[4], size_t n, uint64_t* h,
+                       uint64_t* g);
+int sb_lookup_inverses_device(int field, const void* d_l, const void* d_t, const void* d_m, const uint64_t r[4], size_t n, void* d_h,
+                              void* d_g, void* stream);
+/* The kernel under both: out[i] = scale[i] * (in[i] + shift)^-1, 0 where in[i] + shift == 0; shift NULL = 0,
+ * scale NULL = 1.  With shift NULL it is util::batch_invert_assigned's numerator * denominator^-1
+ * (src/util/mod.rs:120-153; pass denominator 1 for Assigned::Trivial / Zero). */
+int sb_scaled_inverse(int field, const uint64_t* in, const uint64_t shift[4], const uint64_t* scale, uint64_t* out, size_t n);
+int sb_scaled_inverse_device(int field, const void* d_in, const uint64_t shift[4], const void* d_scale, void* d_out, size_t n, void* stream);
+/* is_sat_log_derivative's inner sum (src/plonk/mod.rs:367-376): out = sum_i (a[i] - b[i]); b NULL sums a.
+ * The _device form writes the 32-byte result to d_out without synchronising. */
+int sb_sum_diff(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t out[4]);
+int sb_sum_diff_device(int field, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream);
+
+/* ---- permutation decider (src/nifs/sangria/mod.rs:385-453, src/nifs/protogalaxy/mod.rs:660-689) ------------ */
+
+/* Upload a SparseMatrix = Vec<(row, col, value)> of an N x N matrix (src/polynomial/sparse.rs:5).  Entries outside
+ * the matrix are rejected (the reference panics "invalid matrix multiply", sparse.rs:15-17). */
+int sb_sparse_register(int field, const uint64_t* rows, const uint64_t* cols, const uint64_t* values_mont, size_t nnz, size_t N,
+                       sb_sparse_t* out);
+void sb_sparse_release(sb_sparse_t m);
+size_t sb_sparse_dim(sb_sparse_t m);
+/* mismatches = #{row : (P*Z)[row] != Z[row]} (sparse::matrix_multiply + the filter/count of is_sat_permutation).
+ * Z = head (host cells: the instance part) followed by tail (device cells: W[0][.. 2^k * num_advice]).
+ * Blocks until the count is on the host. */
+int sb_sparse_mismatch(sb_sparse_t m, const uint64_t* Z, size_t N, uint64_t* mismatches);
+int sb_sparse_mismatch_device(sb_sparse_t m, const uint64_t* head, size_t head_len, const void* d_tail, size_t tail_len,
+                              uint64_t* mismatches, void* stream);
+
+/* ---- witness assembly: util::concatenate_with_padding (src/util/mod.rs:214-218) straight into a device round
+ * vector: column c occupies max(lens[c], pad_size) cells, zero-padded (pad_using never truncates).  *out_len (may
+ * be NULL) receives the total; SB_ERR_ARG if it exceeds out_capacity (cells). */
+int sb_concat_pad_device(const uint64_t* const* columns, const size_t* lens, size_t num_columns, size_t pad_size, void* d_out,
+                         size_t out_capacity, size_t* out_len, void* stream);
 
 /* ---- fft (src/fft.rs) ------------------------------------------------------------------------------ */
 

@@ -67,6 +67,20 @@ SIGNATURES = {
     "sb_lincomb_device": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp), u64p, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
     "sb_batch_invert": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t]),
     "sb_batch_invert_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
+    "sb_lookup_multiplicity": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]),
+    "sb_lookup_multiplicity_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, vp, ctypes.c_size_t, vp, vp]),
+    "sb_lookup_inverses": (ctypes.c_int, [ctypes.c_int, u64p, u64p, u64p, u64p, ctypes.c_size_t, u64p, u64p]),
+    "sb_lookup_inverses_device": (ctypes.c_int, [ctypes.c_int, vp, vp, vp, u64p, ctypes.c_size_t, vp, vp, vp]),
+    "sb_scaled_inverse": (ctypes.c_int, [ctypes.c_int, u64p, u64p, u64p, u64p, ctypes.c_size_t]),
+    "sb_scaled_inverse_device": (ctypes.c_int, [ctypes.c_int, vp, u64p, vp, vp, ctypes.c_size_t, vp]),
+    "sb_sum_diff": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p]),
+    "sb_sum_diff_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_size_t, vp, vp]),
+    "sb_sparse_register": (ctypes.c_int, [ctypes.c_int, u64p, u64p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(vp)]),
+    "sb_sparse_release": (None, [vp]),
+    "sb_sparse_dim": (ctypes.c_size_t, [vp]),
+    "sb_sparse_mismatch": (ctypes.c_int, [vp, u64p, ctypes.c_size_t, u64p]),
+    "sb_sparse_mismatch_device": (ctypes.c_int, [vp, u64p, ctypes.c_size_t, vp, ctypes.c_size_t, u64p, vp]),
+    "sb_concat_pad_device": (ctypes.c_int, [ctypes.POINTER(u64p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.c_size_t, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), vp]),
     "sb_ntt": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint32, u64p, u64p]),
     "sb_ntt_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint32, u64p, u64p, vp]),
     "sb_coset_scale": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p, u64p]),

@@ -1,0 +1,563 @@
+// lookup.cu -- the SPS lookup columns and the remaining decider/assembly pieces that sit between two commits of
+// the prover step.  Replaces, on the device:
+//
+//   * lookup::Arguments::evaluate_m        (reference src/plonk/lookup.rs:270-298)
+//         m_i = #{j : l_j = t_i} on the FIRST row holding each distinct table value, 0 on repeats.
+//         The reference builds a HashMap over l and a HashSet over t; here an open-addressing table over the t rows
+//         keeps, per distinct value, the smallest row index (atomicMin), the l rows count into that row, and a last
+//         pass emits F::from_u128(count).  Counts are integers, so the result does not depend on atomic ordering.
+//   * lookup::Arguments::evaluate_h_g      (src/plonk/lookup.rs:300-312)
+//         h_i = 1/(l_i + r) (0 when l_i + r = 0),  g_i = m_i / (t_i + r): Montgomery-trick batches of 16 per thread
+//         around one binary-GCD inversion.  The same kernel with shift 0 resolves halo2 `Assigned` fractions
+//         (util::batch_invert_assigned, src/util/mod.rs:128-153: numerator * denominator^-1, zero denominator -> 0).
+//   * PlonkStructure::is_sat_log_derivative (src/plonk/mod.rs:363-397): sum_i (h_i - g_i).
+//   * sparse::matrix_multiply + the mismatch count of is_sat_permutation
+//         (src/polynomial/sparse.rs:7-20, src/nifs/sangria/mod.rs:385-453, src/nifs/protogalaxy/mod.rs:660-689).
+//   * util::concatenate_with_padding       (src/util/mod.rs:214-218): host columns -> one device round vector.
+//
+// Everything here is 32-byte-cell streaming work (HBM-bound) except the inversions (3 products per cell + 1/16 of a
+// 254-bit binary GCD) and the hash probes (one random 32-byte read per probe).
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "field.cuh"
+
+namespace sb {
+
+namespace {
+
+template <class T>
+SB_D T ldc(const T* p) {
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+    d[0] = s[0];
+    d[1] = s[1];
+    return r;
+}
+template <class T>
+SB_D void stc(T* p, const T& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    d[0] = s[0];
+    d[1] = s[1];
+}
+
+constexpr uint32_t LK_EMPTY = 0xFFFFFFFFu;
+
+template <class F>
+SB_D uint32_t cell_hash(const F& a) {
+    // Montgomery residues of structured values are already well spread; mix all limbs and avalanche once.
+    uint32_t h = 0x9E3779B9u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) h = (h ^ a.v[i]) * 0x85EBCA6Bu + (h >> 15);
+    h ^= h >> 16;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 13;
+    return h;
+}
+
+// slot[h] <- smallest row index of t holding that value
+template <class F>
+__global__ void __launch_bounds__(256)
+k_lookup_insert(const F* __restrict__ t, uint32_t n_t, uint32_t* __restrict__ slots, uint32_t mask) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_t) return;
+    const F key = ldc(t + i);
+    uint32_t h = cell_hash(key) & mask;
+    for (;;) {
+        uint32_t cur = *((volatile uint32_t*)(slots + h));
+        if (cur == LK_EMPTY) {
+            cur = atomicCAS(slots + h, LK_EMPTY, i);
+            if (cur == LK_EMPTY) return;
+        }
+        if (cur == i) return;
+        if (ldc(t + cur) == key) {  // the slot only ever moves between rows with this same value
+            if (i < cur) atomicMin(slots + h, i);
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+// returns the first-occurrence row of `key` in t, or LK_EMPTY
+template <class F>
+SB_D uint32_t lookup_find(const F& key, const F* __restrict__ t, const uint32_t* __restrict__ slots, uint32_t mask) {
+    uint32_t h = cell_hash(key) & mask;
+    for (;;) {
+        const uint32_t cur = slots[h];
+        if (cur == LK_EMPTY) return LK_EMPTY;
+        if (ldc(t + cur) == key) return cur;
+        h = (h + 1) & mask;
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256)
+k_lookup_count(const F* __restrict__ l, uint32_t n_l, const F* __restrict__ t, const uint32_t* __restrict__ slots, uint32_t mask,
+               uint32_t* __restrict__ counts) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t hit = LK_EMPTY;
+    if (j < n_l) hit = lookup_find(ldc(l + j), t, slots, mask);
+    // unused rows usually all look up the same value: aggregate equal targets inside the warp first
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, hit);
+    if (hit != LK_EMPTY && (uint32_t)(__ffs(peers) - 1) == (threadIdx.x & 31u)) atomicAdd(counts + hit, (uint32_t)__popc(peers));
+}
+
+template <class F>
+__global__ void __launch_bounds__(256)
+k_lookup_emit(const F* __restrict__ t, uint32_t n_t, const uint32_t* __restrict__ slots, uint32_t mask,
+              const uint32_t* __restrict__ counts, F* __restrict__ m) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_t) return;
+    F out = F::zero();
+    const uint32_t c = counts[i];
+    if (c != 0 && lookup_find(ldc(t + i), t, slots, mask) == i) {  // counts live on first occurrences only
+        F x = F::zero();
+        x.v[0] = c;
+        out = to_mont(x);
+    }
+    stc(m + i, out);
+}
+
+constexpr int SI_CHUNK = 16;
+
+// out[i] = scale[i] * (in[i] + shift)^-1, 0 where in[i] + shift = 0;  scale == nullptr means 1
+template <class F>
+__global__ void __launch_bounds__(128)
+k_scaled_inverse(const F* __restrict__ in, const F* __restrict__ shift_p, const F* __restrict__ scale, F* __restrict__ out, size_t n) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t base = tid * SI_CHUNK;
+    if (base >= n) return;
+    const int cnt = (n - base) < (size_t)SI_CHUNK ? (int)(n - base) : SI_CHUNK;
+    const F shift = ldc(shift_p);
+    F pre[SI_CHUNK];
+    F acc = F::one();
+#pragma unroll
+    for (int i = 0; i < SI_CHUNK; i++) {
+        if (i < cnt) {
+            const F v = add(ldc(in + base + i), shift);
+            pre[i] = acc;
+            if (!v.is_zero()) acc = mul(acc, v);
+        }
+    }
+    F inv_all = inv_binary(acc);
+#pragma unroll
+    for (int i = SI_CHUNK - 1; i >= 0; i--) {
+        if (i < cnt) {
+            const F v = add(ldc(in + base + i), shift);
+            F o = F::zero();
+            if (!v.is_zero()) {
+                o = mul(inv_all, pre[i]);
+                inv_all = mul(inv_all, v);
+                if (scale) {
+                    const F s = ldc(scale + base + i);
+                    o = s.is_zero() ? s : mul(o, s);
+                }
+            }
+            stc(out + base + i, o);
+        }
+    }
+}
+
+constexpr int SUM_BLOCK = 256;
+
+// partial[b] = sum over a grid-stride slice of (a_i - b_i); b == nullptr sums a alone
+template <class F>
+__global__ void __launch_bounds__(SUM_BLOCK)
+k_sum_diff(const F* __restrict__ a, const F* __restrict__ b, size_t n, F* __restrict__ partial) {
+    __shared__ F sh[SUM_BLOCK];
+    F acc = F::zero();
+    for (size_t i = (size_t)blockIdx.x * SUM_BLOCK + threadIdx.x; i < n; i += (size_t)gridDim.x * SUM_BLOCK) {
+        F v = ldc(a + i);
+        if (b) v = sub(v, ldc(b + i));
+        acc = add(acc, v);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = SUM_BLOCK / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = add(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) stc(partial + blockIdx.x, sh[0]);
+}
+
+// y = P * Z row by row (CSR), count rows with y != Z[row].  Z = head (first head_len cells) ++ tail.
+template <class F>
+__global__ void __launch_bounds__(256)
+k_sparse_mismatch(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col, const F* __restrict__ val, const F* __restrict__ head,
+                  size_t head_len, const F* __restrict__ tail, size_t N, unsigned long long* __restrict__ mismatches) {
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (row < N) {
+        F y = F::zero();
+        for (uint32_t e = row_ptr[row]; e < row_ptr[row + 1]; e++) {
+            const size_t c = col[e];
+            const F z = c < head_len ? ldc(head + c) : ldc(tail + (c - head_len));
+            y = add(y, mul(ldc(val + e), z));
+        }
+        const F zr = row < head_len ? ldc(head + row) : ldc(tail + (row - head_len));
+        bad = y != zr;
+    }
+    const uint32_t votes = __ballot_sync(0xFFFFFFFFu, bad);
+    if ((threadIdx.x & 31u) == 0 && votes) atomicAdd(mismatches, (unsigned long long)__popc(votes));
+}
+
+Scratch g_lk_ws;     // hash slots + counts / reduction partials / mismatch counter
+Scratch g_lk_stage;  // host front ends: staged inputs and outputs
+
+struct SparseMatrix {
+    int field;
+    size_t N, nnz;
+    uint32_t* d_row_ptr = nullptr;
+    uint32_t* d_col = nullptr;
+    void* d_val = nullptr;
+};
+
+template <class F>
+int multiplicity_enqueue(const void* d_l, size_t n_l, const void* d_t, size_t n_t, void* d_m, cudaStream_t st) {
+    if (!n_t) return SB_OK;
+    size_t slots = 1024;
+    while (slots < 2 * n_t) slots <<= 1;
+    const size_t slot_bytes = align_up(slots * 4, 256);
+    SB_TRY(g_lk_ws.reserve(slot_bytes + align_up(n_t * 4, 256)));
+    uint32_t* d_slots = (uint32_t*)g_lk_ws.ptr;
+    uint32_t* d_counts = (uint32_t*)((char*)g_lk_ws.ptr + slot_bytes);
+    SB_CUDA_TRY(cudaMemsetAsync(d_slots, 0xFF, slots * 4, st));
+    SB_CUDA_TRY(cudaMemsetAsync(d_counts, 0, n_t * 4, st));
+    const uint32_t mask = (uint32_t)(slots - 1);
+    k_lookup_insert<F><<<(unsigned)((n_t + 255) / 256), 256, 0, st>>>((const F*)d_t, (uint32_t)n_t, d_slots, mask);
+    SB_KERNEL_CHECK();
+    if (n_l) {
+        k_lookup_count<F><<<(unsigned)((n_l + 255) / 256), 256, 0, st>>>((const F*)d_l, (uint32_t)n_l, (const F*)d_t, d_slots, mask, d_counts);
+        SB_KERNEL_CHECK();
+    }
+    k_lookup_emit<F><<<(unsigned)((n_t + 255) / 256), 256, 0, st>>>((const F*)d_t, (uint32_t)n_t, d_slots, mask, d_counts, (F*)d_m);
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+template <class F>
+int scaled_inverse_enqueue(const void* d_in, const uint64_t* shift, const void* d_scale, void* d_out, size_t n, cudaStream_t st) {
+    if (!n) return SB_OK;
+    SB_TRY(g_lk_stage.reserve(256));
+    uint64_t zero[4] = {0, 0, 0, 0};
+    // the 32-byte shift travels through a tiny device cell (stream-ordered, so back-to-back calls may reuse it)
+    SB_CUDA_TRY(cudaMemcpyAsync(g_lk_stage.ptr, shift ? shift : zero, 32, cudaMemcpyHostToDevice, st));
+    const size_t threads = (n + SI_CHUNK - 1) / SI_CHUNK;
+    k_scaled_inverse<F><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const F*)d_in, (const F*)g_lk_stage.ptr, (const F*)d_scale, (F*)d_out, n);
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+template <class F>
+int sum_diff_enqueue(const void* d_a, const void* d_b, size_t n, void* d_out, cudaStream_t st) {
+    Runtime& rt = runtime();
+    size_t blocks = (n + SUM_BLOCK - 1) / SUM_BLOCK;
+    const size_t cap = (size_t)rt.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    SB_TRY(g_lk_ws.reserve(blocks * 32));
+    F* d_part = (F*)g_lk_ws.ptr;
+    k_sum_diff<F><<<(unsigned)blocks, SUM_BLOCK, 0, st>>>((const F*)d_a, (const F*)d_b, n, d_part);
+    SB_KERNEL_CHECK();
+    k_sum_diff<F><<<1, SUM_BLOCK, 0, st>>>(d_part, (const F*)nullptr, blocks, (F*)d_out);
+    SB_KERNEL_CHECK();
+    return SB_OK;
+}
+
+}  // namespace
+
+}  // namespace sb
+
+using namespace sb;
+
+#define SB_FIELD_DISPATCH(field, fn, name, ...)                      \
+    do {                                                             \
+        if ((field) == FIELD_FR) return fn<Fr>(__VA_ARGS__);         \
+        if ((field) == FIELD_FQ) return fn<Fq>(__VA_ARGS__);         \
+        set_error(name ": unknown field %d", (field));               \
+        return SB_ERR_ARG;                                           \
+    } while (0)
+
+extern "C" {
+
+int sb_lookup_multiplicity_device(int field, const void* d_l, size_t n_l, const void* d_t, size_t n_t, void* d_m, void* stream) {
+    if ((n_l && !d_l) || (n_t && (!d_t || !d_m)) || n_l >= 0xFFFFFFFFull || n_t > 0x40000000ull) {
+        set_error("sb_lookup_multiplicity_device: bad argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    SB_FIELD_DISPATCH(field, multiplicity_enqueue, "sb_lookup_multiplicity_device", d_l, n_l, d_t, n_t, d_m, st);
+}
+
+int sb_scaled_inverse_device(int field, const void* d_in, const uint64_t shift[4], const void* d_scale, void* d_out, size_t n, void* stream) {
+    if (n && (!d_in || !d_out)) {
+        set_error("sb_scaled_inverse_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    SB_FIELD_DISPATCH(field, scaled_inverse_enqueue, "sb_scaled_inverse_device", d_in, shift, d_scale, d_out, n, st);
+}
+
+int sb_lookup_inverses_device(int field, const void* d_l, const void* d_t, const void* d_m, const uint64_t r[4], size_t n, void* d_h,
+                              void* d_g, void* stream) {
+    if (!r || (n && (!d_l || !d_t || !d_m || !d_h || !d_g))) {
+        set_error("sb_lookup_inverses_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(sb_scaled_inverse_device(field, d_l, r, nullptr, d_h, n, stream));
+    return sb_scaled_inverse_device(field, d_t, r, d_m, d_g, n, stream);
+}
+
+int sb_sum_diff_device(int field, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream) {
+    if (!d_out || (n && !d_a)) {
+        set_error("sb_sum_diff_device: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    SB_FIELD_DISPATCH(field, sum_diff_enqueue, "sb_sum_diff_device", d_a, d_b, n, d_out, st);
+}
+
+int sb_sparse_register(int field, const uint64_t* rows, const uint64_t* cols, const uint64_t* values_mont, size_t nnz, size_t N,
+                       sb_sparse_t* out) {
+    if (!out || (nnz && (!rows || !cols || !values_mont)) || N >= 0xFFFFFFFFull || nnz >= 0xFFFFFFFFull ||
+        (field != FIELD_FR && field != FIELD_FQ)) {
+        set_error("sb_sparse_register: bad argument");
+        return SB_ERR_ARG;
+    }
+    for (size_t e = 0; e < nnz; e++) {
+        if (rows[e] >= N || cols[e] >= N) {  // the reference panics with "invalid matrix multiply" (sparse.rs:15-17)
+            set_error("sb_sparse_register: entry %zu (%llu,%llu) outside the %zu x %zu matrix", e, (unsigned long long)rows[e],
+                      (unsigned long long)cols[e], N, N);
+            return SB_ERR_ARG;
+        }
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::vector<uint32_t> row_ptr(N + 1, 0), col(nnz ? nnz : 1);
+    std::vector<uint64_t> val((nnz ? nnz : 1) * 4);
+    for (size_t e = 0; e < nnz; e++) row_ptr[rows[e] + 1]++;
+    for (size_t r = 0; r < N; r++) row_ptr[r + 1] += row_ptr[r];
+    std::vector<uint32_t> fill(row_ptr.begin(), row_ptr.end() - 1);
+    for (size_t e = 0; e < nnz; e++) {  // stable: entries of one row keep the reference's accumulation order
+        const uint32_t p = fill[rows[e]]++;
+        col[p] = (uint32_t)cols[e];
+        memcpy(&val[(size_t)p * 4], values_mont + e * 4, 32);
+    }
+    SparseMatrix* m = new SparseMatrix();
+    m->field = field;
+    m->N = N;
+    m->nnz = nnz;
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaError_t e1 = cudaMalloc(&m->d_row_ptr, (N + 1) * 4);
+    cudaError_t e2 = cudaMalloc(&m->d_col, col.size() * 4);
+    cudaError_t e3 = cudaMalloc(&m->d_val, val.size() * 8);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cudaFree(m->d_row_ptr);
+        cudaFree(m->d_col);
+        cudaFree(m->d_val);
+        delete m;
+        set_error("sb_sparse_register: cudaMalloc failed");
+        return SB_ERR_OOM;
+    }
+    SB_CUDA_TRY(cudaMemcpy(m->d_row_ptr, row_ptr.data(), (N + 1) * 4, cudaMemcpyHostToDevice));
+    SB_CUDA_TRY(cudaMemcpy(m->d_col, col.data(), col.size() * 4, cudaMemcpyHostToDevice));
+    SB_CUDA_TRY(cudaMemcpy(m->d_val, val.data(), val.size() * 8, cudaMemcpyHostToDevice));
+    *out = (sb_sparse_t)m;
+    return SB_OK;
+}
+
+void sb_sparse_release(sb_sparse_t h) {
+    SparseMatrix* m = (SparseMatrix*)h;
+    if (!m) return;
+    cudaDeviceSynchronize();
+    cudaFree(m->d_row_ptr);
+    cudaFree(m->d_col);
+    cudaFree(m->d_val);
+    delete m;
+}
+
+size_t sb_sparse_dim(sb_sparse_t h) { return h ? ((SparseMatrix*)h)->N : 0; }
+
+int sb_sparse_mismatch_device(sb_sparse_t h, const uint64_t* head, size_t head_len, const void* d_tail, size_t tail_len,
+                              uint64_t* mismatches, void* stream) {
+    SparseMatrix* m = (SparseMatrix*)h;
+    if (!m || !mismatches || (head_len && !head) || (tail_len && !d_tail)) {
+        set_error("sb_sparse_mismatch_device: null argument");
+        return SB_ERR_ARG;
+    }
+    if (head_len + tail_len != m->N) {
+        set_error("sb_sparse_mismatch_device: Z has %zu cells, the matrix is %zu x %zu", head_len + tail_len, m->N, m->N);
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    *mismatches = 0;
+    if (!m->N) return SB_OK;
+    const size_t head_bytes = align_up(head_len * 32, 256);
+    SB_TRY(g_lk_ws.reserve(256 + head_bytes));
+    unsigned long long* d_cnt = (unsigned long long*)g_lk_ws.ptr;
+    char* d_head = (char*)g_lk_ws.ptr + 256;
+    SB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
+    if (head_len) SB_CUDA_TRY(cudaMemcpyAsync(d_head, head, head_len * 32, cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((m->N + 255) / 256);
+    if (m->field == FIELD_FR)
+        k_sparse_mismatch<Fr><<<blocks, 256, 0, st>>>(m->d_row_ptr, m->d_col, (const Fr*)m->d_val, (const Fr*)d_head, head_len, (const Fr*)d_tail, m->N, d_cnt);
+    else
+        k_sparse_mismatch<Fq><<<blocks, 256, 0, st>>>(m->d_row_ptr, m->d_col, (const Fq*)m->d_val, (const Fq*)d_head, head_len, (const Fq*)d_tail, m->N, d_cnt);
+    SB_KERNEL_CHECK();
+    unsigned long long got = 0;
+    SB_CUDA_TRY(cudaMemcpyAsync(&got, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    SB_CUDA_TRY(cudaStreamSynchronize(st));
+    *mismatches = got;
+    return SB_OK;
+}
+
+int sb_concat_pad_device(const uint64_t* const* columns, const size_t* lens, size_t num_columns, size_t pad_size, void* d_out,
+                         size_t out_capacity, size_t* out_len, void* stream) {
+    if ((num_columns && (!columns || !lens)) || (!d_out && out_capacity)) {
+        set_error("sb_concat_pad_device: null argument");
+        return SB_ERR_ARG;
+    }
+    size_t total = 0;
+    for (size_t c = 0; c < num_columns; c++) total += lens[c] > pad_size ? lens[c] : pad_size;  // pad_using never truncates
+    if (out_len) *out_len = total;
+    if (total > out_capacity) {
+        set_error("sb_concat_pad_device: %zu cells do not fit the %zu-cell output", total, out_capacity);
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    char* dst = (char*)d_out;
+    for (size_t c = 0; c < num_columns; c++) {
+        if (lens[c]) {
+            if (!columns[c]) {
+                set_error("sb_concat_pad_device: column %zu is null", c);
+                return SB_ERR_ARG;
+            }
+            SB_CUDA_TRY(cudaMemcpyAsync(dst, columns[c], lens[c] * 32, cudaMemcpyHostToDevice, st));
+        }
+        dst += lens[c] * 32;
+        if (lens[c] < pad_size) {
+            SB_CUDA_TRY(cudaMemsetAsync(dst, 0, (pad_size - lens[c]) * 32, st));
+            dst += (pad_size - lens[c]) * 32;
+        }
+    }
+    return SB_OK;
+}
+
+/* ---- host front ends: stage through the library workspace, block until the result is back ---------------- */
+
+int sb_lookup_multiplicity(int field, const uint64_t* l, size_t n_l, const uint64_t* t, size_t n_t, uint64_t* m) {
+    if ((n_l && !l) || (n_t && (!t || !m))) {
+        set_error("sb_lookup_multiplicity: null argument");
+        return SB_ERR_ARG;
+    }
+    if (!n_t) return SB_OK;
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    char* d;
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_lk_stage.reserve(256 + (n_l + 2 * n_t) * 32));
+        d = (char*)g_lk_stage.ptr + 256;
+        if (n_l) SB_CUDA_TRY(cudaMemcpyAsync(d, l, n_l * 32, cudaMemcpyHostToDevice, rt.stream));
+        SB_CUDA_TRY(cudaMemcpyAsync(d + n_l * 32, t, n_t * 32, cudaMemcpyHostToDevice, rt.stream));
+    }
+    SB_TRY(sb_lookup_multiplicity_device(field, d, n_l, d + n_l * 32, n_t, d + (n_l + n_t) * 32, nullptr));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    SB_CUDA_TRY(cudaMemcpyAsync(m, d + (n_l + n_t) * 32, n_t * 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
+}
+
+int sb_scaled_inverse(int field, const uint64_t* in, const uint64_t shift[4], const uint64_t* scale, uint64_t* out, size_t n) {
+    if (n && (!in || !out)) {
+        set_error("sb_scaled_inverse: null argument");
+        return SB_ERR_ARG;
+    }
+    if (!n) return SB_OK;
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    char* d;
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_lk_stage.reserve(256 + 3 * n * 32));
+        d = (char*)g_lk_stage.ptr + 256;
+        SB_CUDA_TRY(cudaMemcpyAsync(d, in, n * 32, cudaMemcpyHostToDevice, rt.stream));
+        if (scale) SB_CUDA_TRY(cudaMemcpyAsync(d + n * 32, scale, n * 32, cudaMemcpyHostToDevice, rt.stream));
+    }
+    SB_TRY(sb_scaled_inverse_device(field, d, shift, scale ? d + n * 32 : nullptr, d + 2 * n * 32, n, nullptr));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    SB_CUDA_TRY(cudaMemcpyAsync(out, d + 2 * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
+}
+
+int sb_lookup_inverses(int field, const uint64_t* l, const uint64_t* t, const uint64_t* m, const uint64_t r[4], size_t n, uint64_t* h,
+                       uint64_t* g) {
+    if (!r || (n && (!l || !t || !m || !h || !g))) {
+        set_error("sb_lookup_inverses: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(sb_scaled_inverse(field, l, r, nullptr, h, n));
+    return sb_scaled_inverse(field, t, r, m, g, n);
+}
+
+int sb_sum_diff(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t out[4]) {
+    if (!out || (n && !a)) {
+        set_error("sb_sum_diff: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    char* d;
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_lk_stage.reserve(256 + 2 * n * 32));
+        d = (char*)g_lk_stage.ptr;
+        if (n) SB_CUDA_TRY(cudaMemcpyAsync(d + 256, a, n * 32, cudaMemcpyHostToDevice, rt.stream));
+        if (n && b) SB_CUDA_TRY(cudaMemcpyAsync(d + 256 + n * 32, b, n * 32, cudaMemcpyHostToDevice, rt.stream));
+    }
+    SB_TRY(sb_sum_diff_device(field, d + 256, b ? d + 256 + n * 32 : nullptr, n, d + 64, nullptr));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    SB_CUDA_TRY(cudaMemcpyAsync(out, d + 64, 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
+}
+
+int sb_sparse_mismatch(sb_sparse_t h, const uint64_t* Z, size_t N, uint64_t* mismatches) {
+    if (!Z && N) {
+        set_error("sb_sparse_mismatch: null argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    char* d;
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_lk_stage.reserve(256 + N * 32));
+        d = (char*)g_lk_stage.ptr + 256;
+        if (N) SB_CUDA_TRY(cudaMemcpyAsync(d, Z, N * 32, cudaMemcpyHostToDevice, rt.stream));
+    }
+    return sb_sparse_mismatch_device(h, nullptr, 0, d, N, mismatches, nullptr);
+}
+
+}  // extern "C"

@@ -85,6 +85,7 @@ class PlonkStructure:
     num_lookups: int
     custom_gates_lookup_compressed: CompressedGates
     gates: Optional[List] = None         # S.gates: the individual gate Expressions (Protogalaxy evaluates them one by one)
+    lookup_arguments: Optional[object] = None  # lookup::Arguments (sirius_b200.lookup.Arguments), src/plonk/mod.rs:156
 
     def __post_init__(self):
         lib = _lib.load()
@@ -99,14 +100,18 @@ class PlonkStructure:
         self._hom_prog = Program(self.field, GraphEvaluator.new(self.custom_gates_lookup_compressed.homogeneous, self.modulus))
 
     def is_sat(self, ck: CommitmentKey, U_challenges, U_W_commitments, W: Sequence[np.ndarray]) -> None:
-        """PlonkStructure::is_sat (src/plonk/mod.rs:304-361) without the host-side sps_verify / log-derivative parts:
-        the compressed gate expression vanishes on every row and the witness rounds re-open."""
+        """PlonkStructure::is_sat (src/plonk/mod.rs:304-361) without the host-side sps_verify (random oracle): the
+        compressed gate expression vanishes on every row, the log-derivative sums agree and the witness rounds re-open."""
         if getattr(self, "_compressed_prog", None) is None:
             self._compressed_prog = Program(self.field, GraphEvaluator.new(self.custom_gates_lookup_compressed.compressed, self.modulus))
         got = evaluate_rows(self, self._compressed_prog, W, np.asarray(U_challenges, dtype=np.uint64).reshape(-1, 4))
         mismatch = int(np.count_nonzero(np.any(got != 0, axis=1)))
         if mismatch:
             raise EvaluationMismatch(mismatch, 1 << self.k)
+        from .lookup import is_sat_log_derivative
+
+        if not is_sat_log_derivative(self, W):
+            raise LogDerivativeNotSat()
         bad = sum(1 for Ci, Wi in zip(U_W_commitments, W) if not np.array_equal(ck.commit(Wi), np.asarray(Ci, dtype=np.uint64).reshape(8)))
         if bad:
             raise CommitmentMismatch(bad)
@@ -158,6 +163,10 @@ class CommitmentMismatch(Exception):
         self.mismatch_count = mismatch_count
 
 
+class LogDerivativeNotSat(Exception):
+    """plonk::Error::LogDerivativeNotSat (src/plonk/mod.rs:348-350, src/nifs/sangria/mod.rs:378-380)"""
+
+
 class ECommitmentMismatch(Exception):
     """VerifyError::ECommitmentMismatch (src/nifs/sangria/mod.rs:319-320)"""
 
@@ -182,14 +191,16 @@ class VanillaFS:
     @staticmethod
     def is_sat_accumulation(S: "PlonkStructure", U_challenges, U_u, W: Sequence[np.ndarray], E: np.ndarray) -> None:
         """src/nifs/sangria/mod.rs:334-383: homogeneous gate polynomial on (W, challenges ++ [u]) must equal E row by
-        row.  (The log-derivative check of lookup arguments stays on the Rust side: lookups are out of scope.)"""
-        if S.num_lookups:
-            raise NotImplementedError("is_sat_log_derivative (lookup arguments) is outside the GPU hot path")
+        row, then the log-derivative sum check of the lookup arguments."""
         ch = np.concatenate([np.asarray(U_challenges, dtype=np.uint64).reshape(-1, 4), np.asarray(U_u, dtype=np.uint64).reshape(1, 4)])
         got = evaluate_rows(S, S._hom_prog, W, ch)
         mismatch = int(np.count_nonzero(np.any(got != np.asarray(E, dtype=np.uint64).reshape(-1, 4), axis=1)))
         if mismatch:
             raise EvaluationMismatch(mismatch, 1 << S.k)
+        from .lookup import is_sat_log_derivative
+
+        if not is_sat_log_derivative(S, W):
+            raise LogDerivativeNotSat()
 
     @staticmethod
     def is_sat_witness_commit(ck: CommitmentKey, W_commitments, W: Sequence[np.ndarray], E: np.ndarray, E_commitment) -> None:
