@@ -189,7 +189,7 @@ template <bool INL = true, class F>
 SB_HD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
     Affine<F> r;
     if (p.is_identity()) { r.x = F::zero(); r.y = F::zero(); return r; }
-    F i = inv_binary(mulx<INL>(p.zz, p.zzz));  // 1/(zz*zzz)
+    F i = inv_safegcd(mulx<INL>(p.zz, p.zzz));  // 1/(zz*zzz)
     F izz = mulx<INL>(i, p.zzz);               // 1/zz
     F izzz = mulx<INL>(i, p.zz);               // 1/zzz
     r.x = mulx<INL>(p.x, izz);

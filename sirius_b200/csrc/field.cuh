@@ -550,6 +550,182 @@ SB_HD Fe<P> inv_binary(const Fe<P>& a) {
     return mul(r, Fe<P>::r_cubed());
 }
 
+// ---- inverse by batched divsteps ("safegcd", Bernstein-Yang 2019, in the 30-bit-limb variable-time form that
+// libsecp256k1's modinv32_var popularised) ------------------------------------------------------------------
+// f, g (the gcd pair, starting at p and the input) and d, e (the Bezout coefficients mod p) live in nine signed
+// 30-bit limbs.  Each round runs 30 divsteps on the low 30 bits of f, g only -- stripping trailing zeros of g with
+// ctz and cancelling up to 8 low bits at once -- while collecting them in a 2x2 integer matrix t with entries below
+// 2^30, and then applies t to the full (f, g) and, modulo p with one exact division by 2^30, to (d, e).  A 254-bit
+// inverse takes ~18-22 rounds of ~150 multiply-adds instead of ~380 dependent whole-number shift/subtract rounds.
+SB_HD int sg_ctz32(uint32_t x) {  // x != 0
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
+struct SgMatrix {
+    int32_t u, v, q, r;
+};
+
+// 30 divsteps on the low limbs; eta = -delta.  Returns the new eta; t maps (f, g) -> 2^30 * (f', g').
+SB_HD int32_t sg_divsteps_30(int32_t eta, uint32_t f, uint32_t g, SgMatrix& t) {
+    uint32_t u = 1, v = 0, q = 0, r = 1;
+    int i = 30;
+    for (;;) {
+        const int zeros = sg_ctz32(g | (0xFFFFFFFFu << i));  // sentinel: never count past the i steps left
+        g >>= zeros;
+        u <<= zeros;
+        v <<= zeros;
+        eta -= zeros;
+        i -= zeros;
+        if (i == 0) break;
+        if (eta < 0) {  // swap: (f, g) <- (g, -f)
+            eta = -eta;
+            uint32_t tmp = f; f = g; g = 0u - tmp;
+            tmp = u; u = q; q = 0u - tmp;
+            tmp = v; v = r; r = 0u - tmp;
+        }
+        // cancel the low min(eta + 1, i, 8) bits of g with a multiple of f (f is odd)
+        const int limit = (eta + 1) > i ? i : (eta + 1);
+        const uint32_t m = (0xFFFFFFFFu >> (32 - limit)) & 255u;
+        uint32_t finv = f;                 // f * f = 1 mod 8
+        finv *= 2u - f * finv;             // mod 2^6
+        finv *= 2u - f * finv;             // mod 2^12
+        const uint32_t w = (g * (0u - finv)) & m;
+        g += f * w;
+        q += u * w;
+        r += v * w;
+    }
+    t.u = (int32_t)u; t.v = (int32_t)v; t.q = (int32_t)q; t.r = (int32_t)r;
+    return eta;
+}
+
+// (f, g) <- t * (f, g) / 2^30   (exact)
+SB_HD void sg_update_fg(int32_t f[9], int32_t g[9], const SgMatrix& t) {
+    const int32_t M30 = 0x3FFFFFFF;
+    int64_t cf = (int64_t)t.u * f[0] + (int64_t)t.v * g[0];
+    int64_t cg = (int64_t)t.q * f[0] + (int64_t)t.r * g[0];
+    cf >>= 30;
+    cg >>= 30;
+#pragma unroll
+    for (int i = 1; i < 9; i++) {
+        cf += (int64_t)t.u * f[i] + (int64_t)t.v * g[i];
+        cg += (int64_t)t.q * f[i] + (int64_t)t.r * g[i];
+        f[i - 1] = (int32_t)cf & M30;
+        g[i - 1] = (int32_t)cg & M30;
+        cf >>= 30;
+        cg >>= 30;
+    }
+    f[8] = (int32_t)cf;
+    g[8] = (int32_t)cg;
+}
+
+// (d, e) <- t * (d, e) / 2^30 mod p, kept in (-2p, p): multiples of p make the low 30 bits vanish first
+SB_HD void sg_update_de(int32_t d[9], int32_t e[9], const SgMatrix& t, const int32_t mod[9], uint32_t mod_inv30) {
+    const int32_t M30 = 0x3FFFFFFF;
+    const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+    int32_t md = (t.u & sd) + (t.v & se);
+    int32_t me = (t.q & sd) + (t.r & se);
+    int64_t cd = (int64_t)t.u * d[0] + (int64_t)t.v * e[0];
+    int64_t ce = (int64_t)t.q * d[0] + (int64_t)t.r * e[0];
+    md -= (int32_t)((mod_inv30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+    me -= (int32_t)((mod_inv30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+    cd += (int64_t)mod[0] * md;
+    ce += (int64_t)mod[0] * me;
+    cd >>= 30;
+    ce >>= 30;
+#pragma unroll
+    for (int i = 1; i < 9; i++) {
+        cd += (int64_t)t.u * d[i] + (int64_t)t.v * e[i] + (int64_t)mod[i] * md;
+        ce += (int64_t)t.q * d[i] + (int64_t)t.r * e[i] + (int64_t)mod[i] * me;
+        d[i - 1] = (int32_t)cd & M30;
+        e[i - 1] = (int32_t)ce & M30;
+        cd >>= 30;
+        ce >>= 30;
+    }
+    d[8] = (int32_t)cd;
+    e[8] = (int32_t)ce;
+}
+
+SB_HD void sg_pack30(const uint32_t w[8], int32_t o[9]) {  // 8 x 32 bits -> 9 x 30 bits
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const int bit = 30 * i, lo = bit >> 5, sh = bit & 31;
+        uint64_t x = (uint64_t)w[lo] >> sh;
+        if (lo + 1 < 8 && sh > 2) x |= (uint64_t)w[lo + 1] << (32 - sh);
+        o[i] = (int32_t)((uint32_t)x & 0x3FFFFFFFu);
+    }
+}
+
+// Inverse of the stored integer a (Montgomery form in, Montgomery form out); zero maps to zero.
+template <class P>
+SB_HD Fe<P> inv_safegcd(const Fe<P>& a) {
+    const int32_t M30 = 0x3FFFFFFF;
+    uint32_t pw[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) pw[i] = Fe<P>::modulus_limb(i);
+    int32_t mod[9], f[9], g[9], d[9], e[9];
+    sg_pack30(pw, mod);
+    sg_pack30(a.v, g);
+    uint32_t minv = pw[0];  // p^-1 mod 2^30 by Newton (p * p = 1 mod 8)
+    minv *= 2u - pw[0] * minv;
+    minv *= 2u - pw[0] * minv;
+    minv *= 2u - pw[0] * minv;
+    minv *= 2u - pw[0] * minv;
+    minv &= (uint32_t)M30;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        f[i] = mod[i];
+        d[i] = 0;
+        e[i] = 0;
+    }
+    e[0] = 1;
+    int32_t eta = -1;
+    for (int round = 0; round < 40; round++) {  // 254-bit inputs finish in about 20; the cap only guards bad input
+        SgMatrix t;
+        eta = sg_divsteps_30(eta, (uint32_t)f[0], (uint32_t)g[0], t);
+        sg_update_de(d, e, t, mod, minv);
+        sg_update_fg(f, g, t);
+        int32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) nz |= g[i];
+        if (nz == 0) break;
+    }
+    // g = 0, f = +-gcd = +-1 (or +-p for a = 0, where d = 0); d = +-a^-1 in (-2p, p): fix the sign and the range
+    const int32_t neg = f[8] >> 31;
+    int32_t add = d[8] >> 31;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        d[i] += mod[i] & add;
+        d[i] = (d[i] ^ neg) - neg;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        d[i + 1] += d[i] >> 30;
+        d[i] &= M30;
+    }
+    add = d[8] >> 31;
+#pragma unroll
+    for (int i = 0; i < 9; i++) d[i] += mod[i] & add;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        d[i + 1] += d[i] >> 30;
+        d[i] &= M30;
+    }
+    Fe<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {  // 9 x 30 bits -> 8 x 32 bits
+        const int bit = 32 * i, lo = bit / 30, sh = bit % 30;
+        uint64_t x = (uint64_t)(uint32_t)d[lo] >> sh;
+        x |= (uint64_t)(uint32_t)d[lo + 1] << (30 - sh);
+        if (lo + 2 < 9) x |= (uint64_t)(uint32_t)d[lo + 2] << (60 - sh);
+        r.v[i] = (uint32_t)x;
+    }
+    return mul(r, Fe<P>::r_cubed());  // (A R)^-1 * R^3 / R = A^-1 R
+}
+
 // a^(p-2) by square-and-multiply over the constant exponent (a != 0).
 template <class P>
 SB_HD Fe<P> inv(const Fe<P>& a) {

@@ -7,16 +7,16 @@
 //         keeps, per distinct value, the smallest row index (atomicMin), the l rows count into that row, and a last
 //         pass emits F::from_u128(count).  Counts are integers, so the result does not depend on atomic ordering.
 //   * lookup::Arguments::evaluate_h_g      (src/plonk/lookup.rs:300-312)
-//         h_i = 1/(l_i + r) (0 when l_i + r = 0),  g_i = m_i / (t_i + r): Montgomery-trick batches of 16 per thread
-//         around one binary-GCD inversion.  The same kernel with shift 0 resolves halo2 `Assigned` fractions
+//         h_i = 1/(l_i + r) (0 when l_i + r = 0),  g_i = m_i / (t_i + r): Montgomery-trick batches of 128/256 cells per
+//         warp around one divstep inversion (field.cuh inv_safegcd).  The same kernel with shift 0 resolves halo2 `Assigned` fractions
 //         (util::batch_invert_assigned, src/util/mod.rs:128-153: numerator * denominator^-1, zero denominator -> 0).
 //   * PlonkStructure::is_sat_log_derivative (src/plonk/mod.rs:363-397): sum_i (h_i - g_i).
 //   * sparse::matrix_multiply + the mismatch count of is_sat_permutation
 //         (src/polynomial/sparse.rs:7-20, src/nifs/sangria/mod.rs:385-453, src/nifs/protogalaxy/mod.rs:660-689).
 //   * util::concatenate_with_padding       (src/util/mod.rs:214-218): host columns -> one device round vector.
 //
-// Everything here is 32-byte-cell streaming work (HBM-bound) except the inversions (3 products per cell + 1/16 of a
-// 254-bit binary GCD) and the hash probes (one random 32-byte read per probe).
+// Everything here is 32-byte-cell streaming work (HBM-bound) except the inversions (4.5-6 products per cell + one
+// 254-bit divstep inversion per warp) and the hash probes (one random 32-byte read per probe).
 #include <string.h>
 
 #include <algorithm>
@@ -123,42 +123,95 @@ k_lookup_emit(const F* __restrict__ t, uint32_t n_t, const uint32_t* __restrict_
     stc(m + i, out);
 }
 
-constexpr int SI_CHUNK = 16;
+// ---- batched inversion ---------------------------------------------------------------------------------------
+// One divstep (safegcd) inversion per WARP: every lane multiplies up its CH cells (strided, so loads coalesce), the 32
+// lane totals are combined by a prefix and a suffix scan through shuffles, lane 0 inverts the warp total, and each
+// lane recovers the inverse of its own total as inv_total * (product of the lanes before) * (product of the lanes
+// after) before unwinding its cells.  3 + 12/CH products per cell and 1/(32 CH) inversions.
+struct InvJobs {
+    const void* in[2];
+    const void* scale[2];  // nullptr = 1
+    void* out[2];
+    const void* shift;     // one 32-byte cell
+};
 
-// out[i] = scale[i] * (in[i] + shift)^-1, 0 where in[i] + shift = 0;  scale == nullptr means 1
 template <class F>
+SB_D F shfl_up_fe(const F& v, int d) {
+    F r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_up_sync(0xFFFFFFFFu, v.v[i], d);
+    return r;
+}
+template <class F>
+SB_D F shfl_down_fe(const F& v, int d) {
+    F r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xFFFFFFFFu, v.v[i], d);
+    return r;
+}
+template <class F>
+SB_D F shfl_fe(const F& v, int src) {
+    F r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xFFFFFFFFu, v.v[i], src);
+    return r;
+}
+
+// out[i] = scale[i] * (in[i] + shift)^-1, 0 where in[i] + shift = 0;  blockIdx.y selects the job
+template <class F, int CH>
 __global__ void __launch_bounds__(128)
-k_scaled_inverse(const F* __restrict__ in, const F* __restrict__ shift_p, const F* __restrict__ scale, F* __restrict__ out, size_t n) {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t base = tid * SI_CHUNK;
-    if (base >= n) return;
-    const int cnt = (n - base) < (size_t)SI_CHUNK ? (int)(n - base) : SI_CHUNK;
-    const F shift = ldc(shift_p);
-    F pre[SI_CHUNK];
+k_scaled_inverse(const InvJobs jobs, size_t n) {
+    const bool second = blockIdx.y != 0;  // (selected, not indexed: keeps the parameter struct out of local memory)
+    const F* __restrict__ in = (const F*)(second ? jobs.in[1] : jobs.in[0]);
+    const F* __restrict__ scale = (const F*)(second ? jobs.scale[1] : jobs.scale[0]);
+    F* __restrict__ out = (F*)(second ? jobs.out[1] : jobs.out[0]);
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t base = warp * (size_t)(32 * CH) + lane;
+    if (warp * (size_t)(32 * CH) >= n) return;  // whole warps leave together
+    const F shift = ldc((const F*)jobs.shift);
+    F pre[CH];
     F acc = F::one();
 #pragma unroll
-    for (int i = 0; i < SI_CHUNK; i++) {
-        if (i < cnt) {
-            const F v = add(ldc(in + base + i), shift);
-            pre[i] = acc;
+    for (int i = 0; i < CH; i++) {
+        const size_t idx = base + (size_t)i * 32;
+        pre[i] = acc;
+        if (idx < n) {
+            const F v = add(ldc(in + idx), shift);
             if (!v.is_zero()) acc = mul(acc, v);
         }
     }
-    F inv_all = inv_binary(acc);
+    F inc = acc, suf = acc;  // inclusive prefix / suffix products of the lane totals
 #pragma unroll
-    for (int i = SI_CHUNK - 1; i >= 0; i--) {
-        if (i < cnt) {
-            const F v = add(ldc(in + base + i), shift);
+    for (int d = 1; d < 32; d <<= 1) {
+        const F up = shfl_up_fe(inc, d);
+        const F dn = shfl_down_fe(suf, d);
+        if (lane >= d) inc = mul(up, inc);
+        if (lane + d < 32) suf = mul(suf, dn);
+    }
+    F inv_total = shfl_fe(inc, 31);
+    if (lane == 0) inv_total = inv_safegcd(inv_total);  // a product of non-zero elements (or one)
+    inv_total = shfl_fe(inv_total, 0);
+    F before = shfl_up_fe(inc, 1);
+    F after = shfl_down_fe(suf, 1);
+    if (lane == 0) before = F::one();
+    if (lane == 31) after = F::one();
+    F inv_all = mul(mul(inv_total, before), after);  // (this lane's total)^-1
+#pragma unroll
+    for (int i = CH - 1; i >= 0; i--) {
+        const size_t idx = base + (size_t)i * 32;
+        if (idx < n) {
+            const F v = add(ldc(in + idx), shift);
             F o = F::zero();
             if (!v.is_zero()) {
                 o = mul(inv_all, pre[i]);
                 inv_all = mul(inv_all, v);
                 if (scale) {
-                    const F s = ldc(scale + base + i);
+                    const F s = ldc(scale + idx);
                     o = s.is_zero() ? s : mul(o, s);
                 }
             }
-            stc(out + base + i, o);
+            stc(out + idx, o);
         }
     }
 }
@@ -240,15 +293,32 @@ int multiplicity_enqueue(const void* d_l, size_t n_l, const void* d_t, size_t n_
     return SB_OK;
 }
 
+Scratch g_inv_shift;  // the 32-byte shift cell of the inversion kernel
+
 template <class F>
-int scaled_inverse_enqueue(const void* d_in, const uint64_t* shift, const void* d_scale, void* d_out, size_t n, cudaStream_t st) {
+int scaled_inverse_enqueue(const void* const* d_in, const uint64_t* shift, const void* const* d_scale, void* const* d_out, int jobs, size_t n,
+                           cudaStream_t st) {
     if (!n) return SB_OK;
-    SB_TRY(g_lk_stage.reserve(256));
+    SB_TRY(g_inv_shift.reserve(256));
     uint64_t zero[4] = {0, 0, 0, 0};
-    // the 32-byte shift travels through a tiny device cell (stream-ordered, so back-to-back calls may reuse it)
-    SB_CUDA_TRY(cudaMemcpyAsync(g_lk_stage.ptr, shift ? shift : zero, 32, cudaMemcpyHostToDevice, st));
-    const size_t threads = (n + SI_CHUNK - 1) / SI_CHUNK;
-    k_scaled_inverse<F><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>((const F*)d_in, (const F*)g_lk_stage.ptr, (const F*)d_scale, (F*)d_out, n);
+    // stream-ordered, so back-to-back calls may reuse the cell
+    SB_CUDA_TRY(cudaMemcpyAsync(g_inv_shift.ptr, shift ? shift : zero, 32, cudaMemcpyHostToDevice, st));
+    InvJobs j;
+    for (int q = 0; q < 2; q++) {
+        j.in[q] = q < jobs ? d_in[q] : nullptr;
+        j.scale[q] = q < jobs ? d_scale[q] : nullptr;
+        j.out[q] = q < jobs ? d_out[q] : nullptr;
+    }
+    j.shift = g_inv_shift.ptr;
+    // few cells: short chains per lane so that every SM gets a warp; many cells: fewer inversions and scan products
+    // per cell (the inversion is issue-bound at ~2 warps per scheduler, profiles/r1_microbench4.txt)
+    const int ch = n <= ((size_t)1 << 18) ? 4 : (n < ((size_t)1 << 20) ? 8 : 16);
+    const size_t per_warp = (size_t)32 * ch;
+    const size_t warps = (n + per_warp - 1) / per_warp;
+    dim3 grid((unsigned)((warps + 3) / 4), (unsigned)jobs);
+    if (ch == 4) k_scaled_inverse<F, 4><<<grid, 128, 0, st>>>(j, n);
+    else if (ch == 8) k_scaled_inverse<F, 8><<<grid, 128, 0, st>>>(j, n);
+    else k_scaled_inverse<F, 16><<<grid, 128, 0, st>>>(j, n);
     SB_KERNEL_CHECK();
     return SB_OK;
 }
@@ -306,7 +376,10 @@ int sb_scaled_inverse_device(int field, const void* d_in, const uint64_t shift[4
     Runtime& rt = runtime();
     std::lock_guard<std::mutex> lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
-    SB_FIELD_DISPATCH(field, scaled_inverse_enqueue, "sb_scaled_inverse_device", d_in, shift, d_scale, d_out, n, st);
+    const void* ins[1] = {d_in};
+    const void* scales[1] = {d_scale};
+    void* outs[1] = {d_out};
+    SB_FIELD_DISPATCH(field, scaled_inverse_enqueue, "sb_scaled_inverse_device", ins, shift, scales, outs, 1, n, st);
 }
 
 int sb_lookup_inverses_device(int field, const void* d_l, const void* d_t, const void* d_m, const uint64_t r[4], size_t n, void* d_h,
@@ -315,8 +388,14 @@ int sb_lookup_inverses_device(int field, const void* d_l, const void* d_t, const
         set_error("sb_lookup_inverses_device: null argument");
         return SB_ERR_ARG;
     }
-    SB_TRY(sb_scaled_inverse_device(field, d_l, r, nullptr, d_h, n, stream));
-    return sb_scaled_inverse_device(field, d_t, r, d_m, d_g, n, stream);
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    const void* ins[2] = {d_l, d_t};       // h = (l + r)^-1 and g = m (t + r)^-1 in one launch
+    const void* scales[2] = {nullptr, d_m};
+    void* outs[2] = {d_h, d_g};
+    SB_FIELD_DISPATCH(field, scaled_inverse_enqueue, "sb_lookup_inverses_device", ins, r, scales, outs, 2, n, st);
 }
 
 int sb_sum_diff_device(int field, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream) {
@@ -517,8 +596,24 @@ int sb_lookup_inverses(int field, const uint64_t* l, const uint64_t* t, const ui
         set_error("sb_lookup_inverses: null argument");
         return SB_ERR_ARG;
     }
-    SB_TRY(sb_scaled_inverse(field, l, r, nullptr, h, n));
-    return sb_scaled_inverse(field, t, r, m, g, n);
+    if (!n) return SB_OK;
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    char* d;
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        SB_TRY(g_lk_stage.reserve(256 + 5 * n * 32));
+        d = (char*)g_lk_stage.ptr + 256;
+        SB_CUDA_TRY(cudaMemcpyAsync(d, l, n * 32, cudaMemcpyHostToDevice, rt.stream));
+        SB_CUDA_TRY(cudaMemcpyAsync(d + n * 32, t, n * 32, cudaMemcpyHostToDevice, rt.stream));
+        SB_CUDA_TRY(cudaMemcpyAsync(d + 2 * n * 32, m, n * 32, cudaMemcpyHostToDevice, rt.stream));
+    }
+    SB_TRY(sb_lookup_inverses_device(field, d, d + n * 32, d + 2 * n * 32, r, n, d + 3 * n * 32, d + 4 * n * 32, nullptr));
+    std::lock_guard<std::mutex> lk(rt.mu);
+    SB_CUDA_TRY(cudaMemcpyAsync(h, d + 3 * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaMemcpyAsync(g, d + 4 * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
+    SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+    return SB_OK;
 }
 
 int sb_sum_diff(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t out[4]) {

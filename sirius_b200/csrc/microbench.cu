@@ -146,6 +146,14 @@ __global__ void k_mb_inv(F* io, int iters) {
     io[2 * i] = a;
 }
 
+template <class F>
+__global__ void k_mb_inv_safegcd(F* io, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    F a = io[2 * i];
+    for (int k = 0; k < iters; k++) a = inv_safegcd(a);
+    io[2 * i] = a;
+}
+
 __global__ void k_mb_imad_wide(uint32_t* io, int iters) {  // raw IMAD.WIDE.U32 issue rate, 8 independent accumulators
     uint32_t a = io[threadIdx.x], b = io[threadIdx.x + 32];
     unsigned long long acc[8];
@@ -194,6 +202,7 @@ extern "C" int sb_microbench(int which, int iters, int blocks, int threads, doub
             case 9: k_mb_quad_double<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 10: k_mb_double_call<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 11: k_mb_inv<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
+            case 12: k_mb_inv_safegcd<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
             default: cudaFree(d); set_error("sb_microbench: unknown test %d", which); return SB_ERR_ARG;
         }
         cudaEventRecord(e1, rt.stream);

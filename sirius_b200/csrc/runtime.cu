@@ -135,7 +135,7 @@ __global__ void k_selftest_field(const F* a, const F* b, size_t n, F* o_ptx, F* 
     o_port[i] = mul_portable(x, y);
     o_add[i] = add(x, y);
     o_sub[i] = sub(x, y);
-    o_inv[i] = x.is_zero() ? x : inv(x);
+    o_inv[i] = (i & 1) ? inv_safegcd(x) : (x.is_zero() ? x : ((i & 2) ? inv_binary(x) : inv(x)));  // all three inversion routines
 }
 
 }  // namespace sb

@@ -20,6 +20,11 @@ template <class F>
 static void t_inv(const uint64_t* a, uint64_t* o, size_t n) {
     for (size_t i = 0; i < n; i++) ((F*)o)[i] = (i & 1) ? inv(((const F*)a)[i]) : inv_binary(((const F*)a)[i]);
 }
+template <class F>
+static int t_inv_safegcd(const uint64_t* a, uint64_t* o, size_t n) {
+    for (size_t i = 0; i < n; i++) ((F*)o)[i] = inv_safegcd(((const F*)a)[i]);
+    return 0;
+}
 // sum_i (+/-) P_i with madd, then tree-combine two halves with xyzz_add, double once, -> affine
 template <class F>
 static void t_points(const uint64_t* pts, const uint8_t* negs, size_t n, uint64_t* out_sum, uint64_t* out_dbl) {
@@ -43,6 +48,9 @@ void ha_addsub(int field, const uint64_t* a, const uint64_t* b, uint64_t* oa, ui
 }
 void ha_inv(int field, const uint64_t* a, uint64_t* o, size_t n) {
     if (field == FIELD_FR) t_inv<Fr>(a, o, n); else t_inv<Fq>(a, o, n);
+}
+void ha_inv_safegcd(int field, const uint64_t* a, uint64_t* o, size_t n) {
+    if (field == FIELD_FR) t_inv_safegcd<Fr>(a, o, n); else t_inv_safegcd<Fq>(a, o, n);
 }
 void ha_points(int curve, const uint64_t* pts, const uint8_t* negs, size_t n, uint64_t* out_sum, uint64_t* out_dbl) {
     if (curve == CURVE_BN256) t_points<Fq>(pts, negs, n, out_sum, out_dbl); else t_points<Fr>(pts, negs, n, out_sum, out_dbl);

@@ -49,6 +49,28 @@ def test_field_portable(ha, oracle, field):
     assert np.array_equal(oi, oracle.field_inv(field, nz))
 
 
+@pytest.mark.parametrize("field", [R.FIELD_FR, R.FIELD_FQ])
+def test_inv_safegcd_portable(ha, oracle, field):
+    """the divstep inversion (field.cuh inv_safegcd) against Python pow on edge values and 20k random elements"""
+    m = R.MODULUS[field]
+    edge = [0, 1, 2, 3, m - 1, m - 2, (m - 1) // 2, (m + 1) // 2, 1 << 30, (1 << 30) - 1, 1 << 253, (1 << 253) - 1, 1 << 128,
+            pow(2, 256, m), pow(2, 512, m), m - pow(2, 256, m)] + [1 << s for s in range(0, 254, 7)] + [m - (1 << s) for s in range(0, 254, 11)]
+    vals = edge + R.from_mont_limbs(oracle.random_field(field, 99, 20000), m)
+    # the routine inverts the stored Montgomery residue: pass v as the residue of V = v * R^-1
+    a = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        for k in range(4):
+            a[i, k] = (v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+    o = np.zeros_like(a)
+    ha.ha_inv_safegcd(field, p(a), p(o), len(vals))
+    Rm = pow(2, 256, m)
+    for i, v in enumerate(vals):
+        got = sum(int(o[i, k]) << (64 * k) for k in range(4))
+        # stored v = V*R  ->  expected stored result V^-1 * R = v^-1 * R^2
+        exp = (pow(v, m - 2, m) * Rm * Rm) % m if v else 0
+        assert got == exp, (i, hex(v))
+
+
 @pytest.mark.parametrize("curve", [R.CURVE_BN256, R.CURVE_GRUMPKIN])
 def test_xyzz_group_law(ha, oracle, curve):
     pts = R.running_bases(12, curve)
