@@ -169,6 +169,101 @@ __global__ void k_mb_imad_wide(uint32_t* io, int iters) {  // raw IMAD.WIDE.U32 
     io[threadIdx.x] = (uint32_t)s ^ (uint32_t)(s >> 32);
 }
 
+
+// ---- raw pipe rates (inline PTX, volatile: nothing is folded away).  Every thread runs `iters` rounds of 8
+// independent dependency chains of one instruction kind; tools/microbench5.py turns the times into cycles per
+// warp-instruction per scheduler.  which: 20 mad.wide.u32 (IMAD.WIDE), 21 mad.lo.cc/madc.hi.cc pairs (the
+// IMAD.WIDE.X carry chain of mul_ptx), 22 mad.lo.u32 (IMAD), 23 add.cc/addc (IADD3.X), 24 fma.rz.f64 (DFMA),
+// 25 DFMA + 64-bit integer add interleaved 3:2 (the FP64 limb-product recipe), 26 IMAD.WIDE and DFMA
+// interleaved 1:1 in one warp, 27 even warps IMAD.WIDE / odd warps DFMA, 28 even warps carry-chain IMAD / odd warps
+// the 3:2 DFMA+add recipe, 29 add.u64.
+template <int KIND>
+__global__ void k_mb_pipe(uint32_t* io, int iters) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a = io[tid & 1023] | 1u, b = io[(tid + 7) & 1023] | 3u;
+    unsigned long long acc[8];
+    double dacc[8];
+    uint32_t r[16];
+    const double da = 4503599627370497.0 + (double)(a & 0xffff), db = 3.0 + (double)(b & 0xff);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc[j] = (unsigned long long)j * 0x9e3779b97f4a7c15ull + a; dacc[j] = (double)j + 0.5; }
+#pragma unroll
+    for (int j = 0; j < 16; j++) r[j] = a * (j + 1) + b;
+    int kind = KIND;
+    if (KIND == 27) kind = ((threadIdx.x >> 5) & 1) ? 24 : 20;
+    if (KIND == 28) kind = ((threadIdx.x >> 5) & 1) ? 25 : 21;
+#pragma unroll 1
+    for (int k = 0; k < iters; k++) {
+        // every chain feeds its own result back as an operand, so ptxas cannot hoist or merge anything
+        if (kind == 20) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = (unsigned long long)(uint32_t)acc[j] * b + acc[j];
+        } else if (kind == 21) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t* q = r + 8 * h;
+                const uint32_t x0 = q[1], x1 = q[3], x2 = q[5], x3 = q[7], s2 = q[0] | 1u;
+                asm volatile("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
+                             "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+                             "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
+                             "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+                             "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
+                             "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+                             "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
+                             "madc.hi.u32 %7, %11, %12, %7;"
+                             : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7])
+                             : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(s2));
+            }
+        } else if (kind == 22) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = r[j] * b + r[j + 8];
+        } else if (kind == 23) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t* q = r + 8 * h;
+                asm volatile("add.cc.u32 %0, %0, %1;\n\t"
+                             "addc.cc.u32 %1, %1, %2;\n\t"
+                             "addc.cc.u32 %2, %2, %3;\n\t"
+                             "addc.cc.u32 %3, %3, %4;\n\t"
+                             "addc.cc.u32 %4, %4, %5;\n\t"
+                             "addc.cc.u32 %5, %5, %6;\n\t"
+                             "addc.cc.u32 %6, %6, %7;\n\t"
+                             "addc.u32 %7, %7, %0;"
+                             : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]));
+            }
+        } else if (kind == 24) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(dacc[j]) : "d"(db), "d"(da));
+        } else if (kind == 25) {  // per limb product: 2 DFMA + 1 DADD on the FP64 pipe, two 64-bit integer adds
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double hi, lo, sub;
+                asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(hi) : "d"(dacc[j]), "d"(db), "d"(da));
+                asm volatile("sub.rz.f64 %0, %1, %2;" : "=d"(sub) : "d"(da), "d"(hi));
+                asm volatile("fma.rz.f64 %0, %1, %2, %3;" : "=d"(lo) : "d"(dacc[j]), "d"(db), "d"(sub));
+                acc[2 * j] += (unsigned long long)__double_as_longlong(hi);
+                acc[2 * j + 1] += (unsigned long long)__double_as_longlong(lo);
+                dacc[j] = lo;
+            }
+        } else if (kind == 26) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                acc[j] = (unsigned long long)(uint32_t)acc[j] * b + acc[j];
+                asm volatile("fma.rz.f64 %0, %0, %1, %2;" : "+d"(dacc[j]) : "d"(db), "d"(da));
+            }
+        } else if (kind == 29) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += acc[(j + 1) & 7] | 1ull;
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += acc[j] + (unsigned long long)__double_as_longlong(dacc[j]);
+#pragma unroll
+    for (int j = 0; j < 16; j++) s += r[j];
+    if (iters == 0x7fffffff) io[tid & 1023] = (uint32_t)s ^ (uint32_t)(s >> 32);  // never true; keeps the chains live
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -203,6 +298,16 @@ extern "C" int sb_microbench(int which, int iters, int blocks, int threads, doub
             case 10: k_mb_double_call<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 11: k_mb_inv<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
             case 12: k_mb_inv_safegcd<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
+            case 20: k_mb_pipe<20><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 21: k_mb_pipe<21><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 22: k_mb_pipe<22><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 23: k_mb_pipe<23><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 24: k_mb_pipe<24><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 25: k_mb_pipe<25><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 26: k_mb_pipe<26><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 27: k_mb_pipe<27><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 28: k_mb_pipe<28><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
+            case 29: k_mb_pipe<29><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
             default: cudaFree(d); set_error("sb_microbench: unknown test %d", which); return SB_ERR_ARG;
         }
         cudaEventRecord(e1, rt.stream);
