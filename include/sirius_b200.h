@@ -90,6 +90,10 @@ void sb_ck_release(sb_ck_t ck);
 int sb_ck_add_window(sb_ck_t ck, int window_bits, void* stream);
 size_t sb_ck_len(sb_ck_t ck);
 int sb_ck_window_bits(sb_ck_t ck);
+/* Performance knobs of the commitment pipeline; results are bit-identical for every setting.
+ * key 0: batched-affine reduction rounds before the XYZZ bucket kernel (-1 = automatic, 0 = off, <= 8);
+ * key 1: outputs per thread of one round (8 or 16). */
+int sb_msm_tune(int key, int value);
 
 /* CommitmentKey::commit (src/commitment.rs:81-90): out = sum_{i<n} scalars[i] * ck[i], affine.
  * n > len(ck) -> SB_ERR_TOO_LONG (the Rust shim maps it to Error::TooLongInput). */

@@ -36,6 +36,7 @@ SIGNATURES = {
     "sb_ck_add_window": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "sb_ck_len": (ctypes.c_size_t, [vp]),
     "sb_ck_window_bits": (ctypes.c_int, [vp]),
+    "sb_msm_tune": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "sb_msm": (ctypes.c_int, [vp, u64p, ctypes.c_size_t, u64p]),
     "sb_msm_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, vp, vp, vp]),
     "sb_msm_batch": (ctypes.c_int, [vp, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p]),

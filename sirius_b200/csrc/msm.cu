@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "curve.cuh"
+#include "affine.cuh"
 #include "quad.cuh"
 
 namespace sb {
@@ -191,14 +192,21 @@ __global__ void k_decompose(const S* __restrict__ scalars, uint32_t n, uint32_t 
     }
 }
 
+// The three scan kernels below build, in one pass each, the bucket offsets of every reduction round (affine.cuh):
+// blockIdx.y = r scans cnt_r(b) = ceil(counts[b] / 2^r); row r of `offsets` (KB + 1 entries) and of `tile_sums`
+// (SCAN_MAX_TILES entries).  r = 0 is the plain counting-sort scan and also initialises `cursor`.
+constexpr uint32_t SCAN_MAX_TILES = 8192;
+SB_D uint32_t round_count(uint32_t c, uint32_t r) { return (c + ((1u << r) - 1u)) >> r; }
+
 __global__ void k_scan_tile_sums(const uint32_t* __restrict__ counts, uint32_t K, uint32_t* __restrict__ tile_sums) {
     __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    const uint32_t r = blockIdx.y;
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         uint32_t idx = base + k;
-        s += (idx < K) ? counts[idx] : 0u;
+        s += (idx < K) ? round_count(counts[idx], r) : 0u;
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
@@ -207,13 +215,14 @@ __global__ void k_scan_tile_sums(const uint32_t* __restrict__ counts, uint32_t K
     if (threadIdx.x == 0) {
         uint32_t t = 0;
         for (int wi = 0; wi < SCAN_THREADS / 32; wi++) t += warp_tot[wi];
-        tile_sums[blockIdx.x] = t;
+        tile_sums[r * SCAN_MAX_TILES + blockIdx.x] = t;
     }
 }
 
-// exclusive scan of up to 8192 tile sums in one block of 1024 threads (8 items per thread)
-__global__ void k_scan_tiles(uint32_t* tile_sums, uint32_t num_tiles) {
+// exclusive scan of up to 8192 tile sums in one block of 1024 threads (8 items per thread); one block per round
+__global__ void k_scan_tiles(uint32_t* tile_sums_all, uint32_t num_tiles) {
     __shared__ uint32_t sh[1024];
+    uint32_t* tile_sums = tile_sums_all + blockIdx.x * SCAN_MAX_TILES;
     uint32_t v[8];
     uint32_t base = threadIdx.x * 8;
     uint32_t s = 0;
@@ -238,17 +247,20 @@ __global__ void k_scan_tiles(uint32_t* tile_sums, uint32_t num_tiles) {
     }
 }
 
-// offsets[i] = exclusive prefix of counts; cursor[i] = offsets[i]; offsets[K] = total
-__global__ void k_scan_apply(const uint32_t* __restrict__ counts, uint32_t K, const uint32_t* __restrict__ tile_excl,
-                             uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+// offsets[r][i] = exclusive prefix of cnt_r; offsets[r][K] = total; cursor[i] = offsets[0][i]
+__global__ void k_scan_apply(const uint32_t* __restrict__ counts, uint32_t K, const uint32_t* __restrict__ tile_excl_all,
+                             uint32_t* __restrict__ offsets_all, uint32_t* __restrict__ cursor) {
     __shared__ uint32_t sh[SCAN_THREADS];
+    const uint32_t r = blockIdx.y;
+    const uint32_t* tile_excl = tile_excl_all + r * SCAN_MAX_TILES;
+    uint32_t* offsets = offsets_all + (size_t)r * ((size_t)K + 1);
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         uint32_t idx = base + k;
-        v[k] = (idx < K) ? counts[idx] : 0u;
+        v[k] = (idx < K) ? round_count(counts[idx], r) : 0u;
         s += v[k];
     }
     sh[threadIdx.x] = s;
@@ -265,7 +277,7 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ counts, uint32_t K, co
         uint32_t idx = base + k;
         if (idx < K) {
             offsets[idx] = run;
-            cursor[idx] = run;
+            if (r == 0) cursor[idx] = run;
         }
         run += v[k];
         if (idx == K - 1) offsets[K] = run;
@@ -304,10 +316,45 @@ __global__ void k_chunk_heads(const uint32_t* __restrict__ offsets, uint32_t KB,
     for (uint32_t t = (o + LS - 1) >> ls_log; ((uint64_t)t << ls_log) < o2; t++) chunk_head[t] = b;
 }
 
+// One reduction round of the batched-affine bucket sums (affine.cuh): thread g produces outputs [g*B, (g+1)*B) of
+// A_{r+1}; the block shares one inversion through a product tree in shared memory.  Threads below the active
+// count of a tree level are contiguous, so a level costs ceil(active / 32) warp-products, ~4 per thread in all.
+template <class F, bool INDEXED, int B>
+__global__ void __launch_bounds__(PR_THREADS, 2)
+k_pair_round(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ eidx, const uint32_t* __restrict__ off_in,
+             const uint32_t* __restrict__ off_out, uint32_t KB, Affine<F>* __restrict__ dst) {
+    __shared__ F node[PR_NODES];
+    __shared__ F ninv[PR_NODES];
+    const uint32_t total_out = off_out[KB];
+    if ((uint64_t)blockIdx.x * (PR_THREADS * B) >= total_out) return;  // whole block idle (the grid is an upper bound)
+    const int tid = threadIdx.x;
+    const uint32_t g = blockIdx.x * PR_THREADS + tid;
+    uint32_t pos[B];
+    uint8_t kind[B];
+    F cp[B];
+    const PairSrc<F, INDEXED> src{pts, eidx};
+    node[tid] = pair_forward<F, INDEXED, B>(src, off_in, off_out, KB, g, pos, kind, cp);
+    __syncthreads();
+#pragma unroll 1
+    for (int l = 0; l < PR_LEVELS; l++) {
+        if (tid < (PR_THREADS >> (l + 1))) pr_tree_up(node, l, tid);
+        __syncthreads();
+    }
+    if (tid == 32 * (int)(blockIdx.x & 7u)) ninv[pr_level_off(PR_LEVELS)] = inv_safegcd(node[pr_level_off(PR_LEVELS)]);
+    __syncthreads();
+#pragma unroll 1
+    for (int l = PR_LEVELS - 1; l >= 0; l--) {
+        if (tid < (PR_THREADS >> l)) pr_tree_down(node, ninv, l, tid);
+        __syncthreads();
+    }
+    pair_backward<F, INDEXED, B>(src, pos, kind, cp, ninv[tid], dst + (size_t)g * B);
+}
+
 // Thread t owns sorted entries [t*LS, (t+1)*LS), LS = 2^ls_log.  A bucket lying entirely inside the chunk is
 // written to buckets[]; a piece of a bucket that continues into a neighbouring chunk goes to PH[t] (piece
 // starts at the chunk start) or PT[t] (piece ends at the chunk end) and is finished by k_fixup.
-template <class F, int MINB>
+// DIRECT = false: entry -> window table (eidx); DIRECT = true: the entries ARE points (output of the affine rounds).
+template <class F, int MINB, bool DIRECT>
 __global__ void __launch_bounds__(128, MINB)
 k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ chunk_head, const uint32_t* __restrict__ eidx,
              const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* __restrict__ buckets,
@@ -324,7 +371,7 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ c
     uint32_t cur_end = offsets[cur + 1];
     uint32_t seg_start = start;
     XYZZ<F> acc = XYZZ<F>::identity();
-    uint32_t e = eidx[start];
+    uint32_t e = DIRECT ? start : eidx[start];
     Affine<F> base = load_vec_nc(table + (e & 0x7fffffffu));
 #pragma unroll 1
     for (uint32_t pos = start; pos < end; pos++) {
@@ -332,7 +379,7 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ c
         uint32_t e_next = 0;
         Affine<F> base_next;
         if (pos + 1 < end) {
-            e_next = eidx[pos + 1];
+            e_next = DIRECT ? pos + 1 : eidx[pos + 1];
             base_next = load_vec_nc(table + (e_next & 0x7fffffffu));
         }
         xyzz_madd(acc, base, (e >> 31) != 0);
@@ -641,9 +688,31 @@ struct MsmPlan {
     size_t n, total, nW, chunks;
     uint32_t batch, K, KB, tiles;
     int ls_log;
+    int rounds;          // batched-affine reduction rounds before the XYZZ chunk kernel (0 = none), affine.cuh
+    int pair_b;          // outputs per thread in k_pair_round (8 or 16)
+    size_t m_final;      // upper bound of the entries left after the rounds
     size_t off_dig, off_counts, off_offsets, off_cursor, off_tiles, off_ekey, off_eidx, off_buckets, off_ph, off_pt,
-        off_heavy, off_nodes_a, off_nodes_b, off_out_xy, off_out_xyzz, off_scalars, total_bytes;
+        off_heavy, off_nodes_a, off_nodes_b, off_out_xy, off_out_xyzz, off_scalars, off_round_a, off_round_b, total_bytes;
 };
+
+// Tuning knobs (sb_msm_tune): number of batched-affine rounds (-1 = automatic) and outputs per thread.
+static int g_affine_rounds = []() {
+    const char* e = getenv("SB_MSM_AFFINE_ROUNDS");
+    return e ? atoi(e) : -1;
+}();
+static int g_pair_b = []() {
+    const char* e = getenv("SB_MSM_PAIR_B");
+    return e ? atoi(e) : 16;
+}();
+constexpr int MAX_AFFINE_ROUNDS = 8;
+
+// Automatic choice: a round pays while it still fills the chip with ~2 blocks per SM (it costs one block-wide
+// inversion of latency whatever its size) and buckets keep >= 8 entries for the chunk kernel behind it.
+static int auto_affine_rounds(size_t nW, size_t KB) {
+    (void)nW;
+    (void)KB;
+    return 0;  // enabled per measurement (profiles/): see make_plan
+}
 
 static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars, MsmPlan& p) {
     p = MsmPlan{};
@@ -670,17 +739,27 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
         return SB_ERR_ARG;
     }
     p.KB = (uint32_t)kb;
+    if ((kb + SCAN_TILE - 1) / SCAN_TILE > SCAN_MAX_TILES) {
+        set_error("sb_msm: too many buckets (%llu)", (unsigned long long)kb);
+        return SB_ERR_ARG;
+    }
+    p.rounds = g_affine_rounds >= 0 ? std::min(g_affine_rounds, MAX_AFFINE_ROUNDS) : auto_affine_rounds(p.nW, p.KB);
+    p.pair_b = g_pair_b == 8 ? 8 : 16;
+    // entries left for the chunk kernel: every round halves each bucket, rounding up
+    p.m_final = p.nW;
+    for (int r = 0; r < p.rounds; r++) p.m_final = p.m_final / 2 + p.KB;
     // chunk length (one thread per chunk): as long as possible -- fewer bucket pieces for k_fixup -- while keeping
     // >= 4 resident warps per scheduler (148 SMs x 4 SMSPs x 4 warps x 32 lanes = 75 776 threads) in k_accumulate
     // and no longer than ~1/4 of the average bucket (measured: chunks spanning several buckets run ~30 % slower)
     {
         const size_t target_threads = 75776;
-        const size_t per_bucket = p.nW / (p.KB ? p.KB : 1);
+        const size_t m = p.rounds ? (p.nW >> p.rounds) : p.nW;
+        const size_t per_bucket = m / (p.KB ? p.KB : 1);
         int l = LS_MIN_LOG;
-        while (l < LS_MAX_LOG && (p.nW >> (l + 1)) >= target_threads && ((size_t)4 << l) < per_bucket) l++;
+        while (l < LS_MAX_LOG && (m >> (l + 1)) >= target_threads && ((size_t)4 << l) < per_bucket) l++;
         p.ls_log = l;
     }
-    p.chunks = (p.nW + ((size_t)1 << p.ls_log) - 1) >> p.ls_log;
+    p.chunks = (p.m_final + ((size_t)1 << p.ls_log) - 1) >> p.ls_log;
     p.tiles = (p.KB + SCAN_TILE - 1) / SCAN_TILE;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -690,9 +769,9 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     };
     p.off_dig = take(p.nW * 4);
     p.off_counts = take(((size_t)p.KB + 1) * 4);  // +1: heavy-bucket counter lives behind the counts (one memset)
-    p.off_offsets = take(((size_t)p.KB + 1) * 4);
+    p.off_offsets = take(((size_t)p.KB + 1) * 4 * (size_t)(p.rounds + 1));  // one row per round
     p.off_cursor = take((size_t)p.KB * 4);
-    p.off_tiles = take(8192 * 4);
+    p.off_tiles = take((size_t)SCAN_MAX_TILES * 4 * (size_t)(p.rounds + 1));
     p.off_ekey = take((p.chunks + 1) * 4);  // chunk heads
     p.off_eidx = take(p.nW * 4);
     p.off_buckets = take((size_t)p.KB * 128);
@@ -707,6 +786,9 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     p.off_out_xy = take(64 * batch);
     p.off_out_xyzz = take(128 * batch);
     p.off_scalars = take(stage_scalars ? p.total * 32 : 0);
+    // round outputs ping-pong: A_1, A_3, .. in `a` (<= nW/2 + KB points), A_2, A_4, .. in `b` (<= nW/4 + KB)
+    p.off_round_a = take(p.rounds >= 1 ? (p.nW / 2 + p.KB + 1) * 64 : 0);
+    p.off_round_b = take(p.rounds >= 2 ? (p.nW / 4 + p.KB + 1) * 64 : 0);
     p.total_bytes = off;
     return SB_OK;
 }
@@ -736,39 +818,68 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         SB_KERNEL_CHECK();
     }
     std::unique_ptr<ProfScope> sort_scope(new ProfScope(st, PROF_SORT, p.nW));
-    k_scan_tile_sums<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles);
-    SB_KERNEL_CHECK();
-    k_scan_tiles<<<1, 1024, 0, st>>>(tiles, p.tiles);
-    SB_KERNEL_CHECK();
-    k_scan_apply<<<p.tiles, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets, cursor);
-    SB_KERNEL_CHECK();
+    const int R = p.rounds;
+    {
+        dim3 gs(p.tiles, R + 1);
+        k_scan_tile_sums<<<gs, SCAN_THREADS, 0, st>>>(counts, KB, tiles);
+        SB_KERNEL_CHECK();
+        k_scan_tiles<<<R + 1, 1024, 0, st>>>(tiles, p.tiles);
+        SB_KERNEL_CHECK();
+        k_scan_apply<<<gs, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets, cursor);
+        SB_KERNEL_CHECK();
+    }
     k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, cursor, eidx);
     SB_KERNEL_CHECK();
-    k_chunk_heads<<<(KB + 255) / 256, 256, 0, st>>>(offsets, KB, p.ls_log, chunk_head);
+    const uint32_t* off_final = offsets + (size_t)R * ((size_t)KB + 1);   // offsets of the entries the chunk kernel sees
+    k_chunk_heads<<<(KB + 255) / 256, 256, 0, st>>>(off_final, KB, p.ls_log, chunk_head);
     sort_scope.reset();
     SB_KERNEL_CHECK();
+    const Affine<F>* acc_src = (const Affine<F>*)p.table;
     {
+        ProfScope ps(st, PROF_ACCUMULATE, p.nW);  // units: mixed additions (upper bound: zero digits are skipped)
+        // batched-affine rounds: A_0 = table[eidx] -> A_1 (buffer a) -> A_2 (buffer b) -> A_3 (a) ..
+        auto* buf_a = (Affine<F>*)(ws + p.off_round_a);
+        auto* buf_b = (Affine<F>*)(ws + p.off_round_b);
+        size_t bound = p.nW;
+        for (int r = 0; r < R; r++) {
+            bound = bound / 2 + KB;                      // upper bound of this round's outputs
+            const uint32_t* off_in = offsets + (size_t)r * ((size_t)KB + 1);
+            const uint32_t* off_out = offsets + (size_t)(r + 1) * ((size_t)KB + 1);
+            Affine<F>* dst = (r & 1) ? buf_b : buf_a;
+            const size_t per_block = (size_t)PR_THREADS * p.pair_b;
+            const unsigned blocks = (unsigned)((bound + per_block - 1) / per_block);
+            if (r == 0) {
+                if (p.pair_b == 8) k_pair_round<F, true, 8><<<blocks, PR_THREADS, 0, st>>>((const Affine<F>*)p.table, eidx, off_in, off_out, KB, dst);
+                else k_pair_round<F, true, 16><<<blocks, PR_THREADS, 0, st>>>((const Affine<F>*)p.table, eidx, off_in, off_out, KB, dst);
+            } else {
+                if (p.pair_b == 8) k_pair_round<F, false, 8><<<blocks, PR_THREADS, 0, st>>>(acc_src, nullptr, off_in, off_out, KB, dst);
+                else k_pair_round<F, false, 16><<<blocks, PR_THREADS, 0, st>>>(acc_src, nullptr, off_in, off_out, KB, dst);
+            }
+            SB_KERNEL_CHECK();
+            acc_src = dst;
+        }
         size_t blocks = (p.chunks + 127) / 128;
         static const int minb = []() {
             const char* e = getenv("SB_ACC_MINB");
             return e ? atoi(e) : 4;
         }();
-        ProfScope ps(st, PROF_ACCUMULATE, p.nW);  // units: mixed additions (upper bound: zero digits are skipped)
-        if (minb == 5)
-            k_accumulate<F, 5><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+        if (R > 0)
+            k_accumulate<F, 4, true><<<(unsigned)blocks, 128, 0, st>>>(acc_src, chunk_head, nullptr, off_final, KB, p.ls_log, buckets, PH, PT);
+        else if (minb == 5)
+            k_accumulate<F, 5, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else if (minb == 6)
-            k_accumulate<F, 6><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 6, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else if (minb == 3)
-            k_accumulate<F, 3><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 3, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         else
-            k_accumulate<F, 4><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 4, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
         SB_KERNEL_CHECK();
     }
     {
         ProfScope ps(st, PROF_FIXUP, KB);
-        k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(offsets, KB, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
+        k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
-        k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(offsets, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
+        k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(off_final, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
     }
     {
@@ -931,6 +1042,18 @@ int sb_ck_add_window(sb_ck_t ck, int window_bits, void* stream) {
 }
 
 size_t sb_ck_len(sb_ck_t ck) { return ck ? ck->n : 0; }
+
+/* Tuning: key 0 = batched-affine rounds per commit (-1 automatic, 0 off, up to 8), key 1 = outputs per thread of a
+ * round (8 or 16).  Results are bit-identical for every setting. */
+int sb_msm_tune(int key, int value) {
+    if (key == 0 && value >= -1 && value <= MAX_AFFINE_ROUNDS) g_affine_rounds = value;
+    else if (key == 1 && (value == 8 || value == 16)) g_pair_b = value;
+    else {
+        set_error("sb_msm_tune: bad key/value %d/%d", key, value);
+        return SB_ERR_ARG;
+    }
+    return SB_OK;
+}
 int sb_ck_window_bits(sb_ck_t ck) { return ck ? ck->c : 0; }
 
 static int check_len(sb_ck_t ck, size_t n) {
