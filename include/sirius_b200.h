@@ -271,6 +271,9 @@ int sb_microbench(int which, int iters, int blocks, int threads, double* out_ms)
 /* ---- self test hooks used by tests/ (device arithmetic vs its portable twin) ----------------------- */
 int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul_ptx,
                       uint64_t* out_mul_portable, uint64_t* out_add, uint64_t* out_sub, uint64_t* out_inv);
+/* lazy-domain twins (operands anywhere in [0, 2p), raw results; out_canon = a mod p with bit 255 set where a = 0 mod p) */
+int sb_selftest_lazy(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul, uint64_t* out_sub,
+                     uint64_t* out_dbl, uint64_t* out_canon);
 
 #ifdef __cplusplus
 }

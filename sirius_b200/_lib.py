@@ -90,6 +90,7 @@ SIGNATURES = {
     "sb_profile_enable": (None, [ctypes.c_int]),
     "sb_profile_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "sb_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "sb_selftest_lazy": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]),
     "sb_selftest_field": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p, u64p]),
 }
 

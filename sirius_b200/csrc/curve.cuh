@@ -149,6 +149,44 @@ SB_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q, bool negate) {
     acc.zzz = mul(acc.zzz, ppp);
 }
 
+// acc += (negate ? -q : q) with the accumulator's coordinates kept in the LAZY domain [0, 2p) (field.cuh): the ten
+// products skip their final conditional subtraction.  q is canonical (a table entry); the identity is still
+// zz == 0 exactly (a non-zero residue is never stored as 0).  canon_point() brings the accumulator back to [0, p)
+// before it leaves the loop.
+template <class F>
+SB_HD void xyzz_madd_lazy(XYZZ<F>& acc, const Affine<F>& q, bool negate) {
+    if (q.is_identity()) return;
+    F qy = negate ? neg(q.y) : q.y;
+    if (acc.is_identity()) {
+        acc.x = q.x; acc.y = qy; acc.zz = F::one(); acc.zzz = F::one();
+        return;
+    }
+    F u2 = mul_lazy(q.x, acc.zz);
+    F s2 = mul_lazy(qy, acc.zzz);
+    F p = sub_lazy(u2, acc.x);
+    F r = sub_lazy(s2, acc.y);
+    if (is_zero_lazy(p)) {
+        if (is_zero_lazy(r)) acc = xyzz_double_affine(q.x, qy);
+        else acc = XYZZ<F>::identity();
+        return;
+    }
+    F pp = mul_lazy(p, p);
+    F ppp = mul_lazy(p, pp);
+    F qq = mul_lazy(acc.x, pp);
+    F x3 = sub_lazy(sub_lazy(mul_lazy(r, r), ppp), dbl_lazy(qq));
+    F y3 = sub_lazy(mul_lazy(r, sub_lazy(qq, x3)), mul_lazy(acc.y, ppp));
+    acc.x = x3;
+    acc.y = y3;
+    acc.zz = mul_lazy(acc.zz, pp);
+    acc.zzz = mul_lazy(acc.zzz, ppp);
+}
+template <class F>
+SB_HD XYZZ<F> canon_point(const XYZZ<F>& a) {
+    XYZZ<F> r;
+    r.x = canon(a.x); r.y = canon(a.y); r.zz = canon(a.zz); r.zzz = canon(a.zzz);
+    return r;
+}
+
 // acc += q, both XYZZ.
 template <bool INL = true, class F>
 SB_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {

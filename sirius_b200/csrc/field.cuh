@@ -167,8 +167,9 @@ SB_HD Fe<P> sub_portable(const Fe<P>& a, const Fe<P>& b) {
     return r;
 }
 
-// CIOS Montgomery product with 32-bit limbs and 64-bit accumulators.
-template <class P>
+// CIOS Montgomery product with 32-bit limbs and 64-bit accumulators.  REDUCE = false is the lazy form (see the
+// "lazy domain" section below): inputs in [0, 2p), result in [0, 2p), no final subtraction.
+template <class P, bool REDUCE = true>
 SB_HD Fe<P> mul_portable(const Fe<P>& a, const Fe<P>& b) {
     uint32_t t[10];
 #pragma unroll
@@ -201,7 +202,7 @@ SB_HD Fe<P> mul_portable(const Fe<P>& a, const Fe<P>& b) {
     Fe<P> r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = t[i];
-    reduce_once_portable<P>(r.v);  // result < 2p, t[8] == 0
+    if (REDUCE) reduce_once_portable<P>(r.v);  // result < 2p, t[8] == 0
     return r;
 }
 
@@ -335,7 +336,7 @@ SB_D void fold_shift_chain_odd(uint32_t X[9], uint32_t Y[9], uint32_t x0, uint32
 // the new O, and the stray e[1] is folded into new-E limb 0 whose carry (weight 2^32) enters the new
 // O chain as its carry-in.  Invariant: S < 2p at row boundaries, S < 2^288 inside a row, hence the
 // "no carry out" claims of chain_odd / fold_shift_chain_odd.
-template <class P>
+template <class P, bool REDUCE = true>
 SB_D Fe<P> mul_ptx(const Fe<P>& a, const Fe<P>& b) {
     uint32_t A[9], B[9];
     const uint32_t b0 = b.v[0];
@@ -399,7 +400,7 @@ SB_D Fe<P> mul_ptx(const Fe<P>& a, const Fe<P>& b) {
         : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
         : "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]), "r"(B[8]),
           "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]));
-    reduce_once_ptx<P>(r.v);
+    if (REDUCE) reduce_once_ptx<P>(r.v);
     return r;
 }
 #endif  // __CUDA_ARCH__
@@ -447,6 +448,168 @@ SB_HD Fe<P> from_mont(const Fe<P>& a) {
 }
 template <class P>
 SB_HD Fe<P> to_mont(const Fe<P>& a) { return mul(a, Fe<P>::r_squared()); }
+
+// ---------------------------------------------------------------------------------------------
+// lazy domain: values kept in [0, 2p) inside a hot loop, canonicalised only when they leave it
+// ---------------------------------------------------------------------------------------------
+// p < 2^254, so 4p < 2^256 = R.  The Montgomery product t = (a*b + m*p)/R of a, b < 2p satisfies
+// t < 4p^2/R + p < 2p (4p/R = 0.756 for both bn256 fields) WITHOUT the final conditional subtraction, and inside
+// the CIOS rows the running sum stays below 3p(1 + 2^-32) < 2^256, so the carry-chain invariants of mul_ptx hold
+// unchanged.  That saves the 17-instruction compare-and-select tail of every product of the bucket kernel.
+// add/sub/double stay closed on [0, 2p) with one conditional correction by 2p; zero is 0 or p.
+template <class P>
+struct TwoP {  // limbs of 2p
+    static SB_HD uint32_t limb(int i) {
+        const uint32_t lo = i ? Fe<P>::modulus_limb(i - 1) >> 31 : 0u;
+        return (Fe<P>::modulus_limb(i) << 1) | lo;
+    }
+};
+
+template <class P>
+SB_HD Fe<P> sub_lazy_portable(const Fe<P>& a, const Fe<P>& b) {  // a - b, + 2p if negative
+    Fe<P> r;
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a.v[i] - b.v[i] - br;
+        r.v[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    if (br) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            c += (uint64_t)r.v[i] + TwoP<P>::limb(i);
+            r.v[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    return r;
+}
+template <class P>
+SB_HD Fe<P> dbl_lazy_portable(const Fe<P>& a) {  // 2a, - 2p if >= 2p   (2a < 4p < 2^256)
+    Fe<P> r, t;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a.v[i] + a.v[i];
+        r.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)r.v[i] - TwoP<P>::limb(i) - br;
+        t.v[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    return br ? r : t;
+}
+
+#if defined(__CUDA_ARCH__)
+template <class P>
+SB_D Fe<P> sub_lazy_ptx(const Fe<P>& a, const Fe<P>& b) {
+    Fe<P> r;
+    uint32_t br;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]), "=r"(br)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7])
+        : "r"(TwoP<P>::limb(0) & br), "r"(TwoP<P>::limb(1) & br), "r"(TwoP<P>::limb(2) & br), "r"(TwoP<P>::limb(3) & br),
+          "r"(TwoP<P>::limb(4) & br), "r"(TwoP<P>::limb(5) & br), "r"(TwoP<P>::limb(6) & br), "r"(TwoP<P>::limb(7) & br));
+    return r;
+}
+template <class P>
+SB_D Fe<P> dbl_lazy_ptx(const Fe<P>& a) {
+    uint32_t s[8], t[8], br;
+    asm("add.cc.u32 %0, %8, %8;\n\t"
+        "addc.cc.u32 %1, %9, %9;\n\t"
+        "addc.cc.u32 %2, %10, %10;\n\t"
+        "addc.cc.u32 %3, %11, %11;\n\t"
+        "addc.cc.u32 %4, %12, %12;\n\t"
+        "addc.cc.u32 %5, %13, %13;\n\t"
+        "addc.cc.u32 %6, %14, %14;\n\t"
+        "addc.u32 %7, %15, %15;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]));
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(br)
+        : "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]),
+          "r"(TwoP<P>::limb(0)), "r"(TwoP<P>::limb(1)), "r"(TwoP<P>::limb(2)), "r"(TwoP<P>::limb(3)),
+          "r"(TwoP<P>::limb(4)), "r"(TwoP<P>::limb(5)), "r"(TwoP<P>::limb(6)), "r"(TwoP<P>::limb(7)));
+    Fe<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = br ? s[i] : t[i];
+    return r;
+}
+#endif
+
+template <class P>
+SB_HD Fe<P> mul_lazy(const Fe<P>& a, const Fe<P>& b) {
+#if defined(__CUDA_ARCH__) && !defined(SB_FORCE_PORTABLE_MUL)
+    return mul_ptx<P, false>(a, b);
+#else
+    return mul_portable<P, false>(a, b);
+#endif
+}
+template <class P>
+SB_HD Fe<P> sub_lazy(const Fe<P>& a, const Fe<P>& b) {
+#if defined(__CUDA_ARCH__)
+    return sub_lazy_ptx(a, b);
+#else
+    return sub_lazy_portable(a, b);
+#endif
+}
+template <class P>
+SB_HD Fe<P> dbl_lazy(const Fe<P>& a) {
+#if defined(__CUDA_ARCH__)
+    return dbl_lazy_ptx(a);
+#else
+    return dbl_lazy_portable(a);
+#endif
+}
+template <class P>
+SB_HD bool is_zero_lazy(const Fe<P>& a) {  // a = 0 (mod p) for a in [0, 2p): a == 0 or a == p; the low limb filters
+    if (a.v[0] != 0u && a.v[0] != P::P0) return false;
+    uint32_t z = 0, q = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        z |= a.v[i];
+        q |= a.v[i] ^ Fe<P>::modulus_limb(i);
+    }
+    return z == 0 || q == 0;
+}
+template <class P>
+SB_HD Fe<P> canon(const Fe<P>& a) {  // [0, 2p) -> [0, p)
+    Fe<P> r = a;
+    reduce_once_portable<P>(r.v);
+    return r;
+}
 
 // ---- plain-integer helpers for the binary inversion --------------------------------------------------
 SB_HD bool limbs_geq(const uint32_t a[8], const uint32_t b[8]) {

@@ -9,7 +9,7 @@
 //            bucket sums: fixed-size chunks of the sorted entries, one chunk per thread, mixed XYZZ adds
 //                         (skew-proof: a bucket of any size is split across as many threads as it needs)
 //                                                                                k_accumulate, k_fixup
-//            sum_b (b+1) * B_b: row/column sums, octal digit sums, quad-lane tail  k_rowcol_sums / k_weighted_digits / k_reduce_final
+//            sum_b (b+1) * B_b: row/column sums, octal digit sums, quad-lane tail  k_rowcol_sums / k_digit_sums / k_weighted_finish / k_reduce_final
 //            XYZZ -> affine                                                      k_finalize
 //
 // Because every window's base multiple is precomputed, all W windows share ONE set of 2^(c-1) buckets and
@@ -382,10 +382,11 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ c
             e_next = DIRECT ? pos + 1 : eidx[pos + 1];
             base_next = load_vec_nc(table + (e_next & 0x7fffffffu));
         }
-        xyzz_madd(acc, base, (e >> 31) != 0);
+        xyzz_madd_lazy(acc, base, (e >> 31) != 0);   // coordinates stay in [0, 2p) inside the run (field.cuh, lazy domain)
         if (pos + 1 == end || pos + 1 == cur_end) {
             const uint32_t seg_end = pos + 1;
             const uint32_t o = offsets[cur];
+            acc = canon_point(acc);
             if (o == seg_start && cur_end == seg_end) store_vec(buckets + cur, acc);
             else if (seg_start == start) store_vec(PH + t, acc);
             else store_vec(PT + t, acc);
@@ -474,7 +475,7 @@ k_fixup_heavy(const uint32_t* __restrict__ offsets, int ls_log, XYZZ<F>* __restr
 //     sum_b (b+1) B_b = C * sum_r r * Row_r  +  sum_q (q+1) * Col_q,      Row_r = sum_q B_{r,q},  Col_q = sum_r B_{r,q}.
 // Stage 1 (k_rowcol_sums) does the 2K plain additions with ordinary lanes (it is throughput-bound for batched
 // commits): one warp per row / per column, a short serial run per lane and a 5-step shuffle tree.
-// Stage 2 (k_weighted_digits) reduces a short vector E_0..E_{n-1} with weights (j + w0) by octal digit sums:
+// Stage 2 (k_digit_sums, k_weighted_finish) reduces a short vector E_0..E_{n-1} with weights (j + w0) by octal digit sums:
 //     sum_j j * E_j = sum_i 8^i sum_{v=1..7} v * D[i][v],   D[i][v] = sum_{j: digit_i(j) = v} E_j   (plain sums, one warp each)
 // and finishes with quad-lane additions (quad.cuh): 7-term weighted sums, Horner over the digit positions.
 // Stage 3 (k_reduce_final) adds the two parts and normalises to affine.
@@ -524,83 +525,88 @@ k_rowcol_sums(const XYZZ<F>* __restrict__ buckets_all, int log_k, int lc, XYZZ<F
     if (lane == 0) store_vec(vec_all + (size_t)blockIdx.y * (R + C) + w, acc);
 }
 
-// grid (2, batch): blockIdx.x = 0 -> X = sum_r r * Row_r (weights from 0), 1 -> Y = sum_q (q+1) * Col_q.
-// 24 warps: warp (pos, v) sums the entries whose octal digit `pos` equals v; then warps 0..2 do the 7-term
-// weighted sums and warp 0 the Horner step, all with quad-lane additions.
-constexpr int WD_THREADS = 768;
+// Octal digit sums, one warp (= one block, so every warp gets a scheduler of its own: the sums are a latency chain)
+// per (part, digit position, digit value): D[batch][part][pos][v] = sum of the entries E_j whose octal digit `pos`
+// of j equals v.  part 0 = the row sums (n = R entries), part 1 = the column sums (n = C entries).
 template <class F>
-__global__ void __launch_bounds__(WD_THREADS)
-k_weighted_digits(const XYZZ<F>* __restrict__ vec_all, int log_k, int lc, XYZZ<F>* __restrict__ xy_all) {
-    __shared__ XYZZ<F> D[3][8];
-    __shared__ XYZZ<F> Xp[3];
-    __shared__ XYZZ<F> S0;
+__global__ void __launch_bounds__(32)
+k_digit_sums(const XYZZ<F>* __restrict__ vec_all, int log_k, int lc, int max_pos, XYZZ<F>* __restrict__ D_all) {
     const uint32_t K = 1u << log_k, C = 1u << lc, R = K >> lc;
-    const int which = blockIdx.x;
+    const int which = blockIdx.x / (max_pos * 8);
+    const int rem = blockIdx.x - which * (max_pos * 8);
+    const int pos = rem >> 3, v = rem & 7;
     const uint32_t n = which == 0 ? R : C;
     const int log_n = which == 0 ? (log_k - lc) : lc;
     const XYZZ<F>* E = vec_all + (size_t)blockIdx.y * (R + C) + (which == 0 ? 0 : R);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int npos = (log_n + 2) / 3 > 0 ? (log_n + 2) / 3 : 1;   // <= 3 for n <= 512 (K <= 2^18); larger n: see loop
-    // digit sums (scalar lanes).  For npos > 3 (very wide windows) the warps loop over the extra positions.
-    XYZZ<F> horner = XYZZ<F>::identity();
-    for (int pos_base = ((npos - 1) / 3) * 3; pos_base >= 0; pos_base -= 3) {
-        const int pos = pos_base + warp / 8, v = warp & 7;
-        XYZZ<F> acc = XYZZ<F>::identity();
-        if (pos < npos) {
-            const int bits = (log_n - 3 * pos) < 3 ? (log_n - 3 * pos) : 3;
-            if (v < (1 << bits)) {
-                const uint32_t cnt = n >> bits;
-                const uint32_t low_mask = (1u << (3 * pos)) - 1;
+    const int lane = threadIdx.x;
+    const int npos = (log_n + 2) / 3 > 0 ? (log_n + 2) / 3 : 1;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (pos < npos) {
+        const int bits = (log_n - 3 * pos) < 3 ? (log_n - 3 * pos) : 3;
+        if (v < (1 << bits)) {
+            const uint32_t cnt = n >> bits;
+            const uint32_t low_mask = (1u << (3 * pos)) - 1;
 #pragma unroll 1
-                for (uint32_t j = lane; j < cnt; j += 32) {
-                    const uint32_t idx = ((j >> (3 * pos)) << (3 * pos + bits)) | ((uint32_t)v << (3 * pos)) | (j & low_mask);
-                    XYZZ<F> x = load_vec(E + idx);
-                    xyzz_add_call(acc, x);
-                }
+            for (uint32_t j = lane; j < cnt; j += 32) {
+                const uint32_t idx = ((j >> (3 * pos)) << (3 * pos + bits)) | ((uint32_t)v << (3 * pos)) | (j & low_mask);
+                XYZZ<F> x = load_vec(E + idx);
+                xyzz_add_call(acc, x);
             }
         }
-        acc = warp_sum_call(acc);
-        if (lane == 0) D[warp / 8][v] = acc;
-        __syncthreads();
-        if (warp < 3) {  // position pos_base + warp: sum_v v * D[v] by suffix sums over the 8 groups
-            const int g = lane >> 2;
-            XYZZ<F> d = D[warp][g];
-            if (pos_base == 0 && warp == 0) {
-                XYZZ<F> tot = warp_group_sum(d);
-                if (lane == 0) S0 = tot;
-            }
-            XYZZ<F> suf = d;
-#pragma unroll 1
-            for (int dist = 1; dist < 8; dist <<= 1) {
-                XYZZ<F> t = group_shfl_down(suf, dist);
-                if (g + dist < 8) quad_add(suf, t);
-            }
-            XYZZ<F> term = (g >= 1) ? suf : XYZZ<F>::identity();
-            term = warp_group_sum(term);
-            if (lane == 0) Xp[warp] = term;
-        }
-        __syncthreads();
-        if (warp == 0) {  // horner = 8^3 * horner + 64 * X2 + 8 * X1 + X0   (positions pos_base .. pos_base + 2)
-            for (int i = 2; i >= 0; i--) {
-                quad_double(horner);
-                quad_double(horner);
-                quad_double(horner);
-                if (pos_base + i < npos) {
-                    XYZZ<F> q = Xp[i];
-                    quad_add(horner, q);
-                }
-            }
-        }
-        __syncthreads();
     }
-    if (warp == 0) {
+    acc = warp_sum_call(acc);
+    if (lane == 0) store_vec(D_all + (((size_t)blockIdx.y * 2 + which) * max_pos + pos) * 8 + v, acc);
+}
+
+// grid (2, batch): blockIdx.x = 0 -> X = C * sum_r r * Row_r (weights from 0), 1 -> Y = sum_q (q+1) * Col_q, from
+// the digit sums:  sum_j j * E_j = sum_pos 8^pos * sum_{v=1..7} v * D[pos][v].
+// Warp `pos` (< npos) forms the 7-term weighted sum of its position by suffix sums over the 8 four-lane groups
+// (quad-lane additions); one more warp sums D[0][*] (= sum of all entries, the "+1" of the column weights); then
+// lane 0 of warp 0 runs the Horner chain with single-lane doublings (8.9k cycles each against 10.6k for the
+// quad-lane form, profiles/r1_microbench3.txt).
+template <class F>
+__global__ void __launch_bounds__(32 * 9)
+k_weighted_finish(const XYZZ<F>* __restrict__ D_all, int log_k, int lc, int max_pos, XYZZ<F>* __restrict__ xy_all) {
+    __shared__ XYZZ<F> Xp[8];
+    __shared__ XYZZ<F> S0;
+    const int which = blockIdx.x;
+    const int log_n = which == 0 ? (log_k - lc) : lc;
+    const int npos = (log_n + 2) / 3 > 0 ? (log_n + 2) / 3 : 1;
+    const XYZZ<F>* D = D_all + (((size_t)blockIdx.y * 2 + which) * max_pos) * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2;
+    if (warp < npos) {  // position `warp`: sum_v v * D[v]
+        XYZZ<F> suf = load_vec(D + warp * 8 + g);
+#pragma unroll 1
+        for (int dist = 1; dist < 8; dist <<= 1) {
+            XYZZ<F> t = group_shfl_down(suf, dist);
+            if (g + dist < 8) quad_add(suf, t);
+        }
+        XYZZ<F> term = (g >= 1) ? suf : XYZZ<F>::identity();
+        term = warp_group_sum(term);
+        if (lane == 0) Xp[warp] = term;
+    } else if (warp == max_pos) {  // the extra warp: total of all entries
+        XYZZ<F> d = load_vec(D + g);
+        d = warp_group_sum(d);
+        if (lane == 0) S0 = d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        XYZZ<F> horner = XYZZ<F>::identity();
+        for (int i = npos - 1; i >= 0; i--) {
+            xyzz_double_call(horner);
+            xyzz_double_call(horner);
+            xyzz_double_call(horner);
+            XYZZ<F> q = Xp[i];
+            xyzz_add_call(horner, q);
+        }
         if (which == 1) {  // weights q + 1
             XYZZ<F> s0 = S0;
-            quad_add(horner, s0);
-        } else {           // the row part carries the factor C = 2^lc (done here, beside the column block)
-            for (int k = 0; k < lc; k++) quad_double(horner);
+            xyzz_add_call(horner, s0);
+        } else {           // the row part carries the factor C = 2^lc
+            for (int k = 0; k < lc; k++) xyzz_double_call(horner);
         }
-        if (lane == 0) store_vec(xy_all + (size_t)blockIdx.y * 2 + which, horner);
+        store_vec(xy_all + (size_t)blockIdx.y * 2 + which, horner);
     }
 }
 
@@ -692,7 +698,7 @@ struct MsmPlan {
     int pair_b;          // outputs per thread in k_pair_round (8 or 16)
     size_t m_final;      // upper bound of the entries left after the rounds
     size_t off_dig, off_counts, off_offsets, off_cursor, off_tiles, off_ekey, off_eidx, off_buckets, off_ph, off_pt,
-        off_heavy, off_nodes_a, off_nodes_b, off_out_xy, off_out_xyzz, off_scalars, off_round_a, off_round_b, total_bytes;
+        off_heavy, off_nodes_a, off_nodes_b, off_digits, off_out_xy, off_out_xyzz, off_scalars, off_round_a, off_round_b, total_bytes;
 };
 
 // Tuning knobs (sb_msm_tune): number of batched-affine rounds (-1 = automatic) and outputs per thread.
@@ -782,6 +788,7 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
         const int log_k = p.c - 1, lc = (log_k + 1) / 2;
         p.off_nodes_a = take((((size_t)1 << lc) + ((size_t)p.K >> lc)) * batch * 128);  // row + column sums
         p.off_nodes_b = take((size_t)batch * 2 * 128);                                   // X, Y
+        p.off_digits = take((size_t)batch * 2 * 8 * 8 * 128);                            // octal digit sums
     }
     p.off_out_xy = take(64 * batch);
     p.off_out_xyzz = take(128 * batch);
@@ -893,8 +900,14 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
             dim3 g1((R + C + 3) / 4, p.batch);
             k_rowcol_sums<F><<<g1, 128, 0, st>>>(buckets, log_k, lc, vec);
             SB_KERNEL_CHECK();
+            const int max_log = (log_k - lc) > lc ? (log_k - lc) : lc;
+            const int max_pos = (max_log + 2) / 3 > 0 ? (max_log + 2) / 3 : 1;   // <= 8: log_k <= 24
+            auto* dsum = (XYZZ<F>*)(ws + p.off_digits);   // [batch][2][max_pos][8]
+            dim3 gd(2 * max_pos * 8, p.batch);
+            k_digit_sums<F><<<gd, 32, 0, st>>>(vec, log_k, lc, max_pos, dsum);
+            SB_KERNEL_CHECK();
             dim3 g2(2, p.batch);
-            k_weighted_digits<F><<<g2, WD_THREADS, 0, st>>>(vec, log_k, lc, xy);
+            k_weighted_finish<F><<<g2, 32 * (max_pos + 1), 0, st>>>(dsum, log_k, lc, max_pos, xy);
             SB_KERNEL_CHECK();
         }
         {

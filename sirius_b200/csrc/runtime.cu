@@ -138,6 +138,20 @@ __global__ void k_selftest_field(const F* a, const F* b, size_t n, F* o_ptx, F* 
     o_inv[i] = (i & 1) ? inv_safegcd(x) : (x.is_zero() ? x : ((i & 2) ? inv_binary(x) : inv(x)));  // all three inversion routines
 }
 
+// lazy-domain operations (field.cuh): PTX forms on operands anywhere in [0, 2p); raw results out
+template <class F>
+__global__ void k_selftest_lazy(const F* a, const F* b, size_t n, F* o_mul, F* o_sub, F* o_dbl, F* o_canon) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i], y = b[i];
+    o_mul[i] = mul_lazy(x, y);
+    o_sub[i] = sub_lazy(x, y);
+    o_dbl[i] = dbl_lazy(x);
+    F c = canon(x);
+    if (is_zero_lazy(x)) c.v[7] |= 0x80000000u;  // flag bit (values are < 2^255)
+    o_canon[i] = c;
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -225,6 +239,42 @@ int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n,
         cudaError_t e = cudaGetLastError();
         uint64_t* outs[5] = {out_mul_ptx, out_mul_portable, out_add, out_sub, out_inv};
         for (int k = 0; k < 5 && e == cudaSuccess; k++) e = cudaMemcpyAsync(outs[k], d + (2 + k) * bytes, bytes, cudaMemcpyDeviceToHost, rt.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
+        if (e != cudaSuccess) {
+            set_error("selftest failed: %s", cudaGetErrorString(e));
+            rc = SB_ERR_CUDA;
+        }
+    } while (0);
+    cudaFree(d);
+    return rc;
+}
+
+int sb_selftest_lazy(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul, uint64_t* out_sub, uint64_t* out_dbl,
+                     uint64_t* out_canon) {
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    std::lock_guard<std::mutex> lk(rt.mu);
+    char* d = nullptr;
+    size_t bytes = n * 32;
+    SB_CUDA_TRY(cudaMalloc(&d, bytes * 6));
+    int rc = SB_OK;
+    do {
+        if (cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, rt.stream) != cudaSuccess ||
+            cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, rt.stream) != cudaSuccess) {
+            set_error("selftest H2D failed");
+            rc = SB_ERR_CUDA;
+            break;
+        }
+        unsigned blocks = (unsigned)((n + 127) / 128);
+        if (field == FIELD_FR)
+            k_selftest_lazy<Fr><<<blocks, 128, 0, rt.stream>>>((const Fr*)d, (const Fr*)(d + bytes), n, (Fr*)(d + 2 * bytes), (Fr*)(d + 3 * bytes),
+                                                              (Fr*)(d + 4 * bytes), (Fr*)(d + 5 * bytes));
+        else
+            k_selftest_lazy<Fq><<<blocks, 128, 0, rt.stream>>>((const Fq*)d, (const Fq*)(d + bytes), n, (Fq*)(d + 2 * bytes), (Fq*)(d + 3 * bytes),
+                                                              (Fq*)(d + 4 * bytes), (Fq*)(d + 5 * bytes));
+        cudaError_t e = cudaGetLastError();
+        uint64_t* outs[4] = {out_mul, out_sub, out_dbl, out_canon};
+        for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaMemcpyAsync(outs[k], d + (2 + k) * bytes, bytes, cudaMemcpyDeviceToHost, rt.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
         if (e != cudaSuccess) {
             set_error("selftest failed: %s", cudaGetErrorString(e));

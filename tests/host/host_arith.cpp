@@ -39,7 +39,43 @@ static void t_points(const uint64_t* pts, const uint8_t* negs, size_t n, uint64_
     memcpy(out_dbl, &d, 64);
 }
 
+// lazy-domain twins (field.cuh "lazy domain"): raw [0, 2p) results, canonicalised by the caller
+template <class F>
+static void t_lazy(const uint64_t* a, const uint64_t* b, uint64_t* o_mul, uint64_t* o_sub, uint64_t* o_dbl, uint8_t* o_zero, size_t n) {
+    const F* A = (const F*)a; const F* B = (const F*)b;
+    for (size_t i = 0; i < n; i++) {
+        ((F*)o_mul)[i] = mul_lazy(A[i], B[i]);
+        ((F*)o_sub)[i] = sub_lazy(A[i], B[i]);
+        ((F*)o_dbl)[i] = dbl_lazy(A[i]);
+        o_zero[i] = is_zero_lazy(A[i]) ? 1 : 0;
+    }
+}
+// the same sums as t_points through xyzz_madd_lazy, with `chain` products of slack: the accumulator is fed back
+// un-canonicalised for the whole run, as in k_accumulate
+template <class F>
+static void t_points_lazy(const uint64_t* pts, const uint8_t* negs, size_t n, uint64_t* out_sum, uint8_t* out_in_range) {
+    const Affine<F>* P = (const Affine<F>*)pts;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    uint8_t ok = 1;
+    F twop;
+    for (int k = 0; k < 8; k++) twop.v[k] = TwoP<typename F::Params>::limb(k);
+    for (size_t i = 0; i < n; i++) {
+        xyzz_madd_lazy(acc, P[i], negs[i] != 0);
+        const F* c[4] = {&acc.x, &acc.y, &acc.zz, &acc.zzz};
+        for (int j = 0; j < 4; j++) ok &= limbs_geq(c[j]->v, twop.v) ? 0 : 1;  // every coordinate stays below 2p
+    }
+    Affine<F> s = xyzz_to_affine(canon_point(acc));
+    memcpy(out_sum, &s, 64);
+    *out_in_range = ok;
+}
+
 extern "C" {
+void ha_lazy(int field, const uint64_t* a, const uint64_t* b, uint64_t* om, uint64_t* os, uint64_t* od, uint8_t* oz, size_t n) {
+    if (field == FIELD_FR) t_lazy<Fr>(a, b, om, os, od, oz, n); else t_lazy<Fq>(a, b, om, os, od, oz, n);
+}
+void ha_points_lazy(int curve, const uint64_t* pts, const uint8_t* negs, size_t n, uint64_t* out_sum, uint8_t* ok) {
+    if (curve == CURVE_BN256) t_points_lazy<Fq>(pts, negs, n, out_sum, ok); else t_points_lazy<Fr>(pts, negs, n, out_sum, ok);
+}
 void ha_mul(int field, const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n) {
     if (field == FIELD_FR) t_mul<Fr>(a, b, o, n); else t_mul<Fq>(a, b, o, n);
 }

@@ -43,6 +43,43 @@ def test_device_field_arithmetic(sb, oracle, field):
     assert np.array_equal(outs[4][nz][:256], oracle.field_inv(field, a[nz][:256]))
 
 
+@pytest.mark.parametrize("field", [R.FIELD_FR, R.FIELD_FQ])
+def test_device_lazy_domain(sb, field):
+    """the PTX forms of the lazy-domain operations (field.cuh; used by the bucket kernel's mixed addition): operands
+    anywhere in [0, 2p), results below 2p and congruent to the exact operation"""
+    import random
+
+    from sirius_b200 import _lib
+
+    m = R.MODULUS[field]
+    rng = random.Random(70 + field)
+    edge = [0, 1, 2, m - 2, m - 1, m, m + 1, 2 * m - 2, 2 * m - 1, (1 << 254) - 1, 1 << 254, (1 << 32) - 1, 1 << 32, m + (1 << 128)]
+    edge = [e for e in edge if e < 2 * m]
+    va = edge * len(edge) + [rng.randrange(2 * m) for _ in range(4000)]
+    vb = [e for e in edge for _ in edge] + [rng.randrange(2 * m) for _ in range(4000)]
+
+    def limbs(vals):
+        a = np.zeros((len(vals), 4), dtype=np.uint64)
+        for i, v in enumerate(vals):
+            for k in range(4):
+                a[i, k] = (v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+        return a
+
+    def ints(a):
+        return [sum(int(a[i, k]) << (64 * k) for k in range(4)) for i in range(a.shape[0])]
+
+    a, b = limbs(va), limbs(vb)
+    outs = [np.zeros_like(a) for _ in range(4)]
+    _lib.check(_lib.load().sb_selftest_lazy(field, p(a), p(b), len(va), *[p(o) for o in outs]))
+    rinv = pow(pow(2, 256, m), m - 2, m)
+    for x, y, gm, gs, gd, gc in zip(va, vb, *[ints(o) for o in outs]):
+        assert gm < 2 * m and gm % m == (x * y * rinv) % m, (hex(x), hex(y))
+        assert gs < 2 * m and gs % m == (x - y) % m
+        assert gd < 2 * m and gd % m == (2 * x) % m
+        flag, val = gc >> 255, gc & ((1 << 255) - 1)
+        assert val == x % m and bool(flag) == (x % m == 0)
+
+
 def _scalars(oracle, curve, n, seed, kind):
     sf = 0 if curve == R.CURVE_BN256 else 1
     sm = R.CURVE_SCALAR[curve]

@@ -94,3 +94,68 @@ def test_xyzz_group_law(ha, oracle, curve):
         ha.ha_points(curve, p(arr), ng.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), len(plist), p(o1), p(o2))
         assert R.limbs_to_points(o1, curve) == [exp]
         assert R.limbs_to_points(o2, curve) == [R.ec_add(exp, exp, curve)]
+
+
+def _to_limbs(vals):
+    a = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        for k in range(4):
+            a[i, k] = (v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+    return a
+
+
+def _from_limbs(a):
+    return [sum(int(a[i, k]) << (64 * k) for k in range(4)) for i in range(a.shape[0])]
+
+
+@pytest.mark.parametrize("field", [R.FIELD_FR, R.FIELD_FQ])
+def test_lazy_domain_ops(ha, field):
+    """field.cuh lazy domain: operands anywhere in [0, 2p) (incl. p, 2p - 1 and values just around p), results must
+    stay in [0, 2p) and be congruent to the canonical operation"""
+    import random
+
+    m = R.MODULUS[field]
+    rng = random.Random(7 + field)
+    edge = [0, 1, 2, m - 2, m - 1, m, m + 1, 2 * m - 2, 2 * m - 1, (1 << 254) - 1, 1 << 254, (1 << 254) + 1, (1 << 32) - 1, 1 << 32,
+            m + (1 << 128), 2 * m - (1 << 200)]
+    edge = [e for e in edge if e < 2 * m]
+    vals_a = edge * len(edge) + [rng.randrange(2 * m) for _ in range(20000)]
+    vals_b = [e for e in edge for _ in edge] + [rng.randrange(2 * m) for _ in range(20000)]
+    a, b = _to_limbs(vals_a), _to_limbs(vals_b)
+    om, os_, od = np.zeros_like(a), np.zeros_like(a), np.zeros_like(a)
+    oz = np.zeros(len(vals_a), dtype=np.uint8)
+    ha.ha_lazy(field, p(a), p(b), p(om), p(os_), p(od), oz.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), len(vals_a))
+    rinv = pow(pow(2, 256, m), m - 2, m)
+    for x, y, gm, gs, gd, gz in zip(vals_a, vals_b, _from_limbs(om), _from_limbs(os_), _from_limbs(od), oz):
+        assert gm < 2 * m and gm % m == (x * y * rinv) % m, (hex(x), hex(y))
+        assert gs < 2 * m and gs % m == (x - y) % m
+        assert gd < 2 * m and gd % m == (2 * x) % m
+        assert bool(gz) == (x % m == 0)
+
+
+@pytest.mark.parametrize("curve", [R.CURVE_BN256, R.CURVE_GRUMPKIN])
+def test_xyzz_madd_lazy(ha, oracle, curve):
+    """xyzz_madd_lazy (the bucket kernel's addition) over long runs with repeats, cancellations and identities: same
+    affine sum as the oracle, every coordinate below 2p at every step"""
+    import random
+
+    rng = random.Random(11 + curve)
+    pts = R.running_bases(24, curve)
+    runs = [
+        [(i, 0) for i in range(24)],
+        [(3, 0), (3, 0), (3, 0), (3, 1), (3, 1), (3, 1), (5, 0)],          # doubling, then cancel to the identity, restart
+        [(None, 0), (7, 1), (None, 0), (7, 0), (7, 0)],
+        [(rng.randrange(24), rng.randrange(2)) for _ in range(3000)],
+    ]
+    for run in runs:
+        plist = [pts[i] if i is not None else None for i, _ in run]
+        negs = np.array([s for _, s in run], dtype=np.uint8)
+        exp = None
+        for q, s in zip(plist, negs):
+            exp = R.ec_add(exp, R.ec_neg(q, curve) if (s and q is not None) else q, curve)
+        arr = R.points_to_limbs(plist, curve)
+        out = np.zeros(8, dtype=np.uint64)
+        ok = ctypes.c_uint8(0)
+        ha.ha_points_lazy(curve, p(arr), negs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), len(plist), p(out), ctypes.byref(ok))
+        assert ok.value == 1
+        assert R.limbs_to_points(out, curve) == [exp]
