@@ -151,12 +151,12 @@ __global__ void k_on_curve(const Affine<F>* __restrict__ pts, size_t n, int b_sm
 // ------------------------------------------------------------------------------------------------
 // commit-time: digits, counting sort
 // ------------------------------------------------------------------------------------------------
-// dig[w*n + i] = 0 (digit 0) or ((|d|) | sign<<31) for the signed base-2^c digit d of scalar i, window w.
+// dig[w*n + i] = (0 (digit 0) or ((|d|) | sign<<31), rank in its bucket) for the signed base-2^c digit d of scalar i, window w.
 // Batched: `total` = batch * n scalars (batch b = i / n shares the same key, its buckets are [b*K, (b+1)*K)),
 // the scalar vectors being `stride` elements apart.
 template <class S>
 __global__ void k_decompose(const S* __restrict__ scalars, uint32_t n, uint32_t total, size_t stride, uint32_t K, int c, int W,
-                            uint32_t* __restrict__ dig, uint32_t* __restrict__ counts) {
+                            uint2* __restrict__ dig, uint32_t* __restrict__ counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const uint32_t batch = i / n;
@@ -187,14 +187,16 @@ __global__ void k_decompose(const S* __restrict__ scalars, uint32_t n, uint32_t 
             carry = 0;
             out = raw;
         }
-        dig[(size_t)w * total + i] = out;
-        if (out) atomicAdd(&counts[bucket_base + (out & 0x7fffffffu) - 1], 1u);
+        // the counter's old value is this entry's rank inside its bucket: the scatter pass needs no second atomic
+        uint32_t rank = 0;
+        if (out) rank = atomicAdd(&counts[bucket_base + (out & 0x7fffffffu) - 1], 1u);
+        dig[(size_t)w * total + i] = make_uint2(out, rank);
     }
 }
 
 // The three scan kernels below build, in one pass each, the bucket offsets of every reduction round (affine.cuh):
 // blockIdx.y = r scans cnt_r(b) = ceil(counts[b] / 2^r); row r of `offsets` (KB + 1 entries) and of `tile_sums`
-// (SCAN_MAX_TILES entries).  r = 0 is the plain counting-sort scan and also initialises `cursor`.
+// (SCAN_MAX_TILES entries).  r = 0 is the plain counting-sort scan.
 constexpr uint32_t SCAN_MAX_TILES = 8192;
 SB_D uint32_t round_count(uint32_t c, uint32_t r) { return (c + ((1u << r) - 1u)) >> r; }
 
@@ -247,9 +249,9 @@ __global__ void k_scan_tiles(uint32_t* tile_sums_all, uint32_t num_tiles) {
     }
 }
 
-// offsets[r][i] = exclusive prefix of cnt_r; offsets[r][K] = total; cursor[i] = offsets[0][i]
+// offsets[r][i] = exclusive prefix of cnt_r; offsets[r][K] = total
 __global__ void k_scan_apply(const uint32_t* __restrict__ counts, uint32_t K, const uint32_t* __restrict__ tile_excl_all,
-                             uint32_t* __restrict__ offsets_all, uint32_t* __restrict__ cursor) {
+                             uint32_t* __restrict__ offsets_all) {
     __shared__ uint32_t sh[SCAN_THREADS];
     const uint32_t r = blockIdx.y;
     const uint32_t* tile_excl = tile_excl_all + r * SCAN_MAX_TILES;
@@ -275,29 +277,26 @@ __global__ void k_scan_apply(const uint32_t* __restrict__ counts, uint32_t K, co
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         uint32_t idx = base + k;
-        if (idx < K) {
-            offsets[idx] = run;
-            if (r == 0) cursor[idx] = run;
-        }
+        if (idx < K) offsets[idx] = run;
         run += v[k];
         if (idx == K - 1) offsets[K] = run;
     }
 }
 
-// entry (table index | sign<<31) placed at its bucket's next free slot; the bucket of a sorted position is
+// entry (table index | sign<<31) placed at offsets[bucket] + its rank (from k_decompose); the bucket of a sorted position is
 // recovered from `offsets` (k_chunk_heads + a walk in k_accumulate), so no key array is written
-__global__ void k_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t total, uint32_t K, uint32_t n_ck, int W,
-                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ eidx) {
+__global__ void k_scatter(const uint2* __restrict__ dig, uint32_t n, uint32_t total, uint32_t K, uint32_t n_ck, int W,
+                          const uint32_t* __restrict__ offsets, uint32_t* __restrict__ eidx) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const uint32_t batch = i / n;
     const uint32_t pt = i - batch * n;
     for (int w = 0; w < W; w++) {
-        uint32_t d = dig[(size_t)w * total + i];
+        const uint2 dr = dig[(size_t)w * total + i];
+        const uint32_t d = dr.x;
         if (d) {
             uint32_t b = batch * K + (d & 0x7fffffffu) - 1;
-            uint32_t pos = atomicAdd(&cursor[b], 1u);
-            eidx[pos] = ((uint32_t)w * n_ck + pt) | (d & 0x80000000u);
+            eidx[offsets[b] + dr.y] = ((uint32_t)w * n_ck + pt) | (d & 0x80000000u);
         }
     }
 }
@@ -697,7 +696,7 @@ struct MsmPlan {
     int rounds;          // batched-affine reduction rounds before the XYZZ chunk kernel (0 = none), affine.cuh
     int pair_b;          // outputs per thread in k_pair_round (8 or 16)
     size_t m_final;      // upper bound of the entries left after the rounds
-    size_t off_dig, off_counts, off_offsets, off_cursor, off_tiles, off_ekey, off_eidx, off_buckets, off_ph, off_pt,
+    size_t off_dig, off_counts, off_offsets, off_tiles, off_ekey, off_eidx, off_buckets, off_ph, off_pt,
         off_heavy, off_nodes_a, off_nodes_b, off_digits, off_out_xy, off_out_xyzz, off_scalars, off_round_a, off_round_b, total_bytes;
 };
 
@@ -773,10 +772,9 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
         off = align_up(off + bytes, 256);
         return o;
     };
-    p.off_dig = take(p.nW * 4);
+    p.off_dig = take(p.nW * 8);   // (digit, rank) pairs
     p.off_counts = take(((size_t)p.KB + 1) * 4);  // +1: heavy-bucket counter lives behind the counts (one memset)
     p.off_offsets = take(((size_t)p.KB + 1) * 4 * (size_t)(p.rounds + 1));  // one row per round
-    p.off_cursor = take((size_t)p.KB * 4);
     p.off_tiles = take((size_t)SCAN_MAX_TILES * 4 * (size_t)(p.rounds + 1));
     p.off_ekey = take((p.chunks + 1) * 4);  // chunk heads
     p.off_eidx = take(p.nW * 4);
@@ -804,10 +802,9 @@ template <class F, class S>
 static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, size_t stride, void* d_out_xy,
                        void* d_out_xyzz, cudaStream_t st) {
     const uint32_t n = (uint32_t)p.n, total = (uint32_t)p.total;
-    auto* dig = (uint32_t*)(ws + p.off_dig);
+    auto* dig = (uint2*)(ws + p.off_dig);
     auto* counts = (uint32_t*)(ws + p.off_counts);
     auto* offsets = (uint32_t*)(ws + p.off_offsets);
-    auto* cursor = (uint32_t*)(ws + p.off_cursor);
     auto* tiles = (uint32_t*)(ws + p.off_tiles);
     auto* chunk_head = (uint32_t*)(ws + p.off_ekey);
     auto* eidx = (uint32_t*)(ws + p.off_eidx);
@@ -832,10 +829,10 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         SB_KERNEL_CHECK();
         k_scan_tiles<<<R + 1, 1024, 0, st>>>(tiles, p.tiles);
         SB_KERNEL_CHECK();
-        k_scan_apply<<<gs, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets, cursor);
+        k_scan_apply<<<gs, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets);
         SB_KERNEL_CHECK();
     }
-    k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, cursor, eidx);
+    k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, offsets, eidx);
     SB_KERNEL_CHECK();
     const uint32_t* off_final = offsets + (size_t)R * ((size_t)KB + 1);   // offsets of the entries the chunk kernel sees
     k_chunk_heads<<<(KB + 255) / 256, 256, 0, st>>>(off_final, KB, p.ls_log, chunk_head);
