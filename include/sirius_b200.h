@@ -92,7 +92,9 @@ size_t sb_ck_len(sb_ck_t ck);
 int sb_ck_window_bits(sb_ck_t ck);
 /* Performance knobs of the commitment pipeline; results are bit-identical for every setting.
  * key 0: batched-affine reduction rounds before the XYZZ bucket kernel (-1 = automatic, 0 = off, <= 8);
- * key 1: outputs per thread of one round (8 or 16). */
+ * key 1: outputs per thread of one round (8 or 16);
+ * key 2: sort of the digit entries (0 = automatic, 1 = counting sort with one atomic per entry, 2 = two-level
+ *        partition sort through shared-memory histograms whenever the bucket count allows). */
 int sb_msm_tune(int key, int value);
 
 /* CommitmentKey::commit (src/commitment.rs:81-90): out = sum_{i<n} scalars[i] * ck[i], affine.

@@ -302,6 +302,246 @@ __global__ void k_scatter(const uint2* __restrict__ dig, uint32_t n, uint32_t to
 }
 
 // ------------------------------------------------------------------------------------------------
+// commit-time, large inputs: two-level partition sort (no per-entry global atomics)
+// ------------------------------------------------------------------------------------------------
+// The counting sort above pays one global atomic per digit entry (n*W of them: ~0.7 ms of a 16 ms step).  For
+// 512 <= KB <= 2^20 buckets the entries are instead partitioned twice through shared-memory histograms:
+//   level 1  partition = bucket >> 8 (P <= 4096 partitions).  k_digits_parts writes the digits and counts entries per
+//            partition (shared-memory counters, P global atomics per block of 1024 scalars); k_scan_small turns the
+//            counts into partition offsets; k_partition re-reads the digits and moves (bucket, table index | sign)
+//            pairs into their partition, reserving one run per (block, partition) with a single global atomic.
+//   level 2  inside a partition only 256 buckets occur: k_bucket_hist counts them in shared memory (-> counts[],
+//            scanned by the usual k_scan_* into offsets[]); k_place reserves one run per (tile, bucket) and writes the
+//            sorted entries eidx[].
+// Order inside a bucket differs from the atomic path; the sums are exact, so the commitment does not.
+constexpr int PART_LO_BITS = 8;
+constexpr uint32_t PART_BUCKETS = 1u << PART_LO_BITS;   // buckets per partition
+constexpr uint32_t PART_MAX = 4096;                     // partitions (shared-memory counters of k_partition: 2 * 4 B each)
+constexpr int PART_SPT = 4;                             // scalars per thread in the level-1 kernels
+constexpr int PART_EPT = 8;                             // entries per thread and tile in k_place
+
+// digit w of a canonical scalar held in limb[0..8] (limb[8] = 0), with the carry of the signed recoding
+SB_D uint32_t signed_digit(const uint32_t* limb, int w, int c, uint32_t& carry) {
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+    const int off = w * c;
+    const int li = off >> 5, sh = off & 31;
+    uint32_t raw = 0;
+    if (li < 8) {
+        uint64_t two = (uint64_t)limb[li] | ((uint64_t)limb[li + 1] << 32);
+        raw = (uint32_t)(two >> sh) & mask;
+    }
+    raw += carry;
+    if (raw > half) {
+        const uint32_t mag = (1u << c) - raw;  // digit = raw - 2^c (negative); raw == 2^c -> 0
+        carry = 1;
+        return mag ? (mag | 0x80000000u) : 0u;
+    }
+    carry = 0;
+    return raw;
+}
+
+template <class S>
+__global__ void __launch_bounds__(256)
+k_digits_parts(const S* __restrict__ scalars, uint32_t n, uint32_t total, size_t stride, uint32_t K, int c, int W, uint32_t P,
+               uint32_t* __restrict__ dig, uint32_t* __restrict__ part_count) {
+    extern __shared__ uint32_t sh_cnt[];
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) sh_cnt[i] = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = 0; s < PART_SPT; s++) {
+        const uint32_t i = (blockIdx.x * PART_SPT + s) * blockDim.x + threadIdx.x;
+        if (i >= total) break;
+        const uint32_t batch = i / n;
+        const uint32_t bucket_base = batch * K;
+        S sc = from_mont(load_vec_nc(scalars + (size_t)batch * stride + (i - batch * n)));
+        uint32_t limb[9];
+#pragma unroll
+        for (int k = 0; k < 8; k++) limb[k] = sc.v[k];
+        limb[8] = 0;
+        uint32_t carry = 0;
+        for (int w = 0; w < W; w++) {
+            const uint32_t out = signed_digit(limb, w, c, carry);
+            dig[(size_t)w * total + i] = out;
+            if (out) atomicAdd(&sh_cnt[(bucket_base + (out & 0x7fffffffu) - 1) >> PART_LO_BITS], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
+        if (sh_cnt[i]) atomicAdd(&part_count[i], sh_cnt[i]);
+}
+
+// exclusive scan of up to 8192 counters in one block of 1024 threads: off[i] = sum_{j<i} cnt[j], off[n] = total
+__global__ void k_scan_small(const uint32_t* __restrict__ cnt, uint32_t n, uint32_t* __restrict__ off) {
+    __shared__ uint32_t sh[1024];
+    uint32_t v[8];
+    const uint32_t base = threadIdx.x * 8;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        v[k] = (base + k < n) ? cnt[base + k] : 0u;
+        s += v[k];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t excl = sh[threadIdx.x] - s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (base + k < n) off[base + k] = excl;
+        excl += v[k];
+        if (base + k + 1 == n) off[n] = excl;
+    }
+}
+
+// exclusive prefix of cnt[0..m) into off[0..m) by the 256 threads of a block (tmp: 256 words of shared memory)
+SB_D void block_excl_scan(const uint32_t* cnt, uint32_t* off, uint32_t m, uint32_t* tmp) {
+    const uint32_t ch = (m + 255u) / 256u;
+    const uint32_t lo = threadIdx.x * ch, hi = (lo + ch < m) ? lo + ch : m;
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += cnt[i];
+    tmp[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        const uint32_t t = (threadIdx.x >= (unsigned)d) ? tmp[threadIdx.x - d] : 0u;
+        __syncthreads();
+        tmp[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t run = tmp[threadIdx.x] - s;
+    for (uint32_t i = lo; i < hi; i++) {
+        off[i] = run;
+        run += cnt[i];
+    }
+    __syncthreads();
+}
+
+// One block = 256 scalars = 256 * W entries: (bucket, table index | sign) pairs are ranked by level-1 partition in
+// shared memory and leave as one contiguous run per partition (coalesced 8-byte stores; a run is reserved in the
+// partition with a single global atomic).  Shared memory: cnt[P] | loc[P] | base[P] | tmp[256] | stage[256 * W] pairs.
+__global__ void __launch_bounds__(256)
+k_partition(const uint32_t* __restrict__ dig, uint32_t n, uint32_t total, uint32_t K, uint32_t n_ck, int W, uint32_t P,
+            const uint32_t* __restrict__ part_off, uint32_t* __restrict__ part_cursor, uint2* __restrict__ out1) {
+    extern __shared__ uint32_t sh[];
+    uint32_t* cnt = sh;               // entries of this block per partition, later the running local rank
+    uint32_t* loc = sh + P;           // start of the partition's run inside the staging area
+    uint32_t* base = sh + 2 * P;      // start of the run inside the partition (global)
+    uint32_t* tmp = sh + 3 * P;
+    uint2* stage = reinterpret_cast<uint2*>(sh + 3 * P + 256 + ((3 * P) & 1u));   // 8-byte aligned
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < total;
+    const uint32_t batch = live ? i / n : 0;
+    const uint32_t pt = i - batch * n;
+    const uint32_t bucket_base = batch * K;
+    if (live)
+        for (int w = 0; w < W; w++) {
+            const uint32_t d = dig[(size_t)w * total + i];
+            if (d) atomicAdd(&cnt[(bucket_base + (d & 0x7fffffffu) - 1) >> PART_LO_BITS], 1u);
+        }
+    __syncthreads();
+    block_excl_scan(cnt, loc, P, tmp);
+    for (uint32_t q = threadIdx.x; q < P; q += blockDim.x) {
+        const uint32_t m = cnt[q];
+        if (m) base[q] = part_off[q] + atomicAdd(&part_cursor[q], m);
+        cnt[q] = 0;
+    }
+    __syncthreads();
+    if (live)
+        for (int w = 0; w < W; w++) {
+            const uint32_t d = dig[(size_t)w * total + i];
+            if (d) {
+                const uint32_t b = bucket_base + (d & 0x7fffffffu) - 1;
+                const uint32_t hi = b >> PART_LO_BITS;
+                const uint32_t r = atomicAdd(&cnt[hi], 1u);
+                stage[loc[hi] + r] = make_uint2(b, ((uint32_t)w * n_ck + pt) | (d & 0x80000000u));
+            }
+        }
+    __syncthreads();
+    // the block's entry count = end of the last partition's run
+    const uint32_t m_total = loc[P - 1] + cnt[P - 1];
+    for (uint32_t idx = threadIdx.x; idx < m_total; idx += blockDim.x) {
+        const uint2 e = stage[idx];
+        const uint32_t hi = e.x >> PART_LO_BITS;
+        out1[base[hi] + (idx - loc[hi])] = e;
+    }
+}
+
+// grid (P, S): block (hi, s) strides over partition hi and counts its 256 buckets
+__global__ void __launch_bounds__(256)
+k_bucket_hist(const uint2* __restrict__ out1, const uint32_t* __restrict__ part_off, uint32_t KB, uint32_t* __restrict__ counts) {
+    __shared__ uint32_t h[PART_BUCKETS];
+    const uint32_t hi = blockIdx.x;
+    const uint32_t start = part_off[hi], end = part_off[hi + 1];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t pos = (uint64_t)start + blockIdx.y * 256u + threadIdx.x; pos < end; pos += (uint64_t)gridDim.y * 256u)
+        atomicAdd(&h[out1[pos].x & (PART_BUCKETS - 1)], 1u);
+    __syncthreads();
+    const uint32_t b = hi * PART_BUCKETS + threadIdx.x;
+    if (b < KB && h[threadIdx.x]) atomicAdd(&counts[b], h[threadIdx.x]);
+}
+
+// grid (P, S): tiles of 256 * PART_EPT entries of one partition are ranked by bucket in shared memory and leave as one
+// contiguous run per bucket (a run is reserved in eidx[] with a single global atomic per (tile, bucket))
+__global__ void __launch_bounds__(256)
+k_place(const uint2* __restrict__ out1, const uint32_t* __restrict__ part_off, const uint32_t* __restrict__ offsets,
+        uint32_t* __restrict__ cursor, uint32_t KB, uint32_t* __restrict__ eidx) {
+    __shared__ uint32_t cnt[PART_BUCKETS];
+    __shared__ uint32_t loc[PART_BUCKETS];
+    __shared__ uint32_t base[PART_BUCKETS];
+    __shared__ uint32_t tmp[256];
+    __shared__ uint2 stage[256 * PART_EPT];
+    const uint32_t hi = blockIdx.x;
+    const uint32_t start = part_off[hi], end = part_off[hi + 1];
+    const uint32_t TILE = 256u * PART_EPT;
+    for (uint64_t tile = (uint64_t)start + (uint64_t)blockIdx.y * TILE; tile < end; tile += (uint64_t)gridDim.y * TILE) {
+        cnt[threadIdx.x] = 0;
+        __syncthreads();
+        uint2 e[PART_EPT];
+#pragma unroll
+        for (int j = 0; j < PART_EPT; j++) {
+            const uint64_t pos = tile + (uint64_t)j * 256u + threadIdx.x;
+            e[j] = make_uint2(0xffffffffu, 0u);
+            if (pos < end) {
+                e[j] = out1[pos];
+                atomicAdd(&cnt[e[j].x & (PART_BUCKETS - 1)], 1u);
+            }
+        }
+        __syncthreads();
+        block_excl_scan(cnt, loc, PART_BUCKETS, tmp);
+        {
+            const uint32_t b = hi * PART_BUCKETS + threadIdx.x;
+            const uint32_t m = cnt[threadIdx.x];
+            if (m && b < KB) base[threadIdx.x] = offsets[b] + atomicAdd(&cursor[b], m);
+            cnt[threadIdx.x] = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PART_EPT; j++) {
+            if (e[j].x != 0xffffffffu) {
+                const uint32_t lo = e[j].x & (PART_BUCKETS - 1);
+                const uint32_t r = atomicAdd(&cnt[lo], 1u);
+                stage[loc[lo] + r] = e[j];
+            }
+        }
+        __syncthreads();
+        const uint32_t m_total = loc[PART_BUCKETS - 1] + cnt[PART_BUCKETS - 1];
+        for (uint32_t idx = threadIdx.x; idx < m_total; idx += 256u) {
+            const uint2 v = stage[idx];
+            const uint32_t lo = v.x & (PART_BUCKETS - 1);
+            eidx[base[lo] + (idx - loc[lo])] = v.y;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // bucket sums
 // ------------------------------------------------------------------------------------------------
 // chunk_head[t] = bucket that contains sorted position t*LS (one thread per bucket, writes one entry per chunk start
@@ -693,17 +933,22 @@ struct MsmPlan {
     size_t n, total, nW, chunks;
     uint32_t batch, K, KB, tiles;
     int ls_log;
+    uint32_t parts;      // level-1 partitions of the two-level sort (0 = per-entry atomic counting sort)
     int rounds;          // batched-affine reduction rounds before the XYZZ chunk kernel (0 = none), affine.cuh
     int pair_b;          // outputs per thread in k_pair_round (8 or 16)
     size_t m_final;      // upper bound of the entries left after the rounds
     size_t off_dig, off_counts, off_offsets, off_tiles, off_ekey, off_eidx, off_buckets, off_ph, off_pt,
-        off_heavy, off_nodes_a, off_nodes_b, off_digits, off_out_xy, off_out_xyzz, off_scalars, off_round_a, off_round_b, total_bytes;
+        off_heavy, off_nodes_a, off_nodes_b, off_digits, off_out_xy, off_out_xyzz, off_scalars, off_round_a, off_round_b, off_parts, off_cursor, off_out1, total_bytes;
 };
 
 // Tuning knobs (sb_msm_tune): number of batched-affine rounds (-1 = automatic) and outputs per thread.
 static int g_affine_rounds = []() {
     const char* e = getenv("SB_MSM_AFFINE_ROUNDS");
     return e ? atoi(e) : -1;
+}();
+static int g_sort_mode = []() {   // 0 = automatic, 1 = always the per-entry atomic counting sort, 2 = partition sort when legal
+    const char* e = getenv("SB_MSM_SORT");
+    return e ? atoi(e) : 0;
 }();
 static int g_pair_b = []() {
     const char* e = getenv("SB_MSM_PAIR_B");
@@ -748,6 +993,12 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
         set_error("sb_msm: too many buckets (%llu)", (unsigned long long)kb);
         return SB_ERR_ARG;
     }
+    {   // two-level partition sort for big inputs (the atomic path stays for tiny / huge bucket counts)
+        const uint64_t P = (kb + PART_BUCKETS - 1) >> PART_LO_BITS;
+        const bool legal = kb >= 2 * PART_BUCKETS && P <= PART_MAX;
+        const bool want = g_sort_mode == 2 || (g_sort_mode == 0 && p.nW >= ((size_t)1 << 18));
+        p.parts = (legal && want) ? (uint32_t)P : 0u;
+    }
     p.rounds = g_affine_rounds >= 0 ? std::min(g_affine_rounds, MAX_AFFINE_ROUNDS) : auto_affine_rounds(p.nW, p.KB);
     p.pair_b = g_pair_b == 8 ? 8 : 16;
     // entries left for the chunk kernel: every round halves each bucket, rounding up
@@ -772,7 +1023,10 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
         off = align_up(off + bytes, 256);
         return o;
     };
-    p.off_dig = take(p.nW * 8);   // (digit, rank) pairs
+    p.off_dig = take(p.nW * (p.parts ? 4 : 8));   // digits (partition sort) or (digit, rank) pairs
+    p.off_parts = take(p.parts ? ((size_t)p.parts * 3 + 2) * 4 : 0);   // partition counts | cursors | offsets (+1)
+    p.off_cursor = take(p.parts ? (size_t)p.KB * 4 : 0);
+    p.off_out1 = take(p.parts ? p.nW * 8 : 0);
     p.off_counts = take(((size_t)p.KB + 1) * 4);  // +1: heavy-bucket counter lives behind the counts (one memset)
     p.off_offsets = take(((size_t)p.KB + 1) * 4 * (size_t)(p.rounds + 1));  // one row per round
     p.off_tiles = take((size_t)SCAN_MAX_TILES * 4 * (size_t)(p.rounds + 1));
@@ -815,14 +1069,45 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     const uint32_t K = p.K, KB = p.KB;
     uint32_t* heavy_count = counts + KB;
 
+    const uint32_t P = p.parts;
+    auto* part_count = (uint32_t*)(ws + p.off_parts);   // [P] counts, [P] cursors, [P + 1] offsets
+    uint32_t* part_cursor = part_count + P;
+    uint32_t* part_off = part_count + 2 * (size_t)P;
+    auto* bucket_cursor = (uint32_t*)(ws + p.off_cursor);
+    auto* out1 = (uint2*)(ws + p.off_out1);
+    const unsigned part_blocks = (unsigned)((p.total + 256 * PART_SPT - 1) / (256 * PART_SPT));
     {
         ProfScope ps(st, PROF_DECOMPOSE, p.total);
         SB_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)KB + 1) * 4, st));
-        k_decompose<S><<<(total + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, total, stride, K, p.c, p.W, dig, counts);
+        if (P) {
+            SB_CUDA_TRY(cudaMemsetAsync(part_count, 0, (size_t)P * 2 * 4, st));
+            SB_CUDA_TRY(cudaMemsetAsync(bucket_cursor, 0, (size_t)KB * 4, st));
+            k_digits_parts<S><<<part_blocks, 256, P * 4, st>>>((const S*)d_scalars, n, total, stride, K, p.c, p.W, P, (uint32_t*)dig, part_count);
+        } else {
+            k_decompose<S><<<(total + 255) / 256, 256, 0, st>>>((const S*)d_scalars, n, total, stride, K, p.c, p.W, dig, counts);
+        }
         SB_KERNEL_CHECK();
     }
     std::unique_ptr<ProfScope> sort_scope(new ProfScope(st, PROF_SORT, p.nW));
     const int R = p.rounds;
+    unsigned part_split = 1;
+    if (P) {   // level 1 partition, then the per-bucket counts of level 2
+        k_scan_small<<<1, 1024, 0, st>>>(part_count, P, part_off);
+        SB_KERNEL_CHECK();
+        const size_t part_smem = ((size_t)3 * P + 256 + 2) * 4 + (size_t)256 * p.W * 8;
+        static size_t part_smem_set = 0;
+        if (part_smem > part_smem_set) {
+            SB_CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            part_smem_set = part_smem;
+        }
+        k_partition<<<(total + 255) / 256, 256, part_smem, st>>>((const uint32_t*)dig, n, total, K, (uint32_t)ck->n, p.W, P, part_off, part_cursor, out1);
+        SB_KERNEL_CHECK();
+        part_split = 2048u / P;
+        if (part_split < 1) part_split = 1;
+        if (part_split > 64) part_split = 64;
+        k_bucket_hist<<<dim3(P, part_split), 256, 0, st>>>(out1, part_off, KB, counts);
+        SB_KERNEL_CHECK();
+    }
     {
         dim3 gs(p.tiles, R + 1);
         k_scan_tile_sums<<<gs, SCAN_THREADS, 0, st>>>(counts, KB, tiles);
@@ -832,8 +1117,13 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         k_scan_apply<<<gs, SCAN_THREADS, 0, st>>>(counts, KB, tiles, offsets);
         SB_KERNEL_CHECK();
     }
-    k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, offsets, eidx);
-    SB_KERNEL_CHECK();
+    if (!P) {
+        k_scatter<<<(total + 255) / 256, 256, 0, st>>>(dig, n, total, K, (uint32_t)ck->n, p.W, offsets, eidx);
+        SB_KERNEL_CHECK();
+    } else {
+        k_place<<<dim3(P, part_split), 256, 0, st>>>(out1, part_off, offsets, bucket_cursor, KB, eidx);
+        SB_KERNEL_CHECK();
+    }
     const uint32_t* off_final = offsets + (size_t)R * ((size_t)KB + 1);   // offsets of the entries the chunk kernel sees
     k_chunk_heads<<<(KB + 255) / 256, 256, 0, st>>>(off_final, KB, p.ls_log, chunk_head);
     sort_scope.reset();
@@ -1054,10 +1344,12 @@ int sb_ck_add_window(sb_ck_t ck, int window_bits, void* stream) {
 size_t sb_ck_len(sb_ck_t ck) { return ck ? ck->n : 0; }
 
 /* Tuning: key 0 = batched-affine rounds per commit (-1 automatic, 0 off, up to 8), key 1 = outputs per thread of a
- * round (8 or 16).  Results are bit-identical for every setting. */
+ * round (8 or 16), key 2 = sort (0 automatic, 1 per-entry atomic counting sort, 2 two-level partition sort whenever the
+ * bucket count allows).  Results are bit-identical for every setting. */
 int sb_msm_tune(int key, int value) {
     if (key == 0 && value >= -1 && value <= MAX_AFFINE_ROUNDS) g_affine_rounds = value;
     else if (key == 1 && (value == 8 || value == 16)) g_pair_b = value;
+    else if (key == 2 && value >= 0 && value <= 2) g_sort_mode = value;
     else {
         set_error("sb_msm_tune: bad key/value %d/%d", key, value);
         return SB_ERR_ARG;

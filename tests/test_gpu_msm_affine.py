@@ -24,13 +24,15 @@ def tune(sb):
 
     lib = _lib.load()
 
-    def set_(rounds, B=16):
+    def set_(rounds, B=16, sort=0):
         _lib.check(lib.sb_msm_tune(0, rounds))
         _lib.check(lib.sb_msm_tune(1, B))
+        _lib.check(lib.sb_msm_tune(2, sort))
 
     yield set_
     _lib.check(lib.sb_msm_tune(0, -1))
     _lib.check(lib.sb_msm_tune(1, 16))
+    _lib.check(lib.sb_msm_tune(2, 0))
 
 
 @pytest.mark.parametrize("curve", [R.CURVE_BN256, R.CURVE_GRUMPKIN])
@@ -81,4 +83,34 @@ def test_affine_rounds_large(sb, oracle, tune):
     for rounds, B in [(0, 16), (2, 16), (3, 8), (3, 16)]:
         tune(rounds, B)
         assert np.array_equal(ck.commit(a), exp), (rounds, B)
+    ck.close()
+
+
+@pytest.mark.parametrize("curve", [R.CURVE_BN256, R.CURVE_GRUMPKIN])
+@pytest.mark.parametrize("sort", [1, 2])
+def test_sort_paths(sb, oracle, tune, curve, sort):
+    """the per-entry atomic counting sort (1) and the two-level partition sort (2) forced on the same inputs:
+    uniform, witness-like and all-equal scalars (one bucket per window holds everything), identity / repeated
+    generators, prefix commits, batched commits with bucket counts that are not a power of two (5 * 512)"""
+    tune(-1, 16, sort)
+    n = 1 << 15
+    bases = oracle.running_bases(curve, n)
+    bases[17] = 0
+    bases[19] = bases[18]
+    for c in (10, 13):      # K = 512 (the smallest the partition sort takes) and 4096
+        ck = sb.CommitmentKey(curve, bases, window_bits=c)
+        for kind in ("uniform", "witness", "equal", "edge"):
+            s = _scalars(oracle, curve, n, 91, kind)
+            assert np.array_equal(ck.commit(s), oracle.msm(curve, s, bases)), (c, kind)
+        s = _scalars(oracle, curve, n, 92, "uniform")
+        assert np.array_equal(ck.commit(s[:777]), oracle.msm(curve, s[:777], bases))
+        vs = [_scalars(oracle, curve, 3000, 50 + j, kind) for j, kind in enumerate(["uniform", "witness", "equal", "edge", "uniform"])]
+        vs[4][:] = 0
+        got = ck.commit_batch(vs)
+        for j, v in enumerate(vs):
+            assert np.array_equal(got[j], oracle.msm(curve, v, bases)), (c, j)
+        ck.close()
+    ck = sb.CommitmentKey(curve, bases, window_bits=6)   # K = 32: too few buckets, mode 2 falls back to the atomic path
+    s = _scalars(oracle, curve, n, 93, "uniform")
+    assert np.array_equal(ck.commit(s), oracle.msm(curve, s, bases))
     ck.close()
