@@ -146,7 +146,8 @@ SB_D F fetch(const EvalArgs<F>& A, uint32_t kind, uint32_t v, const uint4* sm, u
     }
 }
 
-// runs the calculation list once for (row, t); result left in registers
+// runs the calculation list once for (row, t); result left in registers.  Intermediates are kept in the LAZY domain
+// [0, 2p) (field.cuh): products skip their final conditional subtraction; callers canonicalise what they store.
 template <class F>
 SB_D F run_program(const EvalArgs<F>& A, uint4* sm, uint32_t row, uint32_t row_mask, uint32_t t) {
     F last = F::zero();
@@ -156,12 +157,12 @@ SB_D F run_program(const EvalArgs<F>& A, uint4* sm, uint32_t row, uint32_t row_m
         F a = fetch(A, ak, raw.y, sm, row, row_mask, t);
         F r;
         switch (op) {
-            case OP_ADD: r = add(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
-            case OP_SUB: r = sub(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
-            case OP_MUL: r = mul(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
-            case OP_SQUARE: r = sqr(a); break;
-            case OP_DOUBLE: r = dbl(a); break;
-            case OP_NEGATE: r = neg(a); break;
+            case OP_ADD: r = add_lazy(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
+            case OP_SUB: r = sub_lazy(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
+            case OP_MUL: r = mul_lazy(a, fetch(A, bk, raw.z, sm, row, row_mask, t)); break;
+            case OP_SQUARE: r = mul_lazy(a, a); break;
+            case OP_DOUBLE: r = dbl_lazy(a); break;
+            case OP_NEGATE: r = neg_lazy(a); break;
             default: r = a; break;  // OP_STORE
         }
         slot_store(sm, raw.w, blockDim.x, r);
@@ -179,7 +180,7 @@ k_expr_eval(EvalArgs<F> A, uint32_t t, int row0_only, F* __restrict__ out) {
     if (row >= n) return;
     // row0_only reproduces the reference's `index & total_row` leaf addressing (src/plonk/mod.rs:714)
     F r = run_program(A, sm, row0_only ? 0u : row, n - 1, t);
-    stg32(out + row, r);
+    stg32(out + row, canon(r));
 }
 
 // out[(j-1)*n + row] = T_j(row), j = 1..degree;  vinv is the (degree+1)^2 inverse Vandermonde on points 0..degree.
@@ -206,8 +207,8 @@ k_cross_terms(EvalArgs<F> A, uint32_t degree, uint32_t rows_per_block, const F* 
     if (live && t + 1 <= degree) {
         const uint32_t j = t + 1;
         F acc = F::zero();
-        for (uint32_t s = 0; s <= degree; s++) acc = add(acc, mul(ldg32(vinv + j * m + s), exch[r_in * m + s]));
-        stg32(out + (size_t)(j - 1) * n + row, acc);
+        for (uint32_t s = 0; s <= degree; s++) acc = add_lazy(acc, mul_lazy(ldg32(vinv + j * m + s), exch[r_in * m + s]));
+        stg32(out + (size_t)(j - 1) * n + row, canon(acc));
     }
 }
 

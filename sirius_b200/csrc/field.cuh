@@ -506,7 +506,59 @@ SB_HD Fe<P> dbl_lazy_portable(const Fe<P>& a) {  // 2a, - 2p if >= 2p   (2a < 4p
     return br ? r : t;
 }
 
+template <class P>
+SB_HD Fe<P> add_lazy_portable(const Fe<P>& a, const Fe<P>& b) {  // a + b, - 2p if >= 2p   (a + b < 4p < 2^256)
+    Fe<P> r, t;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a.v[i] + b.v[i];
+        r.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)r.v[i] - TwoP<P>::limb(i) - br;
+        t.v[i] = (uint32_t)d;
+        br = (d >> 32) & 1;
+    }
+    return br ? r : t;
+}
+
 #if defined(__CUDA_ARCH__)
+template <class P>
+SB_D Fe<P> add_lazy_ptx(const Fe<P>& a, const Fe<P>& b) {
+    uint32_t s[8], t[8], br;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(br)
+        : "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]),
+          "r"(TwoP<P>::limb(0)), "r"(TwoP<P>::limb(1)), "r"(TwoP<P>::limb(2)), "r"(TwoP<P>::limb(3)),
+          "r"(TwoP<P>::limb(4)), "r"(TwoP<P>::limb(5)), "r"(TwoP<P>::limb(6)), "r"(TwoP<P>::limb(7)));
+    Fe<P> r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = br ? s[i] : t[i];
+    return r;
+}
 template <class P>
 SB_D Fe<P> sub_lazy_ptx(const Fe<P>& a, const Fe<P>& b) {
     Fe<P> r;
@@ -584,6 +636,21 @@ SB_HD Fe<P> sub_lazy(const Fe<P>& a, const Fe<P>& b) {
 #else
     return sub_lazy_portable(a, b);
 #endif
+}
+template <class P>
+SB_HD Fe<P> add_lazy(const Fe<P>& a, const Fe<P>& b) {
+#if defined(__CUDA_ARCH__)
+    return add_lazy_ptx(a, b);
+#else
+    return add_lazy_portable(a, b);
+#endif
+}
+template <class P>
+SB_HD Fe<P> neg_lazy(const Fe<P>& a) {  // 2p - a, and 0 for a = 0 (2p itself is outside the domain)
+    Fe<P> tp;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tp.v[i] = TwoP<P>::limb(i);
+    return a.is_zero() ? a : sub_lazy(tp, a);
 }
 template <class P>
 SB_HD Fe<P> dbl_lazy(const Fe<P>& a) {

@@ -63,6 +63,16 @@ __global__ void k_mb_madd(XYZZ<F>* io, int iters) {
     for (int k = 0; k < iters; k++) xyzz_madd(a, q, (k & 1) != 0);
     io[2 * i] = a;
 }
+template <class F>
+__global__ void k_mb_madd_lazy(XYZZ<F>* io, int iters) {  // the bucket kernel's addition (lazy domain, field.cuh)
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ<F> a = io[2 * i];
+    Affine<F> q;
+    q.x = io[2 * i + 1].x;
+    q.y = io[2 * i + 1].y;
+    for (int k = 0; k < iters; k++) xyzz_madd_lazy(a, q, (k & 1) != 0);
+    io[2 * i] = canon_point(a);
+}
 // Timing experiment only (wrong results): the product with 16 of its 128 IMAD.WIDE removed and ~100 extra
 // carry-chain additions, to price a Karatsuba product (48 + 64 wide multiplies + more additions) before writing it.
 template <class P>
@@ -298,6 +308,7 @@ extern "C" int sb_microbench(int which, int iters, int blocks, int threads, doub
             case 10: k_mb_double_call<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 11: k_mb_inv<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
             case 12: k_mb_inv_safegcd<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
+            case 13: k_mb_madd_lazy<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 20: k_mb_pipe<20><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
             case 21: k_mb_pipe<21><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
             case 22: k_mb_pipe<22><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;

@@ -145,8 +145,8 @@ __global__ void k_selftest_lazy(const F* a, const F* b, size_t n, F* o_mul, F* o
     if (i >= n) return;
     F x = a[i], y = b[i];
     o_mul[i] = mul_lazy(x, y);
-    o_sub[i] = sub_lazy(x, y);
-    o_dbl[i] = dbl_lazy(x);
+    o_sub[i] = (i & 1) ? sub_lazy(x, y) : add_lazy(x, neg_lazy(y));   // both routes to x - y
+    o_dbl[i] = (i & 1) ? dbl_lazy(x) : add_lazy(x, x);
     F c = canon(x);
     if (is_zero_lazy(x)) c.v[7] |= 0x80000000u;  // flag bit (values are < 2^255)
     o_canon[i] = c;

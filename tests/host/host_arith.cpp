@@ -46,7 +46,8 @@ static void t_lazy(const uint64_t* a, const uint64_t* b, uint64_t* o_mul, uint64
     for (size_t i = 0; i < n; i++) {
         ((F*)o_mul)[i] = mul_lazy(A[i], B[i]);
         ((F*)o_sub)[i] = sub_lazy(A[i], B[i]);
-        ((F*)o_dbl)[i] = dbl_lazy(A[i]);
+        ((F*)o_dbl)[i] = (i & 1) ? dbl_lazy(A[i]) : add_lazy(A[i], A[i]);
+        ((F*)o_sub)[i] = (i & 1) ? sub_lazy(A[i], B[i]) : add_lazy(A[i], neg_lazy(B[i]));
         o_zero[i] = is_zero_lazy(A[i]) ? 1 : 0;
     }
 }
