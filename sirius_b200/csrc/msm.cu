@@ -544,15 +544,14 @@ k_place(const uint2* __restrict__ out1, const uint32_t* __restrict__ part_off, c
 // ------------------------------------------------------------------------------------------------
 // bucket sums
 // ------------------------------------------------------------------------------------------------
-// chunk_head[t] = bucket that contains sorted position t*LS (one thread per bucket, writes one entry per chunk start
+// chunk_head[t] = bucket that contains sorted position t*LS (LS = chunk length, any value; one thread per bucket, writes one entry per chunk start
 // inside its range: #chunks writes in total instead of one key per entry)
-__global__ void k_chunk_heads(const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, uint32_t* __restrict__ chunk_head) {
+__global__ void k_chunk_heads(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, uint32_t* __restrict__ chunk_head) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= KB) return;
     const uint32_t o = offsets[b], o2 = offsets[b + 1];
     if (o2 == o) return;
-    const uint32_t LS = 1u << ls_log;
-    for (uint32_t t = (o + LS - 1) >> ls_log; ((uint64_t)t << ls_log) < o2; t++) chunk_head[t] = b;
+    for (uint32_t t = (o + LS - 1) / LS; (uint64_t)t * LS < o2; t++) chunk_head[t] = b;
 }
 
 // One reduction round of the batched-affine bucket sums (affine.cuh): thread g produces outputs [g*B, (g+1)*B) of
@@ -589,21 +588,20 @@ k_pair_round(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ eid
     pair_backward<F, INDEXED, B>(src, pos, kind, cp, ninv[tid], dst + (size_t)g * B);
 }
 
-// Thread t owns sorted entries [t*LS, (t+1)*LS), LS = 2^ls_log.  A bucket lying entirely inside the chunk is
+// Thread t owns sorted entries [t*LS, (t+1)*LS).  A bucket lying entirely inside the chunk is
 // written to buckets[]; a piece of a bucket that continues into a neighbouring chunk goes to PH[t] (piece
 // starts at the chunk start) or PT[t] (piece ends at the chunk end) and is finished by k_fixup.
 // DIRECT = false: entry -> window table (eidx); DIRECT = true: the entries ARE points (output of the affine rounds).
 template <class F, int MINB, bool DIRECT>
 __global__ void __launch_bounds__(128, MINB)
 k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ chunk_head, const uint32_t* __restrict__ eidx,
-             const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* __restrict__ buckets,
+             const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>* __restrict__ buckets,
              XYZZ<F>* __restrict__ PH, XYZZ<F>* __restrict__ PT) {
     const uint32_t M = offsets[KB];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t start64 = (uint64_t)t << ls_log;
+    const uint64_t start64 = (uint64_t)t * LS;
     if (start64 >= M) return;
     const uint32_t start = (uint32_t)start64;
-    const uint32_t LS = 1u << ls_log;
     const uint32_t end = (M - start < LS) ? M : start + LS;
 
     uint32_t cur = chunk_head[t];               // offsets[cur] <= start < offsets[cur + 1]
@@ -648,7 +646,7 @@ k_accumulate(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ c
 // k_fixup_heavy.  (Throughput-bound for batched commits: plain lanes, not quad-lane groups -- measured.)
 template <class F>
 __global__ void __launch_bounds__(128)
-k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* __restrict__ buckets,
+k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>* __restrict__ buckets,
         const XYZZ<F>* __restrict__ PH, const XYZZ<F>* __restrict__ PT, uint32_t* __restrict__ heavy_count,
         uint32_t* __restrict__ heavy_list) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -658,14 +656,14 @@ k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* 
         store_vec(buckets + b, XYZZ<F>::identity());
         return;
     }
-    const uint32_t t0 = o >> ls_log;
-    const uint32_t np = ((o2 - 1) >> ls_log) - t0 + 1;
+    const uint32_t t0 = o / LS;
+    const uint32_t np = (o2 - 1) / LS - t0 + 1;
     if (np == 1) return;  // written by k_accumulate
     if (np > (uint32_t)FIX_SEQ) {
         heavy_list[atomicAdd(heavy_count, 1u)] = b;
         return;
     }
-    XYZZ<F> acc = (o & ((1u << ls_log) - 1)) ? load_vec(PT + t0) : load_vec(PH + t0);
+    XYZZ<F> acc = (o - t0 * LS) ? load_vec(PT + t0) : load_vec(PH + t0);
 #pragma unroll 1
     for (uint32_t p = 1; p < np; p++) {
         XYZZ<F> q = load_vec(PH + t0 + p);
@@ -677,18 +675,19 @@ k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, int ls_log, XYZZ<F>* 
 // One block per queued bucket: threads stride over its pieces, then a shared-memory tree.
 template <class F>
 __global__ void __launch_bounds__(HEAVY_THREADS)
-k_fixup_heavy(const uint32_t* __restrict__ offsets, int ls_log, XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ PH,
+k_fixup_heavy(const uint32_t* __restrict__ offsets, uint32_t LS, XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ PH,
               const XYZZ<F>* __restrict__ PT, const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ heavy_list) {
     __shared__ XYZZ<F> sh[HEAVY_THREADS];
     const uint32_t count = *heavy_count;
     for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
         const uint32_t b = heavy_list[h];
         const uint32_t o = offsets[b], o2 = offsets[b + 1];
-        const uint32_t t0 = o >> ls_log;
-        const uint32_t np = ((o2 - 1) >> ls_log) - t0 + 1;
+        const uint32_t t0 = o / LS;
+        const uint32_t np = (o2 - 1) / LS - t0 + 1;
+        const bool head_is_tail = (o - t0 * LS) != 0;   // the bucket starts inside chunk t0: its first piece is PT[t0]
         XYZZ<F> acc = XYZZ<F>::identity();
         for (uint32_t p = threadIdx.x; p < np; p += HEAVY_THREADS) {
-            XYZZ<F> q = (p == 0 && (o & ((1u << ls_log) - 1))) ? load_vec(PT + t0) : load_vec(PH + t0 + p);
+            XYZZ<F> q = (p == 0 && head_is_tail) ? load_vec(PT + t0) : load_vec(PH + t0 + p);
             xyzz_add_call(acc, q);
         }
         sh[threadIdx.x] = acc;
@@ -932,7 +931,7 @@ struct MsmPlan {
     const void* table;
     size_t n, total, nW, chunks;
     uint32_t batch, K, KB, tiles;
-    int ls_log;
+    uint32_t chunk_len;  // sorted entries per thread of k_accumulate
     uint32_t parts;      // level-1 partitions of the two-level sort (0 = per-entry atomic counting sort)
     int rounds;          // batched-affine reduction rounds before the XYZZ chunk kernel (0 = none), affine.cuh
     int pair_b;          // outputs per thread in k_pair_round (8 or 16)
@@ -1008,14 +1007,22 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     // >= 4 resident warps per scheduler (148 SMs x 4 SMSPs x 4 warps x 32 lanes = 75 776 threads) in k_accumulate
     // and no longer than ~1/4 of the average bucket (measured: chunks spanning several buckets run ~30 % slower)
     {
-        const size_t target_threads = 75776;
+        const size_t wave_threads = (size_t)(runtime().sm_count > 0 ? runtime().sm_count : 148) * 4 * 128;  // one full wave of k_accumulate
         const size_t m = p.rounds ? (p.nW >> p.rounds) : p.nW;
         const size_t per_bucket = m / (p.KB ? p.KB : 1);
         int l = LS_MIN_LOG;
-        while (l < LS_MAX_LOG && (m >> (l + 1)) >= target_threads && ((size_t)4 << l) < per_bucket) l++;
-        p.ls_log = l;
+        while (l < LS_MAX_LOG && (m >> (l + 1)) >= wave_threads && ((size_t)4 << l) < per_bucket) l++;
+        size_t len = (size_t)1 << l;
+        // shorten the chunks so that the threads fill a whole number of waves (every thread does the same work: a
+        // partly filled last wave costs a full wave's latency on the SMs it touches)
+        if (m >= wave_threads * 16) {
+            const size_t waves = (m + len * wave_threads - 1) / (len * wave_threads);
+            len = (m + waves * wave_threads - 1) / (waves * wave_threads);
+            if (len < 16) len = 16;
+        }
+        p.chunk_len = (uint32_t)len;
     }
-    p.chunks = (p.m_final + ((size_t)1 << p.ls_log) - 1) >> p.ls_log;
+    p.chunks = (p.m_final + p.chunk_len - 1) / p.chunk_len;
     p.tiles = (p.KB + SCAN_TILE - 1) / SCAN_TILE;
     size_t off = 0;
     auto take = [&](size_t bytes) {
@@ -1125,7 +1132,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         SB_KERNEL_CHECK();
     }
     const uint32_t* off_final = offsets + (size_t)R * ((size_t)KB + 1);   // offsets of the entries the chunk kernel sees
-    k_chunk_heads<<<(KB + 255) / 256, 256, 0, st>>>(off_final, KB, p.ls_log, chunk_head);
+    k_chunk_heads<<<(KB + 255) / 256, 256, 0, st>>>(off_final, KB, p.chunk_len, chunk_head);
     sort_scope.reset();
     SB_KERNEL_CHECK();
     const Affine<F>* acc_src = (const Affine<F>*)p.table;
@@ -1158,22 +1165,22 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
             return e ? atoi(e) : 4;
         }();
         if (R > 0)
-            k_accumulate<F, 4, true><<<(unsigned)blocks, 128, 0, st>>>(acc_src, chunk_head, nullptr, off_final, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 4, true><<<(unsigned)blocks, 128, 0, st>>>(acc_src, chunk_head, nullptr, off_final, KB, p.chunk_len, buckets, PH, PT);
         else if (minb == 5)
-            k_accumulate<F, 5, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 5, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.chunk_len, buckets, PH, PT);
         else if (minb == 6)
-            k_accumulate<F, 6, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 6, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.chunk_len, buckets, PH, PT);
         else if (minb == 3)
-            k_accumulate<F, 3, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 3, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.chunk_len, buckets, PH, PT);
         else
-            k_accumulate<F, 4, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.ls_log, buckets, PH, PT);
+            k_accumulate<F, 4, false><<<(unsigned)blocks, 128, 0, st>>>((const Affine<F>*)p.table, chunk_head, eidx, offsets, KB, p.chunk_len, buckets, PH, PT);
         SB_KERNEL_CHECK();
     }
     {
         ProfScope ps(st, PROF_FIXUP, KB);
-        k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
+        k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
-        k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(off_final, p.ls_log, buckets, PH, PT, heavy_count, heavy_list);
+        k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(off_final, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
     }
     {
