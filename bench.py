@@ -326,18 +326,18 @@ def run_gpu(args):
             "roofline": {
                 "kernel": "sb::k_accumulate (MSM bucket accumulation)", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak,
                 "unit": "GB/s", "frac": round(achieved / hbm_peak, 5),
-                "traffic": 3.476e9 if world == 1 else None,
+                "traffic": 3.123e9 if world == 1 else None,
                 "traffic_note": "dram__bytes_read+write of the largest launch (primary W commit, 1 572 864 points, 151 MB algorithmic) from "
-                                "profiles/r1_accumulate_ncu_full_summary.txt: each point is gathered once per window (16 x 64 B table entries) by design; "
-                                "the kernel sits at 9 % of DRAM throughput and is integer-pipe bound",
+                                "profiles/r1_accumulate_s2_ncu_full_summary.txt: each point is gathered once per window (15 x 64 B table entries, a "
+                                "random 64 B gather costs a 128 B DRAM fetch) by design; the kernel sits at 10 % of DRAM throughput and is integer-pipe bound",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "launches": int(acc_n), "avg_launch_ms": round(acc_ms / acc_n, 4) if acc_n else None,
                 "note": "algorithmic 96 B/point; the kernel is integer-pipe bound (SURVEY F7): see int_pipe and DESIGN.md 4.2",
                 "int_pipe": {
                     "achieved_gmadd_per_s": round(acc_madds / (acc_ms * 1e6), 3) if acc_ms else None,
-                    "peak_gmadd_per_s": 6.07,
-                    "frac": round(acc_madds / (acc_ms * 1e6) / 6.07, 4) if acc_ms else None,
-                    "peak_source": "profiles/r1_microbench.txt: serial XYZZ mixed additions on the full chip (IMAD.WIDE issue bound, 65.4 G Montgomery products/s)",
+                    "peak_gmadd_per_s": 6.386,
+                    "frac": round(acc_madds / (acc_ms * 1e6) / 6.386, 4) if acc_ms else None,
+                    "peak_source": "profiles/r1_microbench6_madd_lazy.txt: serial lazy-domain XYZZ mixed additions on the full chip (IMAD.WIDE issue bound, 65.4 G Montgomery products/s)",
                 },
             },
             "breakdown_ms_per_step": breakdown,
