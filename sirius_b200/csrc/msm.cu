@@ -995,7 +995,10 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     {   // two-level partition sort for big inputs (the atomic path stays for tiny / huge bucket counts)
         const uint64_t P = (kb + PART_BUCKETS - 1) >> PART_LO_BITS;
         const bool legal = kb >= 2 * PART_BUCKETS && P <= PART_MAX;
-        const bool want = g_sort_mode == 2 || (g_sort_mode == 0 && p.nW >= ((size_t)1 << 18));
+        // automatic: only up to 256 partitions (<= 65 536 buckets).  With more, a block's 256*W entries spread over so
+        // many partitions that its runs shrink to a few entries (scattered stores again): at 2^23 scalars, c = 19,
+        // 1024 partitions the commit takes 34.4 ms against 23.0 ms with the counting sort (profiles/r1_large_msm_check.txt)
+        const bool want = g_sort_mode == 2 || (g_sort_mode == 0 && p.nW >= ((size_t)1 << 18) && P <= 256);
         p.parts = (legal && want) ? (uint32_t)P : 0u;
     }
     p.rounds = g_affine_rounds >= 0 ? std::min(g_affine_rounds, MAX_AFFINE_ROUNDS) : auto_affine_rounds(p.nW, p.KB);
