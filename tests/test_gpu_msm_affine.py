@@ -114,3 +114,17 @@ def test_sort_paths(sb, oracle, tune, curve, sort):
     s = _scalars(oracle, curve, n, 93, "uniform")
     assert np.array_equal(ck.commit(s), oracle.msm(curve, s, bases))
     ck.close()
+
+
+def test_large_commit_sort_paths_and_linearity():
+    """2^22 bn256 scalars (BASELINE sweep size, window c = 17, 65 536 buckets): the partition sort and the counting sort
+    agree bit for bit and commit(a) + commit(b) == commit(a + b) -- size-independent properties, no CPU MSM
+    (tools/check_large_msm.py, also run by hand at 2^23: profiles/r1_large_msm_check.txt)"""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_large_msm.py"), "22"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "sort paths agree: True" in r.stdout and "commit(a+b): True" in r.stdout
