@@ -12,7 +12,12 @@
  *   - the group law: `CommitmentKey::commit` (src/commitment.rs:81-90) has NO known-answer vector in
  *     the reference ("parity unpinned by KAT"); its result sum_i v_i*ck_i -> affine is mathematically
  *     unique, and tests/ cross-check this file against an independent big-int affine implementation
- *     (oracle/pyref.py).
+ *     (oracle/pyref.py), and
+ *   - PUBLIC known answers from outside both repositories for the bn256 G1 group law the commit is made of: the
+ *     EIP-196 bn256Add / bn256ScalarMul precompile vectors (tests/golden/bn256_g1_kat.json: 5 scalar
+ *     multiplications, 3 additions, the doubling of (1,2)), checked for this file in tests/test_oracle.py and
+ *     for the CUDA path in tests/test_gpu_msm.py.  Grumpkin has no public vectors: it is anchored by the cycle
+ *     identity (its group order is the bn256 base-field modulus: r*G = O).
  *
  * The MSM arithmetic lives in a third-party crate that is not vendored: halo2_proofs
  * (github.com/snarkify/halo2, branch snarkify/dev.scroll.alpha.2, commit unpinned -- Cargo.toml:44-46).

@@ -147,3 +147,35 @@ def test_bn256_public_doubling_vector(oracle):
         m1 = R.to_mont_limbs([R.CURVE_SCALAR[curve] - 1], R.CURVE_SCALAR[curve])
         got = oracle.msm(curve, m1, R.points_to_limbs([g], curve))
         assert R.limbs_to_points(got, curve) == [R.ec_neg(g, curve)]
+
+
+def _bn256_kat():
+    import json, os
+
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "bn256_g1_kat.json")))
+
+
+def test_msm_oracle_public_precompile_vectors(oracle):
+    """The C oracle's commit on the public EIP-196 bn256Add / bn256ScalarMul known answers (tests/golden/
+    bn256_g1_kat.json): commit([k], [P]) = k*P and commit([1, 1], [P, Q]) = P + Q.  These pin the MSM oracle to
+    vectors that come from outside both this repository and the reference."""
+    kat = _bn256_kat()
+    C = R.CURVE_BN256
+    h = lambda s: int(s, 16)
+    for v in kat["scalar_mul"]:
+        P, exp = (h(v["x"]), h(v["y"])), (h(v["ex"]), h(v["ey"]))
+        k = R.to_mont_limbs([h(v["k"]) % R.FR], R.FR)
+        b = R.points_to_limbs([P], C)
+        assert R.limbs_to_points(oracle.msm(C, k, b), C) == [exp], v["name"]
+        assert R.limbs_to_points(oracle.msm_naive(C, k, b), C) == [exp], v["name"]
+    ones = R.to_mont_limbs([1, 1], R.FR)
+    for v in kat["add"]:
+        P, Q, exp = (h(v["x1"]), h(v["y1"])), (h(v["x2"]), h(v["y2"])), (h(v["ex"]), h(v["ey"]))
+        assert R.limbs_to_points(oracle.msm(C, ones, R.points_to_limbs([P, Q], C)), C) == [exp], v["name"]
+    # a 6-term commitment built from the vectors: sum k_i * P_i with the answers combined by the big-int group law
+    pts = [(h(v["x"]), h(v["y"])) for v in kat["scalar_mul"]]
+    ks = [h(v["k"]) % R.FR for v in kat["scalar_mul"]]
+    exp = None
+    for v in kat["scalar_mul"]:
+        exp = R.ec_add(exp, (h(v["ex"]), h(v["ey"])), C)
+    assert R.limbs_to_points(oracle.msm(C, R.to_mont_limbs(ks, R.FR), R.points_to_limbs(pts, C)), C) == [exp]
