@@ -52,8 +52,8 @@ def shapes(side):
 
 def workload_config(n_gpus):
     return {
-        "workload": "benches/sangria_poseidon k=17 bn256/grumpkin: fold_step hot path "
-                    "(MSM 1572864 + 6x131072 bn256, MSM 917504 + 5x131072 grumpkin, 11 cross-term vectors, W/E folds)",
+        "workload": f"benches/sangria_poseidon k={K_TABLE} bn256/grumpkin: fold_step hot path "
+                    f"(MSM {12 << K_TABLE} + 6x{1 << K_TABLE} bn256, MSM {7 << K_TABLE} + 5x{1 << K_TABLE} grumpkin, 11 cross-term vectors, W/E folds)",
         "k": K_TABLE,
         "ck_log2": CK_LOG,
         "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks, all-gather of partial sums per commitment",
@@ -130,7 +130,7 @@ def build_side_gpu(side, rank, world, stream):
         sharding.check_rotations_row_local(P.GraphEvaluator.new(cg.homogeneous, modulus).rotations)
     # commitment key restricted to this rank's rows: ck[col * n + row] for row in the slice, column-major
     lib = _lib.load()
-    assert nadv * n <= (1 << CK_LOG), "the 2^21 key must cover W (only the prefix W needs is materialised)"
+    assert nadv * n <= (1 << CK_LOG), "the 2^(k+4) key must cover W (only the prefix W needs is materialised)"
     d_bases = torch.zeros((nadv * n_loc, 8), dtype=torch.int64, device="cuda")
     g = curves.generator_limbs(side["curve"])
     for col, (first, count) in enumerate(sharding.key_segments(nadv, n, rank, world)):
@@ -525,13 +525,19 @@ def run_reference(args):
 
 
 def main():
+    global K_TABLE, CK_LOG, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--k", type=int, default=17, help="table size 2^k rows (default 17 = BASELINE configs[1]; 20 = the north star's larger case, "
+                                                       "same shapes; needs ~45 GB of window tables)")
     args = ap.parse_args()
+    if args.k != K_TABLE:   # same circuit shapes at another table size (the key covers 16 * 2^k generators, as at k = 17)
+        K_TABLE, CK_LOG = args.k, args.k + 4
+        METRIC = f"sangria_poseidon k={args.k} IVC fold_step prover hot-path time"
     if args.impl == "reference":
         run_reference(args)
     else:
