@@ -955,13 +955,9 @@ static int g_pair_b = []() {
 }();
 constexpr int MAX_AFFINE_ROUNDS = 8;
 
-// Automatic choice: a round pays while it still fills the chip with ~2 blocks per SM (it costs one block-wide
-// inversion of latency whatever its size) and buckets keep >= 8 entries for the chunk kernel behind it.
-static int auto_affine_rounds(size_t nW, size_t KB) {
-    (void)nW;
-    (void)KB;
-    return 0;  // enabled per measurement (profiles/): see make_plan
-}
+// Automatic choice (-1): no affine rounds -- on B200 a round is memory-latency bound and loses to the XYZZ chunk kernel at
+// every measured shape (profiles/r1_affine_sweep_bn256.txt); the rounds run only when asked for.
+static int auto_affine_rounds() { return 0; }
 
 static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars, MsmPlan& p) {
     p = MsmPlan{};
@@ -1001,7 +997,7 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
         const bool want = g_sort_mode == 2 || (g_sort_mode == 0 && p.nW >= ((size_t)1 << 18) && P <= 256);
         p.parts = (legal && want) ? (uint32_t)P : 0u;
     }
-    p.rounds = g_affine_rounds >= 0 ? std::min(g_affine_rounds, MAX_AFFINE_ROUNDS) : auto_affine_rounds(p.nW, p.KB);
+    p.rounds = g_affine_rounds >= 0 ? std::min(g_affine_rounds, MAX_AFFINE_ROUNDS) : auto_affine_rounds();
     p.pair_b = g_pair_b == 8 ? 8 : 16;
     // entries left for the chunk kernel: every round halves each bucket, rounding up
     p.m_final = p.nW;
