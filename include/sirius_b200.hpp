@@ -14,6 +14,7 @@
 // (text of sb_last_error) when the CUDA library cannot run.  Header-only; link with libsirius_b200.so.
 #pragma once
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -136,6 +137,28 @@ class CommitmentKey {
     std::vector<Affine> ck_;          // Box<[C]>
     mutable sb_ck_t handle_ = nullptr;  // device-resident window tables, built at the first commit
 };
+
+// `setup_smallest_key(k_table_size, cs, tag)` (src/commitment.rs:172-186): the key must cover one witness round
+// (advice + 5 columns per lookup) and the selector + fixed columns.  smallest_power mirrors the reference's
+// `((n * 2^K) as f64).log2().ceil() as usize` (n = 0: -inf casts to 0).
+inline size_t smallest_power(size_t n, uint32_t K) {
+    const double v = (double)n * (double)((uint64_t)1 << K);
+    if (v == 0.0) return 0;
+    const double w = std::ceil(std::log2(v));
+    return w < 0 ? 0 : (size_t)w;
+}
+inline size_t smallest_key_log2(uint32_t k_table_size, size_t num_advice_columns, size_t num_lookups, size_t num_selectors,
+                                size_t num_fixed_columns) {
+    const size_t p1 = smallest_power(num_advice_columns + 5 * num_lookups, k_table_size);
+    const size_t p2 = smallest_power(num_selectors + num_fixed_columns, k_table_size);
+    return p1 > p2 ? p1 : p2;
+}
+inline CommitmentKey setup_smallest_key(Curve curve, uint32_t k_table_size, size_t num_advice_columns, size_t num_lookups,
+                                        size_t num_selectors, size_t num_fixed_columns, const std::string& tag,
+                                        const std::function<std::vector<Affine>(size_t, const std::string&)>& setup) {
+    // `setup` stands in for CommitmentKey::setup (hash_to_curve of the un-vendored halo2curves)
+    return CommitmentKey(curve, setup(smallest_key_log2(k_table_size, num_advice_columns, num_lookups, num_selectors, num_fixed_columns), tag));
+}
 
 // ------------------------------------------------------------------------------------------------ fft (bn256 Fr)
 namespace fft {

@@ -17,4 +17,4 @@ from ._lib import (  # noqa: F401
     SiriusB200Error,
     load,
 )
-from .commitment import CommitmentKey, TooLongInput  # noqa: F401
+from .commitment import CommitmentKey, TooLongInput, setup_smallest_key, smallest_key_log2  # noqa: F401

@@ -163,3 +163,30 @@ class CommitmentKey:
             self.close()
         except Exception:
             pass
+
+
+def smallest_power(n: int, K: int) -> int:
+    """`smallest_power` inside `setup_smallest_key` (src/commitment.rs:177-180): the smallest w with 2^w >= n * 2^K,
+    computed as the reference does it, `((n * 2^K) as f64).log2().ceil() as usize` (n = 0 gives -inf -> 0)."""
+    import math
+
+    v = float(n * (1 << K))
+    return 0 if v == 0.0 else max(0, math.ceil(math.log2(v)))
+
+
+def smallest_key_log2(k_table_size: int, num_advice_columns: int, num_lookups: int, num_selectors: int, num_fixed_columns: int) -> int:
+    """The `k` that `setup_smallest_key` passes to `CommitmentKey::setup` (src/commitment.rs:182-185): the key must
+    cover a witness round (advice + 5 columns per lookup) and the selector + fixed columns."""
+    p1 = smallest_power(num_advice_columns + 5 * num_lookups, k_table_size)
+    p2 = smallest_power(num_selectors + num_fixed_columns, k_table_size)
+    return max(p1, p2)
+
+
+def setup_smallest_key(curve: int, k_table_size: int, num_advice_columns: int, num_lookups: int, num_selectors: int, num_fixed_columns: int,
+                       tag: str, setup) -> CommitmentKey:
+    """`setup_smallest_key(k_table_size, cs, tag)` (src/commitment.rs:172-186) with the ConstraintSystem's four counts
+    spelled out.  `setup(k, tag) -> uint64[2^k, 8]` stands in for `CommitmentKey::setup`, whose hash_to_curve lives in
+    the un-vendored halo2curves."""
+    k = smallest_key_log2(k_table_size, num_advice_columns, num_lookups, num_selectors, num_fixed_columns)
+    return CommitmentKey(curve, setup(k, tag))
+

@@ -66,6 +66,9 @@ int main(int argc, char** argv) {
         fft::get_omega_or_inv(fft::S + 1, false);
         REQUIRE(false);
     } catch (const std::invalid_argument&) {}
+    // setup_smallest_key's size rule (src/commitment.rs:172-186) at the benches' shapes
+    REQUIRE(smallest_power(12, 17) == 21 && smallest_power(7, 17) == 20 && smallest_power(16, 17) == 21 && smallest_power(0, 17) == 0);
+    REQUIRE(smallest_key_log2(17, 12, 0, 0, 26) == 22 && smallest_key_log2(17, 7, 0, 0, 15) == 21 && smallest_key_log2(10, 3, 1, 2, 1) == 13);
     std::printf("host ok\n");
 
     // ---- everything that computes goes through libsirius_b200.so

@@ -103,3 +103,19 @@ def test_header_is_plain_c():
     src = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)  # declarations only; comments may name the types
     src = re.sub(r"//[^\n]*", "", src)
     assert "torch" not in src and "cudaStream_t" not in src and "at::" not in src
+
+
+def test_setup_smallest_key_size_rule():
+    """`setup_smallest_key` (src/commitment.rs:172-186): k = max over (advice + 5*lookups, selectors + fixed) of
+    ceil(log2(n * 2^K)), with the reference's float arithmetic"""
+    from sirius_b200.commitment import smallest_key_log2, smallest_power
+
+    assert smallest_power(12, 17) == 21 and smallest_power(7, 17) == 20 and smallest_power(16, 17) == 21
+    assert smallest_power(1, 17) == 17 and smallest_power(0, 17) == 0 and smallest_power(3, 0) == 2
+    assert smallest_key_log2(17, 12, 0, 0, 26) == 22      # sangria_poseidon primary: 26 fixed columns dominate
+    assert smallest_key_log2(17, 7, 0, 0, 15) == 21       # secondary
+    assert smallest_key_log2(10, 3, 1, 2, 1) == 13        # 3 advice + 5 lookup columns = 8 -> 2^13
+    for n in range(1, 70):
+        for K in (0, 5, 17, 20):
+            w = smallest_power(n, K)
+            assert (1 << w) >= n << K and (w == 0 or (1 << (w - 1)) < n << K)
