@@ -16,7 +16,7 @@
  *   - PUBLIC known answers from outside both repositories for the bn256 G1 group law the commit is made of: the
  *     EIP-196 bn256Add / bn256ScalarMul precompile vectors (tests/golden/bn256_g1_kat.json: 5 scalar
  *     multiplications, 3 additions, the doubling of (1,2)), checked for this file in tests/test_oracle.py and
- *     for the CUDA path in tests/test_gpu_msm.py.  Grumpkin has no public vectors: it is anchored by the cycle
+ *     for the CUDA path in tests/test_zy_gpu_public_vectors.py.  Grumpkin has no public vectors: it is anchored by the cycle
  *     identity (its group order is the bn256 base-field modulus: r*G = O).
  *
  * The MSM arithmetic lives in a third-party crate that is not vendored: halo2_proofs
