@@ -88,6 +88,22 @@ class CommitmentKey {
         return out;
     }
     Affine commit(const std::vector<Scalar>& v) const { return commit(v.data(), v.size()); }
+    // [commit(v) for v in vs] as ONE device pipeline (all vectors of the same length): the d cross-term commits of
+    // VanillaFS::commit_cross_terms (src/nifs/sangria/mod.rs:151-154)
+    std::vector<Affine> commit_batch(const std::vector<std::vector<Scalar>>& vs) const {
+        std::vector<Affine> out(vs.size());
+        if (vs.empty()) return out;
+        const size_t n = vs[0].size();
+        std::vector<const uint64_t*> ptrs;
+        for (const auto& v : vs) {
+            if (v.size() != n) throw std::invalid_argument("commit_batch: vectors must have equal length");
+            ptrs.push_back(reinterpret_cast<const uint64_t*>(v.data()));
+        }
+        if (n > ck_.size()) throw TooLongInput(n, ck_.size());
+        ensure_registered();
+        check(sb_msm_batch(handle_, ptrs.data(), n, vs.size(), reinterpret_cast<uint64_t*>(out.data())));
+        return out;
+    }
 
     // `save_to_file`: the key as a memory image, 64 bytes per point (src/commitment.rs:99-116)
     void save_to_file(const std::string& file_path) const {

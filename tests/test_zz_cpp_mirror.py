@@ -125,3 +125,132 @@ def test_cpp_mirror_on_the_device(binary, inputs, oracle):
     out, _ = run(binary, inputs)
     check_host_part(out)
     check_device_part(out, oracle, inputs)
+
+
+# ---------------------------------------------------------------------------------------------- expression compiler
+@pytest.fixture(scope="module")
+def expr_binary(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("cppexpr") / "cpp_expr_check")
+    libdir = os.path.join(ROOT, "sirius_b200")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-o", out, os.path.join(HERE, "host", "cpp_expr_check.cpp"),
+                           "-L" + libdir, "-lsirius_b200", "-Wl,-rpath," + libdir])
+    return out
+
+
+def _fmt_program(ev):
+    lines = ["rotations" + "".join(f" {r}" for r in ev.rotations), "constants" + "".join(f" {c:064x}" for c in ev.constants)]
+    for op, a, b, target in ev.calculations:
+        lines.append(f"calc {op} {a[0]} {a[1]} {a[2]} {b[0]} {b[1]} {b[2]} {target}" if b is not None else f"calc {op} {a[0]} {a[1]} {a[2]} - {target}")
+    return lines
+
+
+@pytest.mark.parametrize("T_list", [[2], [5], [5, 3]])
+def test_cpp_expression_compiler_matches_python_and_oracle(expr_binary, T_list):
+    """include/sirius_b200_expr.hpp (Expression, homogeneous, compress_expression, CompressedGates, GraphEvaluator::new,
+    main_gate_expression) emits the calculation lists of the Python mirror -- which tests/test_host_logic.py ties to the
+    oracle -- for the MainGate structures of the benches, for both the compressed gate and its homogeneous form"""
+    from sirius_b200 import polynomial as P
+
+    r = subprocess.run([expr_binary, ",".join(str(t) for t in T_list)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout.splitlines()
+    nfix, nadv = sum(2 * T + 5 for T in T_list), sum(T + 2 for T in T_list)
+    gates, fb, ab = [], 0, 0
+    for T in T_list:
+        gates.append(P.main_gate_expression(T, fb, ab, 0, nfix))
+        fb, ab = fb + 2 * T + 5, ab + T + 2
+    cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_fixed=nfix, num_advice=nadv))
+    assert out[0] == f"degree {cg.degree} num_challenges {cg.ctx.num_challenges}"
+    pos = 1
+    for which, expr in enumerate((cg.compressed, cg.homogeneous)):
+        ev = P.GraphEvaluator.new(expr, P.FR)
+        assert out[pos] == f"program {which} calcs {len(ev.calculations)} intermediates {ev.num_intermediates}"
+        exp = _fmt_program(ev)
+        assert out[pos + 1: pos + 1 + len(exp)] == exp
+        pos += 1 + len(exp)
+        assert out[pos] == f"const2_mont {(2 << 256) % P.FR:064x}"     # constants cross the ABI in Montgomery form
+        pos += 1
+    # Negated constant / Scaled / Sub / rotation, over Fq
+    e = (P.Expression.Polynomial(3, 1) - P.Expression.Constant(5)) * 7 + (-P.Expression.Constant(9)) * P.Expression.Challenge(0)
+    ev = P.GraphEvaluator.new(e, P.FQ)
+    assert out[pos] == f"extra calcs {len(ev.calculations)}"
+    assert out[pos + 1:] == _fmt_program(ev)[1:]
+
+
+# ---------------------------------------------------------------------------------------------- commit_cross_terms
+CT_T_LIST, CT_K = [2, 2], 4      # two MainGate<2> gates (a compression challenge + the homogenising one), 16 rows
+
+
+@pytest.fixture(scope="module")
+def ct_binary(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("cppct") / "cpp_cross_terms_check")
+    libdir = os.path.join(ROOT, "sirius_b200")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-o", out, os.path.join(HERE, "host", "cpp_cross_terms_check.cpp"),
+                           "-L" + libdir, "-lsirius_b200", "-Wl,-rpath," + libdir])
+    return out
+
+
+@pytest.fixture(scope="module")
+def ct_inputs(oracle, tmp_path_factory):
+    from oracle import expr_ref as E
+
+    d = tmp_path_factory.mktemp("cppct_in")
+    n = 1 << CT_K
+    nfix, nadv = sum(2 * T + 5 for T in CT_T_LIST), sum(T + 2 for T in CT_T_LIST)
+    gates, fb, ab = [], 0, 0
+    for T in CT_T_LIST:
+        gates.append(E.main_gate_expression(T, fb, ab, 0, nfix))
+        fb, ab = fb + 2 * T + 5, ab + T + 2
+    cg = E.CompressedGates(gates, E.Ctx(num_fixed=nfix, num_advice=nadv))
+    nch = cg.ctx.num_challenges
+    key = oracle.running_bases(R.CURVE_BN256, n)
+    fixed = [oracle.random_field(R.FIELD_FR, 300 + j, n) for j in range(nfix)]
+    W1, W2 = oracle.random_field(R.FIELD_FR, 31, nadv * n), oracle.random_field(R.FIELD_FR, 32, nadv * n)
+    U1c, U1u, U2c = oracle.random_field(R.FIELD_FR, 33, nch - 1), oracle.random_field(R.FIELD_FR, 34, 1), oracle.random_field(R.FIELD_FR, 35, nch - 1)
+    path = str(d / "ct_inputs.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([len(CT_T_LIST)] + CT_T_LIST + [CT_K, n], dtype=np.uint64).tobytes())
+        for a in [key] + fixed + [W1, W2, U1c, U1u, U2c]:
+            f.write(np.ascontiguousarray(a, dtype=np.uint64).tobytes())
+    # expected: the reference's literal path (one GraphEvaluator per degree-grouped expression), Python integers
+    m = R.FR
+    S = E.Structure(CT_K, [], [R.from_mont_limbs(c, m) for c in fixed], nadv, 0, cg, m)
+    exp_T = E.commit_cross_terms_eval(S, R.from_mont_limbs(U1c, m), R.from_mont_limbs(U1u, m)[0], [R.from_mont_limbs(W1, m)],
+                                      R.from_mont_limbs(U2c, m), [R.from_mont_limbs(W2, m)])
+    return dict(path=path, key=key, exp_T=exp_T, degree=cg.degree, nch=nch)
+
+
+def _check_cross_terms(out_text, ct_inputs, oracle):
+    lines = out_text.splitlines()
+    assert lines[0] == f"degree {ct_inputs['degree']} num_challenges {ct_inputs['nch']}"
+    assert lines[-1] == "device ok", lines[-1]
+    T, C = {}, {}
+    for line in lines[1:-1]:
+        parts = line.split()
+        (T if parts[0] == "cross_term" else C)[int(parts[1])] = words(parts[2:])
+    assert len(T) == len(C) == ct_inputs["degree"]
+    for j, exp in enumerate(ct_inputs["exp_T"]):
+        got = T[j].reshape(-1, 4)
+        assert R.from_mont_limbs(got, R.FR) == exp, f"cross term {j + 1}"
+        assert np.array_equal(C[j], oracle.msm(R.CURVE_BN256, got, ct_inputs["key"])), f"commitment of cross term {j + 1}"
+
+
+def test_cpp_commit_cross_terms_against_oracle_stub(ct_binary, ct_inputs, oracle, tmp_path):
+    """VanillaFS::commit_cross_terms of the C++ mirror (structure registration, program upload, round vectors and
+    challenge vectors in the reference's order, batched commit) executed against the oracle-backed ABI stub and compared
+    with the reference's literal degree-grouped evaluation (oracle/expr_ref.py) + the oracle MSM"""
+    so = tmp_path / "libsirius_b200.so"
+    subprocess.check_call(["/usr/bin/gcc", "-O1", "-shared", "-fPIC", "-o", str(so), os.path.join(HERE, "host", "fake_sirius_b200.c"),
+                           "-L" + os.path.join(ROOT, "oracle"), "-lsirius_oracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+    e = dict(os.environ)
+    e["LD_LIBRARY_PATH"] = str(tmp_path)
+    r = subprocess.run([ct_binary, ct_inputs["path"]], capture_output=True, text=True, timeout=300, env=e)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_cross_terms(r.stdout, ct_inputs, oracle)
+
+
+@pytest.mark.gpu
+def test_cpp_commit_cross_terms_on_the_device(ct_binary, ct_inputs, oracle):
+    r = subprocess.run([ct_binary, ct_inputs["path"]], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    _check_cross_terms(r.stdout, ct_inputs, oracle)
