@@ -1,25 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- one Sangria IVC fold step's prover hot path at the shapes of benches/sangria_poseidon (k = 17).
+"""bench.py -- the Sangria IVC fold step's prover hot path at the shapes of benches/sangria_poseidon.
 
 A "step" is one pass of the hot path of `IVC::fold_step` (reference
 src/ivc/sangria/incrementally_verifiable_computation.rs:428-635) over one batch of synthetic witness
-columns, in the reference's call order:
+columns, in the reference's call order (sirius_b200/workload.py):
 
-  1. VanillaFS::prove, secondary side (grumpkin; A=7, F=15, 1 gate, d=5):
-       commit_cross_terms = 5 cross-term vectors over 2^17 rows + 5 commits of 2^17 scalars, then W/E fold
-  2. generate_plonk_trace, primary side (bn256): commit W, 12*2^17 = 1 572 864 scalars
+  1. VanillaFS::prove, secondary side (grumpkin; A=7, F=15, 1 gate, d=5): 5 cross-term vectors + 5 commits of 2^k, W/E fold
+  2. generate_plonk_trace, primary side (bn256): commit W, 12*2^k scalars
   3. VanillaFS::prove, primary side (bn256; A=12, F=26, 2 gates, d=6): 6 cross terms + 6 commits + folds
-  4. generate_plonk_trace, secondary side: commit W, 7*2^17 = 917 504 scalars
+  4. generate_plonk_trace, secondary side: commit W, 7*2^k scalars
 
-halo2 circuit synthesis (CPU, out of scope per SURVEY section 2) is not part of the step.  Every commitment is
-copied back to the host and synchronised before the next stage, as the random oracle requires.
+halo2 circuit synthesis (CPU, out of scope per SURVEY section 2) is not part of the step.  Every commitment is copied
+back to the host and synchronised before the next stage, as the random oracle requires.
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload sangria_poseidon|cyclefold_poseidon|msm_sweep]
 
-`value`  : ms per step, all inputs resident in HBM.
-`e2e`    : ms per step with that step's fresh witness columns copied host->device (pinned) inside the timed region.
-N > 1    : rows are sharded across ranks (strong scaling); each commitment is one NCCL all-gather of 128-byte
-           partial sums plus a combine kernel.
+`value`        : ms per step at k = 17 (BASELINE configs[1]), all inputs resident in HBM.
+`e2e`          : ms per step with that step's fresh witness columns copied host->device (pinned) inside the timed
+                 region and the 13 commitments read back: the device-resident prover state of SURVEY 8f-1.
+`e2e_host_abi` : the same step through the host-buffer entry points a verbatim Rust shim binds (CommitmentKey.commit,
+                 VanillaFS.commit_cross_terms, RelaxedPlonkWitness.fold on PAGEABLE host arrays; T, folded W and E copied
+                 back), N = 1 only.
+`verified`     : before timing, one step of the exact timed objects is compared bit for bit (13 commitments, folded W
+                 and E on both sides) with the CPU restatement of the reference on identical inputs.
+`extra.k20`    : the same measurement at k = 20, the table size the north star quotes its target on.
+`stages`       : the rest of the measured bench iteration (benches/sangria_poseidon.rs:159-175): `new` and `verify` legs.
+N > 1          : rows are sharded across ranks (strong scaling); each commitment group is one exchange of 128-byte
+                 partial sums plus a combine kernel.
 --impl reference : the CPU restatement of the reference (oracle/, OpenMP on all host cores) on the same shapes.
 """
 from __future__ import annotations
@@ -37,27 +44,21 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 K_TABLE = 17
-PRIMARY = dict(name="primary", curve=0, field=0, T_list=[5, 3])   # bn256 / Fr : MainGate<5> + Poseidon MainGate<3>
-SECONDARY = dict(name="secondary", curve=1, field=1, T_list=[5])  # grumpkin / Fq : MainGate<5> (trivial step circuit)
-CK_LOG = 21                                                       # benches/sangria_poseidon.rs:26-30
-METRIC = "sangria_poseidon k=17 IVC fold_step prover hot-path time"
 SEED = 0x5349524955530000
 
 
-def shapes(side):
-    nfix = sum(2 * T + 5 for T in side["T_list"])
-    nadv = sum(T + 2 for T in side["T_list"])
-    return nfix, nadv
+def metric_name(k):
+    return f"sangria_poseidon k={k} IVC fold_step prover hot-path time"
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, k):
     return {
-        "workload": f"benches/sangria_poseidon k={K_TABLE} bn256/grumpkin: fold_step hot path "
-                    f"(MSM {12 << K_TABLE} + 6x{1 << K_TABLE} bn256, MSM {7 << K_TABLE} + 5x{1 << K_TABLE} grumpkin, 11 cross-term vectors, W/E folds)",
-        "k": K_TABLE,
-        "ck_log2": CK_LOG,
-        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks, all-gather of partial sums per commitment",
-        "l2": "inputs larger than L2 (2 x 2 GiB window tables gathered at random; 0.4 GB of per-step scratch)",
+        "workload": f"benches/sangria_poseidon k={k} bn256/grumpkin: fold_step hot path "
+                    f"(MSM {12 << k} + 6x{1 << k} bn256, MSM {7 << k} + 5x{1 << k} grumpkin, 11 cross-term vectors, W/E folds)",
+        "k": k,
+        "ck_log2": k + 4,
+        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks, one exchange of 128-byte partial sums per commitment group",
+        "l2": "inputs larger than L2 (window tables of several GB gathered at random; 0.4 GB of per-step scratch at k=17)",
     }
 
 
@@ -98,308 +99,7 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
-def build_side_gpu(side, rank, world, stream):
-    """Structure + key + device session for one curve, restricted to this rank's rows."""
-    import numpy as np
-    import torch
-
-    import sirius_b200
-    from sirius_b200 import _lib, curves, device
-    from sirius_b200 import polynomial as P
-    from sirius_b200 import sangria as SG
-    import ctypes
-
-    nfix, nadv = shapes(side)
-    gates, fb, ab = [], 0, 0
-    for T in side["T_list"]:
-        gates.append(P.main_gate_expression(T, fb, ab, 0, nfix))
-        fb += 2 * T + 5
-        ab += T + 2
-    cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_fixed=nfix, num_advice=nadv))
-    from sirius_b200 import sharding
-
-    n = 1 << K_TABLE
-    row0, n_loc = sharding.row_slice(rank, world, n)
-    k_loc = n_loc.bit_length() - 1
-    modulus = curves.SCALAR_FIELD[side["curve"]]
-    # fixed columns: synthetic uniform, generated in HBM then registered (register copies from host memory)
-    fixed = [device.random_field_device(n_loc, SEED + 1000 * side["curve"] + 10 * rank + j).cpu().numpy().view(np.uint64) for j in range(nfix)]
-    S = SG.PlonkStructure(side["field"], modulus, k_loc, [], fixed, nadv, 0, cg)
-    if world > 1:
-        sharding.check_rotations_row_local(P.GraphEvaluator.new(cg.homogeneous, modulus).rotations)
-    # commitment key restricted to this rank's rows: ck[col * n + row] for row in the slice, column-major
-    lib = _lib.load()
-    assert nadv * n <= (1 << CK_LOG), "the 2^(k+4) key must cover W (only the prefix W needs is materialised)"
-    d_bases = torch.zeros((nadv * n_loc, 8), dtype=torch.int64, device="cuda")
-    g = curves.generator_limbs(side["curve"])
-    for col, (first, count) in enumerate(sharding.key_segments(nadv, n, rank, world)):
-        _lib.check(lib.sb_index_multiples_device(side["curve"], g.ctypes.data_as(_lib.u64p), first, count,
-                                                 ctypes.c_void_p(d_bases.data_ptr() + col * n_loc * 64), ctypes.c_void_p(stream.cuda_stream)))
-    stream.synchronize()
-    # several window widths per key: each commit picks the cheapest one for its size (the W commits want wide
-    # windows, the batched cross-term commits of 2^17/world scalars narrow ones)
-    windows = [int(x) for x in os.environ.get("SB_BENCH_WINDOWS", "16,13,15,17").split(",")]
-    ck = sirius_b200.CommitmentKey.from_device(side["curve"], d_bases.data_ptr(), nadv * n_loc, window_bits=windows[0], stream=stream.cuda_stream)
-    for wb in windows[1:]:
-        ck.add_window(wb, stream.cuda_stream)
-    stream.synchronize()
-    del d_bases
-    sess = device.DeviceSangriaSide(S, ck, stream)
-    with torch.cuda.stream(stream):
-        sess.W_acc.copy_(device.random_field_device(nadv * n_loc, SEED + 7 + side["curve"] + 100 * rank))
-        sess.E_acc.copy_(device.random_field_device(n_loc, SEED + 8 + side["curve"] + 100 * rank))
-        sess.W_in.copy_(device.random_field_device(nadv * n_loc, SEED + 9 + side["curve"] + 100 * rank))
-    host_W = sess.W_in.cpu().pin_memory()
-    nch = cg.ctx.num_challenges - 1
-    ch = device.random_field_device(2 * nch + 2, SEED + 11 + side["curve"]).cpu().numpy().view(np.uint64)
-    extra = dict(host_W=host_W, c1=ch[:nch], c2=ch[nch:2 * nch], u1=ch[2 * nch], r=ch[2 * nch + 1], nadv=nadv, n_loc=n_loc)
-    return sess, extra
-
-
-class Combiner:
-    """N > 1: all-gather the XYZZ partial sums of a commitment group and add them."""
-
-    def __init__(self, world, stream):
-        import torch
-
-        self.world, self.stream, self.torch = world, stream, torch
-        self.bufs = {}
-
-    def _buffers(self, batch):
-        torch = self.torch
-        if batch not in self.bufs:
-            self.bufs[batch] = (torch.zeros((batch, 16), dtype=torch.int64, device="cuda"),
-                                torch.zeros((self.world, batch, 16), dtype=torch.int64, device="cuda"),
-                                torch.zeros((batch, 8), dtype=torch.int64, device="cuda"))
-        return self.bufs[batch]
-
-    def commit(self, sess, d_scalars, n, batch, h_out):
-        import ctypes
-
-        import torch
-        import torch.distributed as dist
-
-        from sirius_b200 import _lib
-
-        lib = _lib.load()
-        part, gathered, out = self._buffers(batch)
-        sess.ck.commit_batch_device(d_scalars, n, n, batch, 0, part.data_ptr(), self.stream.cuda_stream)
-        with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(gathered, part)
-        _lib.check(lib.sb_msm_combine_batch_device(sess.ck.curve, ctypes.c_void_p(gathered.data_ptr()), self.world, batch, batch,
-                                                   ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(self.stream.cuda_stream)))
-        with torch.cuda.stream(self.stream):
-            h_out.copy_(out.view(h_out.shape), non_blocking=True)
-        self.stream.synchronize()
-
-
-def gpu_step(sides, extras, upload, combiner):
-    """One fold_step hot path.  Returns bytes copied host->device."""
-    prim, sec = sides
-    ep, es = extras
-    h2d = 0
-
-    def prove(sess, ex):
-        if combiner is None:
-            sess.commit_cross_terms(ex["c1"], ex["u1"], ex["c2"])
-        else:
-            import ctypes
-            import numpy as np
-
-            from sirius_b200 import _lib
-
-            lib = _lib.load()
-            c1, c2 = sess.challenge_vectors(ex["c1"], ex["u1"], ex["c2"])
-            _lib.check(lib.sb_cross_terms_device(sess.S._hom_prog._h, sess.d, sess.S._cols, sess._cols(sess.W_acc), sess._cols(sess.W_in), sess.A,
-                                                 c1.ctypes.data_as(_lib.u64p), c2.ctypes.data_as(_lib.u64p), c1.shape[0],
-                                                 ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(sess.stream.cuda_stream)))
-            combiner.commit(sess, sess.T.data_ptr(), sess.n, sess.d, sess.h_commit_T)
-        sess.fold(ex["r"])
-
-    def commit_w(sess, ex):
-        nonlocal h2d
-        if upload:
-            h2d += sess.upload_incoming(ex["host_W"])
-        if combiner is None:
-            sess.commit_incoming()
-        else:
-            combiner.commit(sess, sess.W_in.data_ptr(), sess.A * sess.n, 1, sess.h_commit_W)
-
-    prove(sec, es)       # 1. fold the secondary accumulator
-    commit_w(prim, ep)   # 2. primary trace: commit W
-    prove(prim, ep)      # 3. fold the primary accumulator
-    commit_w(sec, es)    # 4. secondary trace: commit W
-    return h2d
-
-
-def run_gpu(args):
-    import torch
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    import sirius_b200
-    from sirius_b200 import _lib
-
-    lib = sirius_b200.load()
-    _lib.check(lib.sb_init(local_rank))
-    if world > 1:
-        import torch.distributed as dist
-
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the one JSON line (NCCL prints its banner there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.Stream()
-    prim, ep = build_side_gpu(PRIMARY, rank, world, stream)
-    sec, es = build_side_gpu(SECONDARY, rank, world, stream)
-    combiner = Combiner(world, stream) if world > 1 else None
-    sides, extras = (prim, sec), (ep, es)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(upload):
-        for _ in range(args.warmup):
-            gpu_step(sides, extras, upload, combiner)
-        barrier()
-        import ctypes
-
-        NT = 10
-        ms_arr, un_arr, ln_arr = (ctypes.c_double * NT)(), (ctypes.c_uint64 * NT)(), (ctypes.c_uint64 * NT)()
-        lib.sb_profile_enable(1)
-        lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
-        launches0 = lib.sb_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        h2d = 0
-        for _ in range(args.steps):
-            h2d += gpu_step(sides, extras, upload, combiner)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        _lib.check(lib.sb_profile_collect(ms_arr, un_arr, ln_arr))
-        lib.sb_profile_enable(0)
-        tags = ["decompose", "sort", "accumulate", "fixup", "reduce", "finalize", "cross_terms", "fold", "ntt", "protogalaxy"]
-        breakdown = {t: round(ms_arr[i] / args.steps, 4) for i, t in enumerate(tags) if ln_arr[i]}
-        launches = lib.sb_launch_count() - launches0
-        if world > 1:
-            import torch.distributed as dist
-
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / args.steps, h2d // max(1, args.steps), launches // max(1, args.steps), (ms_arr[2], un_arr[2], ln_arr[2]), breakdown
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms_dev, _, launches, prof, breakdown = timed(upload=False)
-    ms_e2e, h2d_bytes, _, _, _ = timed(upload=True)
-    clocks = sampler.stop() if rank == 0 else None
-
-    extra = {}
-    if rank == 0 and world == 1:
-        extra = gpu_side_metrics(stream)
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        acc_ms, acc_madds, acc_n = prof
-        points_per_step = (12 + 6 + 7 + 5) * (1 << K_TABLE)
-        acc_pts = points_per_step * args.steps / world   # points this rank pushed through k_accumulate in the timed region
-        achieved = (96.0 * acc_pts / 1e9) / (acc_ms / 1e3) if acc_ms else 0.0
-        line = {
-            "metric": METRIC, "value": round(ms_dev, 4), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_dev, 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic", "config": workload_config(world),
-            "e2e": {"value": round(ms_e2e, 4), "unit": "ms", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 13 * 64},
-            "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {
-                "kernel": "sb::k_accumulate (MSM bucket accumulation)", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak,
-                "unit": "GB/s", "frac": round(achieved / hbm_peak, 5),
-                "traffic": 3.123e9 if world == 1 else None,
-                "traffic_note": "dram__bytes_read+write of the largest launch (primary W commit, 1 572 864 points, 151 MB algorithmic) from "
-                                "profiles/r1_accumulate_s2_ncu_full_summary.txt: each point is gathered once per window (15 x 64 B table entries, a "
-                                "random 64 B gather costs a 128 B DRAM fetch) by design; the kernel sits at 10 % of DRAM throughput and is integer-pipe bound",
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "launches": int(acc_n), "avg_launch_ms": round(acc_ms / acc_n, 4) if acc_n else None,
-                "note": "algorithmic 96 B/point; the kernel is integer-pipe bound (SURVEY F7): see int_pipe and DESIGN.md 4.2",
-                "int_pipe": {
-                    "achieved_gmadd_per_s": round(acc_madds / (acc_ms * 1e6), 3) if acc_ms else None,
-                    "peak_gmadd_per_s": 6.386,
-                    "frac": round(acc_madds / (acc_ms * 1e6) / 6.386, 4) if acc_ms else None,
-                    "peak_source": "profiles/r1_microbench6_madd_lazy.txt: serial lazy-domain XYZZ mixed additions on the full chip (IMAD.WIDE issue bound, 65.4 G Montgomery products/s)",
-                },
-            },
-            "breakdown_ms_per_step": breakdown,
-            "msm_points_per_step": points_per_step,
-            "msm_mscalar_per_s_in_step": round(points_per_step / ms_dev / 1e3, 2),
-            "extra": extra,
-        }
-        if not args.no_cpu_baseline and world == 1:
-            try:
-                line["cpu_baseline"] = cpu_step_baseline(1)
-            except Exception as exc:  # the oracle is test infrastructure; never let it take the GPU number down
-                line["cpu_baseline"] = {"error": str(exc)}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.destroy_process_group()
-
-
-def gpu_side_metrics(stream):
-    """MSM Mscalar/s (2^20, bn256) and NTT Gelt/s (k = 17, 20) -- BASELINE.json's secondary metrics."""
-    import torch
-
-    from sirius_b200 import device, fft
-
-    out = {}
-    n = 1 << 20
-    ck = device.synthetic_key(0, n, stream=stream)
-    s = device.random_field_device(n, SEED + 77)
-    o = torch.zeros(8, dtype=torch.int64, device="cuda")
-    for _ in range(3):
-        ck.commit_device(s.data_ptr(), n, o.data_ptr(), 0, stream.cuda_stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(5):
-        ck.commit_device(s.data_ptr(), n, o.data_ptr(), 0, stream.cuda_stream)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    out["msm_2^20_bn256"] = {"ms": round(ms, 3), "mscalar_per_s": round(n / ms / 1e3, 1), "gbps_algorithmic": round(96 * n / ms / 1e6, 1)}
-    ck.close()
-    for k in (17, 20):
-        a = device.random_field_device(1 << k, SEED + k)
-        w = fft.get_omega_or_inv(k, False)
-        for _ in range(3):
-            fft.ntt_device(a.data_ptr(), k, w, None, stream.cuda_stream)
-        e0.record(stream)
-        for _ in range(20):
-            fft.ntt_device(a.data_ptr(), k, w, None, stream.cuda_stream)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 20
-        out[f"ntt_k{k}"] = {"us": round(ms * 1e3, 1), "gelt_per_s": round((1 << k) / ms / 1e6, 3), "gbps_algorithmic": round(64 * (1 << k) / ms / 1e6, 1)}
-    return out
-
-
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
-_CPU_STATE = {}
-
-
 def cpu_threads() -> int:
     """Host threads for the CPU arm: the physical cores (the restatement, like rayon-based halo2, gets slower when
     it is spread over SMT siblings: 9.2 s on 128 logical vs 4.7 s on 64 physical cores of the round-1 box)."""
@@ -414,89 +114,15 @@ def cpu_threads() -> int:
     return os.cpu_count() or 1
 
 
-def cpu_setup():
-    """The same shapes for the CPU restatement (oracle/): test infrastructure, used only as the timed baseline."""
-    if _CPU_STATE:
-        return _CPU_STATE
-    import numpy as np
-
+def cpu_fold_step(inputs, bases):
+    """(results, ms): the CPU restatement of the reference on `inputs` (oracle/step_ref.py), all host cores."""
     import oracle
-    from oracle import expr_ref as E
-    from oracle import pyref as R
+    from oracle import step_ref
 
     oracle.build()
-    n = 1 << K_TABLE
-    st = {}
-    for side in (PRIMARY, SECONDARY):
-        nfix, nadv = shapes(side)
-        gates, fb, ab = [], 0, 0
-        for T in side["T_list"]:
-            gates.append(E.main_gate_expression(T, fb, ab, 0, nfix))
-            fb += 2 * T + 5
-            ab += T + 2
-        cg = E.CompressedGates(gates, E.Ctx(num_fixed=nfix, num_advice=nadv))
-        f = side["field"]
-        evs = [None if ex is None else E.GraphEvaluator(ex, R.MODULUS[f]) for ex in cg.grouped()[1:]]
-        nch = cg.ctx.num_challenges - 1
-        st[side["name"]] = dict(
-            side=side, nadv=nadv, evs=evs,
-            fixed=[oracle.random_field(f, SEED + 31 * j + side["curve"], n) for j in range(nfix)],
-            W1=oracle.random_field(f, SEED + 1, nadv * n), W2=oracle.random_field(f, SEED + 2, nadv * n),
-            E1=oracle.random_field(f, SEED + 3, n),
-            ch=np.concatenate([oracle.random_field(f, SEED + 4, nch + 1), oracle.random_field(f, SEED + 5, nch), R.to_mont_limbs([1], R.MODULUS[f])]),
-            r=oracle.random_field(f, SEED + 6, 1).reshape(4),
-            bases=oracle.running_bases(side["curve"], nadv * n),
-        )
-    _CPU_STATE.update(st)
-    return _CPU_STATE
-
-
-def cpu_step():
-    """Literal reference order on the host cores: d evaluator sweeps + d commits + folds, W commits."""
-    import ctypes
-
-    import numpy as np
-
-    import oracle
-    from oracle import expr_ref as E
-
-    st = cpu_setup()
-    n = 1 << K_TABLE
-    u64p = ctypes.POINTER(ctypes.c_uint64)
-    lib = oracle.lib()
-
-    def prove(s):
-        f, curve, nadv = s["side"]["field"], s["side"]["curve"], s["nadv"]
-        adv = [s["W1"][i * n:(i + 1) * n] for i in range(nadv)] + [s["W2"][i * n:(i + 1) * n] for i in range(nadv)]
-        T = [np.zeros((n, 4), dtype=np.uint64) if ev is None else E.c_graph_evaluate(f, ev, [], s["fixed"], adv, s["ch"], K_TABLE, threads=cpu_threads()) for ev in s["evs"]]
-        for t in T:
-            oracle.msm(curve, t, s["bases"], threads=cpu_threads())
-        outw = np.zeros_like(s["W1"])
-        lib.so_axpy(f, s["W1"].ctypes.data_as(u64p), s["W2"].ctypes.data_as(u64p), s["r"].ctypes.data_as(u64p), outw.ctypes.data_as(u64p), ctypes.c_size_t(nadv * n))
-        ptrs = (u64p * len(T))(*[t.ctypes.data_as(u64p) for t in T])
-        oute = np.zeros_like(s["E1"])
-        lib.so_error_fold(f, s["E1"].ctypes.data_as(u64p), ptrs, ctypes.c_size_t(len(T)), s["r"].ctypes.data_as(u64p), oute.ctypes.data_as(u64p), ctypes.c_size_t(n))
-
-    def commit_w(s):
-        oracle.msm(s["side"]["curve"], s["W2"], s["bases"], threads=cpu_threads())
-
-    prove(st["secondary"])
-    commit_w(st["primary"])
-    prove(st["primary"])
-    commit_w(st["secondary"])
-
-
-def cpu_step_baseline(steps):
-    import oracle
-
-    cpu_setup()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_step()
-    ms = (time.perf_counter() - t0) * 1e3 / steps
-    return {"value": round(ms, 2), "unit": "ms", "cores": cpu_threads(), "kind": "port",
-            "sample": f"{steps} full fold_step hot path(s) of the same workload (CPU restatement of the reference: halo2-style chunked Pippenger, "
-                      "literal GroupedPoly/GraphEvaluator cross terms, OpenMP on all host cores)"}
+    res = step_ref.fold_step(inputs, bases, threads=cpu_threads())
+    return res, (time.perf_counter() - t0) * 1e3
 
 
 def run_reference(args):
@@ -505,39 +131,392 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import oracle
+    from oracle import step_ref
+    from sirius_b200 import workload as WL
 
-    cpu_setup()
+    oracle.build()
+    k = args.k
+    inputs = step_ref.synthetic_inputs((WL.PRIMARY, WL.SECONDARY), k, SEED)
+    bases = step_ref.bases_for(inputs)
     for _ in range(min(args.warmup, 1)):
-        cpu_step()
+        cpu_fold_step(inputs, bases)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step()
+        cpu_fold_step(inputs, bases)
     ms = (time.perf_counter() - t0) * 1e3 / args.steps
     base = {"value": round(ms, 2), "unit": "ms", "cores": cpu_threads(), "kind": "port",
             "sample": "full fold_step hot path per step (CPU restatement of the reference; the Rust crate cannot be built here: no cargo/rustc)"}
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(ms, 2), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": metric_name(k), "value": round(ms, 2), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 1),
         "ms_per_step": round(ms, 2), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u64 limbs (254-bit modular integers)", "data": "synthetic", "config": workload_config(world),
+        "dtype": "u64 limbs (254-bit modular integers)", "data": "synthetic", "config": workload_config(world, k),
         "cpu_baseline": base, "e2e": {"value": round(ms, 2), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm
+TAGS = ["decompose", "sort", "accumulate", "fixup", "reduce", "finalize", "cross_terms", "fold", "ntt", "protogalaxy"]
+
+
+class GpuArm:
+    def __init__(self, args):
+        import torch
+
+        self.args, self.torch = args, torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        import sirius_b200
+        from sirius_b200 import _lib
+
+        self._lib = _lib
+        self.lib = sirius_b200.load()
+        _lib.check(self.lib.sb_init(self.local_rank))
+        if self.world > 1:
+            import torch.distributed as dist
+
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"   # keep rank 0's stdout to the one JSON line (NCCL prints its banner there)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.stream = torch.cuda.Stream()
+
+    def barrier(self):
+        torch = self.torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return ms
+        import torch.distributed as dist
+
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # -------------------------------------------------------------------------- verification against the oracle
+    def verify(self, wl):
+        """One step of the timed objects vs the CPU restatement on identical inputs (rank 0 runs the oracle)."""
+        snap = wl.snapshot_inputs()
+        wl.step(upload=True)     # the e2e form: the uploaded pinned copy equals W_in, so both timed variants are covered
+        res = wl.snapshot_results()
+        report, cpu_ms = None, None
+        if self.rank == 0:
+            from oracle import step_ref
+
+            bases = step_ref.bases_for(snap)
+            cpu_res, cpu_ms = cpu_fold_step(snap, bases)
+            report = step_ref.compare(res, cpu_res)
+            report["what"] = "13 commitments + folded W and E of both sides, bit for bit, one step of the timed objects vs oracle/step_ref.py on identical inputs"
+        self.barrier()
+        return report, cpu_ms
+
+    # -------------------------------------------------------------------------- timing
+    def timed(self, wl, upload, steps, warmup):
+        import ctypes
+
+        torch, lib = self.torch, self.lib
+        for _ in range(warmup):
+            wl.step(upload)
+        self.barrier()
+        NT = len(TAGS)
+        ms_arr, un_arr, ln_arr = (ctypes.c_double * NT)(), (ctypes.c_uint64 * NT)(), (ctypes.c_uint64 * NT)()
+        lib.sb_profile_enable(1)
+        lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
+        launches0 = lib.sb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        h2d = 0
+        for _ in range(steps):
+            h2d += wl.step(upload)
+        e1.record(self.stream)
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        self._lib.check(lib.sb_profile_collect(ms_arr, un_arr, ln_arr))
+        lib.sb_profile_enable(0)
+        breakdown = {t: round(ms_arr[i] / steps, 4) for i, t in enumerate(TAGS) if ln_arr[i]}
+        launches = lib.sb_launch_count() - launches0
+        ms = self.max_over_ranks(ms)
+        return dict(ms=ms / steps, h2d=h2d // max(1, steps), launches=launches // max(1, steps), acc=(ms_arr[2], un_arr[2], ln_arr[2]), breakdown=breakdown)
+
+    def timed_leg(self, fn, steps, warmup):
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    # -------------------------------------------------------------------------- the host-buffer ABI path (N = 1)
+    def host_abi(self, wl, steps, warmup):
+        """The step through the entry points a verbatim Rust shim binds: pageable host arrays in, T / folded W / E back."""
+        import numpy as np
+
+        from sirius_b200 import sangria as SG
+
+        torch = self.torch
+        sides = []
+        for sess, ex in zip(wl.sides, wl.extras):
+            torch.cuda.synchronize()
+            sides.append(dict(sess=sess, ex=ex, acc=SG.RelaxedPlonkWitness(sess.S.field, [sess.W_acc.cpu().numpy().view(np.uint64).copy()], sess.E_acc.cpu().numpy().view(np.uint64).copy()),
+                              W2=sess.W_in.cpu().numpy().view(np.uint64).copy()))
+        prim, sec = sides
+        h2d = d2h = 0
+
+        def prove(s):
+            nonlocal h2d, d2h
+            sess, ex = s["sess"], s["ex"]
+            T, commits = SG.VanillaFS.commit_cross_terms(sess.ck, sess.S, ex["c1"], ex["u1"], s["acc"].W, ex["c2"], [s["W2"]])
+            s["acc"] = s["acc"].fold([s["W2"]], T, ex["r"])
+            wb, tb, eb = s["W2"].nbytes, sum(t.nbytes for t in T), s["acc"].E.nbytes
+            h2d += 2 * wb + tb + 2 * wb + eb + tb    # commit_cross_terms: W1, W2 ; commit(T_j) ; fold: W1, W2, E, T
+            d2h += tb + wb + eb + 64 * len(T)
+
+        def commit_w(s):
+            nonlocal h2d, d2h
+            s["sess"].ck.commit(s["W2"])
+            h2d += s["W2"].nbytes
+            d2h += 64
+
+        def step():
+            prove(sec)
+            commit_w(prim)
+            prove(prim)
+            commit_w(sec)
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        h2d = d2h = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        return {"value": round(ms, 3), "unit": "ms", "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps, "steps": steps,
+                "timer": "host wall clock: every call blocks until its result is in host memory",
+                "path": "CommitmentKey.commit / VanillaFS.commit_cross_terms / RelaxedPlonkWitness.fold on pageable host arrays (sb_msm, sb_cross_terms, sb_msm_batch, sb_axpy_fold, sb_error_fold)"}
+
+    # -------------------------------------------------------------------------- one table size
+    def measure(self, k, steps, warmup, with_cpu, with_host_abi, with_stages):
+        from sirius_b200 import workload as WL
+
+        wl = WL.SangriaStepWorkload(k, self.rank, self.world, self.stream)
+        out = {"k": k, "steps": steps, "warmup": warmup}
+        cpu_ms = None
+        if not self.args.no_verify:
+            report, cpu_ms = self.verify(wl)
+            if self.rank == 0:
+                out["verified"] = bool(report["ok"])
+                out["verify"] = report
+                if not report["ok"]:
+                    raise SystemExit(f"bench.py: the timed path disagrees with the oracle: {report['bad']}")
+        dev = self.timed(wl, False, steps, warmup)
+        e2e = self.timed(wl, True, steps, warmup)
+        out.update(dev=dev, e2e=e2e)
+        if with_stages:
+            out["stages"] = {
+                "new_ms": round(self.timed_leg(wl.new_leg, max(2, steps // 2), 1), 4),
+                "verify_ms": round(self.timed_leg(wl.verify_leg, max(2, steps // 2), 1), 4),
+                "note": "benches/sangria_poseidon.rs:159-175 times IVC::fold(.., 1) = new + fold_step + verify: new_ms = the two W commits of IVC::new; "
+                        "verify_ms = is_sat_accumulation row sweep + re-commit of W_acc, E, W_in + PlonkStructure::is_sat row sweep, both sides (device-resident)",
+            }
+        if with_host_abi and self.world == 1:
+            out["e2e_host_abi"] = self.host_abi(wl, max(2, min(steps, 3)), 1)
+        if with_cpu and cpu_ms is not None and self.rank == 0:
+            out["cpu_baseline"] = {"value": round(cpu_ms, 2), "unit": "ms", "cores": cpu_threads(), "kind": "port",
+                                   "sample": "1 full fold_step hot path of the same workload ON THE SAME INPUTS as the verified GPU step (CPU restatement of the reference: "
+                                             "halo2-style chunked Pippenger, literal GroupedPoly/GraphEvaluator cross terms, OpenMP on all host cores)"}
+        wl.close()
+        del wl
+        import gc
+
+        gc.collect()
+        self.torch.cuda.synchronize()
+        self.torch.cuda.empty_cache()
+        return out
+
+
+def roofline_block(m, world, peaks):
+    k, steps = m["k"], m["steps"]
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    acc_ms, acc_madds, acc_n = m["dev"]["acc"]
+    points_per_step = (12 + 6 + 7 + 5) * (1 << k)
+    acc_pts = points_per_step * steps / world   # points this rank pushed through k_accumulate in the timed region
+    achieved = (96.0 * acc_pts / 1e9) / (acc_ms / 1e3) if acc_ms else 0.0
+    traffic, traffic_note = None, "no ncu capture of this kernel at this shape"
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "accumulate_traffic.json")))
+        if world == 1 and k == t.get("k"):
+            traffic, traffic_note = t["dram_bytes_per_launch"], t["note"]
+    except Exception:
+        pass
+    # instruction-level bound of the integer pipe: one IMAD.WIDE warp-instruction per 4 cycles per scheduler (quarter
+    # rate, profiles/r1_microbench5_pipes.txt), >= 128 of them per 254-bit Montgomery product (8x8 limb products for
+    # a*b and 8x8 for the reduction), 592 schedulers at the sampled clock
+    sm_clock = 1.965e9
+    prod_peak = 148 * 4 * sm_clock * 32 / (128 * 4.0) / 1e9          # G products/s
+    gmadd = acc_madds / (acc_ms * 1e6) if acc_ms else None
+    return {
+        "kernel": "sb::k_accumulate (MSM bucket accumulation)", "bound": "hbm", "achieved": round(achieved, 2), "peak": hbm_peak,
+        "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "traffic_note": traffic_note,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        "launches": int(acc_n), "avg_launch_ms": round(acc_ms / acc_n, 4) if acc_n else None,
+        "note": "algorithmic 96 B/point; the kernel is integer-pipe bound (SURVEY F7): see int_pipe and DESIGN.md 4.2",
+        "int_pipe": {
+            "achieved_gmadd_per_s": round(gmadd, 3) if gmadd else None,
+            "issue_bound_gproducts_per_s": round(prod_peak, 2),
+            "frac_of_issue_bound_xyzz": round(gmadd * 10 / prod_peak, 4) if gmadd else None,
+            "frac_of_issue_bound_affine": round(gmadd * 6 / prod_peak, 4) if gmadd else None,
+            "peak_source": "IMAD.WIDE issue rate (1 warp-instruction / 4 cycles / scheduler) x 128 IMAD.WIDE per Montgomery product x 592 schedulers x 1.965 GHz; "
+                           "xyzz = 10 products per mixed addition (what the kernel executes), affine = 6 products (batched-affine addition, the algorithmic minimum): "
+                           "the second fraction is the slack left to the ALGORITHM, the first to the loop",
+        },
+    }
+
+
+def run_gpu(args):
+    arm = GpuArm(args)
+    rank, world = arm.rank, arm.world
+    sampler = ClockSampler(arm.local_rank)
+    if rank == 0:
+        sampler.start()
+    main = arm.measure(args.k, args.steps, args.warmup, with_cpu=not args.no_cpu_baseline and world == 1, with_host_abi=not args.no_host_abi, with_stages=True)
+    clocks = sampler.stop() if rank == 0 else None
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = gpu_side_metrics(arm.stream)
+    if not args.no_k20 and args.k != 20:
+        sampler20 = ClockSampler(arm.local_rank)
+        if rank == 0:
+            sampler20.start()
+        m20 = arm.measure(20, max(2, min(args.steps, 3)), 2, with_cpu=not args.no_cpu_baseline and world == 1, with_host_abi=False, with_stages=False)
+        c20 = sampler20.stop() if rank == 0 else None
+        if rank == 0:
+            peaks = _peaks()
+            extra["k20"] = {
+                "metric": metric_name(20), "value": round(m20["dev"]["ms"], 3), "unit": "ms", "n_gpus": world, "steps": m20["steps"], "warmup": m20["warmup"],
+                "e2e": {"value": round(m20["e2e"]["ms"], 3), "unit": "ms", "h2d_bytes_per_step": int(m20["e2e"]["h2d"]), "d2h_bytes_per_step": 13 * 64},
+                "verified": m20.get("verified"), "verify_bad": (m20.get("verify") or {}).get("bad"),
+                "breakdown_ms_per_step": m20["dev"]["breakdown"], "gpu_launches": int(m20["dev"]["launches"]), "clocks": c20,
+                "cpu_baseline": m20.get("cpu_baseline"), "config": workload_config(world, 20), "roofline": roofline_block(m20, world, peaks),
+                "note": "the north star's target configuration (sangria_poseidon at k=20): same circuit shapes, 2^20 rows",
+            }
+    if rank == 0:
+        peaks = _peaks()
+        k = args.k
+        points_per_step = (12 + 6 + 7 + 5) * (1 << k)
+        line = {
+            "metric": metric_name(k), "value": round(main["dev"]["ms"], 4), "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(main["dev"]["ms"], 4), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic", "config": workload_config(world, k),
+            "e2e": {"value": round(main["e2e"]["ms"], 4), "unit": "ms", "h2d_bytes_per_step": int(main["e2e"]["h2d"]), "d2h_bytes_per_step": 13 * 64,
+                    "path": "device-resident prover state (SURVEY 8f-1): fresh witness columns from pinned host memory, 13 commitments read back"},
+            "gpu_launches": int(main["dev"]["launches"]), "clocks": clocks,
+            "verified": main.get("verified"), "verify": main.get("verify"),
+            "roofline": roofline_block(main, world, peaks),
+            "breakdown_ms_per_step": main["dev"]["breakdown"],
+            "stages": main.get("stages"),
+            "msm_points_per_step": points_per_step,
+            "msm_mscalar_per_s_in_step": round(points_per_step / main["dev"]["ms"] / 1e3, 2),
+            "extra": extra,
+        }
+        if "e2e_host_abi" in main:
+            line["e2e_host_abi"] = main["e2e_host_abi"]
+        if "cpu_baseline" in main:
+            line["cpu_baseline"] = main["cpu_baseline"]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def gpu_side_metrics(stream):
+    """MSM Mscalar/s (2^20, bn256) and NTT Gelt/s (k = 17, 20) -- BASELINE.json's secondary metrics."""
+    import torch
+
+    from sirius_b200 import device, fft
+
+    out = {}
+    n = 1 << 20
+    ck = device.synthetic_key(0, n, stream=stream)
+    with torch.cuda.stream(stream):
+        s = device.random_field_device(n, SEED + 77)
+        o = torch.zeros(8, dtype=torch.int64, device="cuda")
+    stream.synchronize()
+    for _ in range(3):
+        ck.commit_device(s.data_ptr(), n, o.data_ptr(), 0, stream.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(5):
+        ck.commit_device(s.data_ptr(), n, o.data_ptr(), 0, stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out["msm_2^20_bn256"] = {"ms": round(ms, 3), "mscalar_per_s": round(n / ms / 1e3, 1), "gbps_algorithmic": round(96 * n / ms / 1e6, 1)}
+    ck.close()
+    for k in (17, 20):
+        with torch.cuda.stream(stream):
+            a = device.random_field_device(1 << k, SEED + k)
+        stream.synchronize()
+        w = fft.get_omega_or_inv(k, False)
+        for _ in range(3):
+            fft.ntt_device(a.data_ptr(), k, w, None, stream.cuda_stream)
+        e0.record(stream)
+        for _ in range(20):
+            fft.ntt_device(a.data_ptr(), k, w, None, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        out[f"ntt_k{k}"] = {"us": round(ms * 1e3, 1), "gelt_per_s": round((1 << k) / ms / 1e6, 3), "gbps_algorithmic": round(64 * (1 << k) / ms / 1e6, 1)}
+    return out
+
+
+def run_cyclefold(args):
+    raise SystemExit("bench.py: --workload cyclefold_poseidon is not built yet")
+
+
+def run_msm_sweep(args):
+    raise SystemExit("bench.py: --workload msm_sweep is not built yet")
+
+
 def main():
-    global K_TABLE, CK_LOG, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sangria_poseidon", choices=["sangria_poseidon", "cyclefold_poseidon", "msm_sweep"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--k", type=int, default=17, help="table size 2^k rows (default 17 = BASELINE configs[1]; 20 = the north star's larger case, "
-                                                       "same shapes; needs ~45 GB of window tables)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the bit-for-bit comparison of one timed step with the oracle")
+    ap.add_argument("--no-k20", action="store_true", help="skip the extra.k20 block (the same measurement at k = 20)")
+    ap.add_argument("--no-host-abi", action="store_true", help="skip the e2e_host_abi figure")
+    ap.add_argument("--no-extra", action="store_true", help="skip the MSM 2^20 / NTT side metrics")
+    ap.add_argument("--k", type=int, default=K_TABLE, help="table size 2^k rows of the main line (default 17 = BASELINE configs[1])")
     args = ap.parse_args()
-    if args.k != K_TABLE:   # same circuit shapes at another table size (the key covers 16 * 2^k generators, as at k = 17)
-        K_TABLE, CK_LOG = args.k, args.k + 4
-        METRIC = f"sangria_poseidon k={args.k} IVC fold_step prover hot-path time"
+    if args.workload == "cyclefold_poseidon":
+        return run_cyclefold(args)
+    if args.workload == "msm_sweep":
+        return run_msm_sweep(args)
     if args.impl == "reference":
         run_reference(args)
     else:

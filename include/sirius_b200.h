@@ -13,8 +13,12 @@
  *     is in host memory.  "_device" entry points take device pointers on the current device and enqueue on
  *     the given CUDA stream (cudaStream_t passed as void*; NULL = the library's stream), returning without
  *     synchronising.
- *   - "_device" entry points of one family share a grow-only device workspace: enqueue them on ONE stream (or
- *     synchronise between streams); calls are serialised on an internal mutex at enqueue time only.
+ *   - Threading: every entry point may be called from any host thread (CommitmentKey is Sync; cargo test is
+ *     multi-threaded).  Host entry points are serialised on the library's own stream, each one a single critical
+ *     section from staging to the synchronised download.  "_device" entry points keep their device scratch PER
+ *     STREAM: calls on one stream are ordered by the stream, calls on different streams (from different threads)
+ *     share nothing and may overlap; only the host-side enqueue is serialised.  sb_stream_release(stream) frees
+ *     the scratch of a stream that is about to be destroyed.
  *   - There is no CPU fallback: without a CUDA device every call fails with SB_ERR_CUDA.
  */
 #ifndef SIRIUS_B200_H
@@ -75,6 +79,8 @@ int sb_version(void);
 int sb_init(int device);
 void sb_shutdown(void);
 int sb_device_count(void);
+/* Frees the device scratch kept for `stream` (synchronises it first). */
+void sb_stream_release(void* stream);
 
 /* ---- CommitmentKey (src/commitment.rs) ------------------------------------------------------------ */
 
@@ -225,6 +231,11 @@ int sb_scaled_inverse_device(int field, const void* d_in, const uint64_t shift[4
  * The _device form writes the 32-byte result to d_out without synchronising. */
 int sb_sum_diff(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t out[4]);
 int sb_sum_diff_device(int field, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream);
+
+/* Row filter of the deciders: *d_count_u64 (device, 8 bytes) = #{i < n : a[i] != b[i]}; b NULL compares with zero.
+ * is_sat_accumulation compares the evaluated rows with E (src/nifs/sangria/mod.rs:349-370), PlonkStructure::is_sat with
+ * zero (src/plonk/mod.rs:321-338).  Enqueues without synchronising. */
+int sb_count_mismatch_device(int field, const void* d_a, const void* d_b, size_t n, void* d_count_u64, void* stream);
 
 /* ---- permutation decider (src/nifs/sangria/mod.rs:385-453, src/nifs/protogalaxy/mod.rs:660-689) ------------ */
 

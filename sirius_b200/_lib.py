@@ -30,6 +30,7 @@ SIGNATURES = {
     "sb_init": (ctypes.c_int, [ctypes.c_int]),
     "sb_shutdown": (None, []),
     "sb_device_count": (ctypes.c_int, []),
+    "sb_stream_release": (None, [vp]),
     "sb_ck_register": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(vp)]),
     "sb_ck_register_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_int, vp, ctypes.POINTER(vp)]),
     "sb_ck_release": (None, [vp]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "sb_scaled_inverse_device": (ctypes.c_int, [ctypes.c_int, vp, u64p, vp, vp, ctypes.c_size_t, vp]),
     "sb_sum_diff": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p]),
     "sb_sum_diff_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_size_t, vp, vp]),
+    "sb_count_mismatch_device": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_size_t, vp, vp]),
     "sb_sparse_register": (ctypes.c_int, [ctypes.c_int, u64p, u64p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(vp)]),
     "sb_sparse_release": (None, [vp]),
     "sb_sparse_dim": (ctypes.c_size_t, [vp]),

@@ -5,12 +5,6 @@
 #include "common.cuh"
 #include "field.cuh"
 
-namespace sb {
-
-static Scratch g_bi_stage;
-
-}  // namespace sb
-
 using namespace sb;
 
 extern "C" {
@@ -31,14 +25,15 @@ int sb_batch_invert(int field, const uint64_t* in, uint64_t* out, size_t n) {
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // one critical section from staging to the synchronised download
+    Scratch& g_bi_stage = ws_slot(rt.stream, WS_BI_STAGE);
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
         SB_TRY(g_bi_stage.reserve(n * 64 + 64));
         SB_CUDA_TRY(cudaMemcpyAsync(g_bi_stage.ptr, in, n * 32, cudaMemcpyHostToDevice, rt.stream));
     }
     char* d = (char*)g_bi_stage.ptr;
     SB_TRY(sb_batch_invert_device(field, d, d + n * 32, n, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(out, d + n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;

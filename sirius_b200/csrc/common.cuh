@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "../../include/sirius_b200.h"
@@ -53,13 +54,17 @@ struct ProfScope {  // CUDA events around the launches issued while the scope is
     } while (0)
 
 // Library-wide state for the device this process drives (one process per GPU).
+using RtMutex = std::recursive_mutex;
+using RtLock = std::lock_guard<std::recursive_mutex>;
 struct Runtime {
-    std::mutex mu;          // serialises library calls that share the workspace (commit is called sequentially
-                            // by the reference, SURVEY 3.3, but cargo test runs tests on many threads)
+    RtMutex mu;             // serialises the HOST side of library calls (commit is called sequentially by the
+                            // reference, SURVEY 3.3, but cargo test runs tests on many threads).  Recursive: a
+                            // host-memory entry point holds it across stage -> enqueue -> download -> sync and
+                            // calls the matching _device entry point inside.
     int device = -1;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    bool ready = false;
+    cudaStream_t stream = nullptr;   // the library's own stream: host-memory entry points run here
+    std::atomic<bool> ready{false};
 };
 Runtime& runtime();
 int ensure_runtime();
@@ -71,6 +76,17 @@ struct Scratch {
     int reserve(size_t bytes);
     void release();
 };
+
+// Device scratch is kept PER CUDA STREAM: two threads driving two streams never share a buffer, and calls on
+// one stream are ordered by the stream itself, so every _device entry point is re-entrant across streams
+// (SURVEY 8b "Threading").  The caller holds runtime().mu while it looks a slot up and enqueues.
+enum WsSlot : int {
+    WS_MSM = 0, WS_EXPR_ARGS, WS_EXPR_STAGE, WS_FOLD_CONSTS, WS_FOLD_STAGE, WS_NTT_TMP, WS_NTT_STAGE, WS_PG, WS_LINCOMB_ARGS,
+    WS_PG_STAGE, WS_BI_STAGE, WS_LK, WS_LK_STAGE, WS_INV_SHIFT, WS_MSM_HOST, WS_NUM_SLOTS
+};
+Scratch& ws_slot(cudaStream_t st, int slot);
+void ws_release_stream(cudaStream_t st);   // frees every slot of `st` (all streams when st == nullptr-all flag is used by sb_shutdown)
+void ws_release_all();
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -245,11 +245,10 @@ struct sb_prog {
     void* d_ops;
     void* d_constants;
     void* d_rotations;
-    void* d_args;  // per-call tables: column pointer arrays, challenge table, Vandermonde inverse, r powers
-    size_t args_cap;
     uint32_t vinv_degree;  // inverse Vandermonde on 0..degree, built once per (program, degree)
     void* d_vinv;
     std::vector<uint32_t> poly_indices;  // distinct column indices the program reads (for validation)
+    std::vector<uint32_t> fixed_indices; // ValueSource::Fixed column indices (checked against the registered columns)
     uint32_t max_challenge;
     bool uses_challenge;
 };
@@ -306,13 +305,12 @@ static void host_vandermonde_inverse(uint32_t degree, std::vector<F>& out) {
     }
 }
 
-static int args_reserve(sb_prog* p, size_t bytes) {
-    if (bytes <= p->args_cap) return SB_OK;
-    if (p->d_args) cudaFree(p->d_args);
-    p->d_args = nullptr;
-    p->args_cap = 0;
-    SB_CUDA_TRY(cudaMalloc(&p->d_args, bytes));
-    p->args_cap = bytes;
+// per-call tables (column pointer arrays, challenge table, blend coefficients) live in the launching stream's
+// scratch: two streams evaluating the same program never share them
+static int args_reserve(cudaStream_t st, size_t bytes, char** out) {
+    Scratch& a = ws_slot(st, WS_EXPR_ARGS);
+    SB_TRY(a.reserve(bytes < 4096 ? 4096 : bytes));
+    *out = (char*)a.ptr;
     return SB_OK;
 }
 
@@ -347,6 +345,12 @@ static int validate_program(const sb_prog* prog, const sb_columns* cols, size_t 
             return SB_ERR_ARG;
         }
     }
+    for (uint32_t idx : prog->fixed_indices) {
+        if (idx >= cols->num_fixed) {   // graph_evaluator.rs:104-110 -> eval::Error::ColumnVariableIndexOutOfBoundary
+            set_error("expression reads fixed column %u but the structure has %u (ColumnVariableIndexOutOfBoundary)", idx, cols->num_fixed);
+            return SB_ERR_ARG;
+        }
+    }
     if (prog->uses_challenge && prog->max_challenge >= num_challenges) {
         set_error("challenge index out of boundary: %u (have %zu)", prog->max_challenge, num_challenges);
         return SB_ERR_ARG;
@@ -360,8 +364,8 @@ static int eval_enqueue(sb_prog* prog, sb_columns* cols, const void* const* h_ad
     SB_TRY(validate_program(prog, cols, nfv, h_adv2 != nullptr, num_challenges));
     const size_t ptr_bytes = align_up(sizeof(void*) * nfv * 2, 32);
     const size_t ch_bytes = align_up(32 * (num_challenges ? num_challenges : 1), 32);
-    SB_TRY(args_reserve(prog, ptr_bytes + ch_bytes));
-    char* d = (char*)prog->d_args;
+    char* d = nullptr;
+    SB_TRY(args_reserve(st, ptr_bytes + ch_bytes, &d));
     if (nfv) {
         SB_CUDA_TRY(cudaMemcpyAsync(d, h_adv1, sizeof(void*) * nfv, cudaMemcpyHostToDevice, st));
         if (h_adv2) SB_CUDA_TRY(cudaMemcpyAsync(d + sizeof(void*) * nfv, h_adv2, sizeof(void*) * nfv, cudaMemcpyHostToDevice, st));
@@ -409,8 +413,8 @@ static int pg_leaves_enqueue(sb_prog* const* gates, size_t num_gates, sb_columns
     for (size_t g = 0; g < num_gates; g++) {
         sb_prog* prog = gates[g];
         SB_TRY(validate_program(prog, cols, nfv, false, num_challenges));
-        SB_TRY(args_reserve(prog, ptr_bytes + coef_bytes + ch_bytes));
-        char* d = (char*)prog->d_args;
+        char* d = nullptr;
+        SB_TRY(args_reserve(st, ptr_bytes + coef_bytes + ch_bytes, &d));
         if (nfv) SB_CUDA_TRY(cudaMemcpyAsync(d, h_cols_tables, sizeof(void*) * nfv * num_traces, cudaMemcpyHostToDevice, st));
         SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes, coef, 32 * num_blends * num_traces, cudaMemcpyHostToDevice, st));
         if (num_challenges) SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes + coef_bytes, challenges, 32 * num_blends * num_challenges, cudaMemcpyHostToDevice, st));
@@ -452,7 +456,8 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
     const size_t ptr_bytes = align_up(sizeof(void*) * nfv * 2, 32);
     const size_t ch_bytes = (size_t)32 * m * (num_challenges ? num_challenges : 1);
     const size_t vinv_bytes = (size_t)32 * m * m;
-    SB_TRY(args_reserve(prog, ptr_bytes + ch_bytes));
+    char* d = nullptr;
+    SB_TRY(args_reserve(st, ptr_bytes + ch_bytes, &d));
     if (prog->vinv_degree != degree || !prog->d_vinv) {
         std::vector<F> vinv;
         host_vandermonde_inverse<F>(degree, vinv);
@@ -463,7 +468,6 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
         SB_CUDA_TRY(cudaStreamSynchronize(st));
         prog->vinv_degree = degree;
     }
-    char* d = (char*)prog->d_args;
     // challenge table: c1 + t*c2 for t = 0..degree, built on the host with the portable field code
     std::vector<F> table((size_t)m * (num_challenges ? num_challenges : 1));
     for (size_t i = 0; i < num_challenges; i++) {
@@ -533,7 +537,6 @@ static int fold_var_location(size_t index, size_t num_advice, size_t num_lookup,
     return SB_ERR_ARG;
 }
 
-static Scratch g_expr_stage;
 
 }  // namespace sb
 
@@ -632,6 +635,7 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
         if (v.kind == VS_INTERMEDIATE) return slot_of[v.index];
         if (v.kind == VS_POLY || v.kind == VS_FIXED) {
             if (v.kind == VS_POLY) p->poly_indices.push_back(v.index);
+            else p->fixed_indices.push_back(v.index);
             return v.index | (v.rot << 24);
         }
         if (v.kind == VS_CHALLENGE) {
@@ -673,12 +677,11 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
     p->result_slot = n_calcs ? slot_of[calcs[n_calcs - 1].target] : 0;
     p->num_constants = (uint32_t)n_constants;
     p->num_rotations = (uint32_t)n_rotations;
-    p->d_ops = p->d_constants = p->d_rotations = p->d_args = nullptr;
+    p->d_ops = p->d_constants = p->d_rotations = nullptr;
     p->vinv_degree = 0;
     p->d_vinv = nullptr;
-    p->args_cap = 0;
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaError_t e = cudaMalloc(&p->d_ops, sizeof(DevOp) * (n_ops ? n_ops : 1));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_constants, 32 * (n_constants ? n_constants : 1));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_rotations, 4 * (n_rotations ? n_rotations : 1));
@@ -700,7 +703,6 @@ void sb_expr_free(sb_prog_t p) {
     if (p->d_ops) cudaFree(p->d_ops);
     if (p->d_constants) cudaFree(p->d_constants);
     if (p->d_rotations) cudaFree(p->d_rotations);
-    if (p->d_args) cudaFree(p->d_args);
     if (p->d_vinv) cudaFree(p->d_vinv);
     delete p;
 }
@@ -717,7 +719,7 @@ int sb_columns_register(int field, uint32_t log_rows, const uint8_t* const* sele
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     const size_t n = (size_t)1 << log_rows;
     const size_t sel_bytes = align_up(n, 32);
     const size_t total = sel_bytes * num_selectors + n * 32 * num_fixed;
@@ -767,7 +769,7 @@ int sb_expr_eval_device(sb_prog_t prog, sb_columns_t cols, const void* const* d_
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     if (prog->field == FIELD_FR) return eval_enqueue<Fr>(prog, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges, num_challenges, d_out, st);
     return eval_enqueue<Fq>(prog, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges, num_challenges, d_out, st);
@@ -782,7 +784,7 @@ int sb_cross_terms_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, co
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     if (prog->field == FIELD_FR)
         return cross_terms_enqueue<Fr>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st);
@@ -799,7 +801,7 @@ int sb_pg_leaves_device(sb_prog_t const* gates, size_t num_gates, sb_columns_t c
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     const int compat = row_mode == 0;
     if (gates[0]->field == FIELD_FR)
@@ -846,6 +848,8 @@ int sb_cross_terms(sb_prog_t prog, uint32_t degree, sb_columns_t cols, uint32_t 
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // ONE critical section: stage -> enqueue -> download -> sync (the stage buffer is shared)
+    Scratch& g_expr_stage = ws_slot(rt.stream, WS_EXPR_STAGE);
     const size_t n = (size_t)1 << cols->log_rows;
     size_t bytes = 0;
     for (size_t r = 0; r < W1_rounds; r++) bytes += align_up(W1_lens[r] * 32, 256);
@@ -854,7 +858,7 @@ int sb_cross_terms(sb_prog_t prog, uint32_t degree, sb_columns_t cols, uint32_t 
     bytes += (size_t)degree * n * 32;
     std::vector<const void*> p1, p2;
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
+        RtLock lk(rt.mu);
         SB_TRY(g_expr_stage.reserve(bytes));
         size_t off = 0;
         SB_TRY(stage_witness(W1, W1_lens, W1_rounds, num_advice, num_lookup, n, (char*)g_expr_stage.ptr, &off, p1, rt.stream));
@@ -862,7 +866,7 @@ int sb_cross_terms(sb_prog_t prog, uint32_t degree, sb_columns_t cols, uint32_t 
     }
     char* d_out = (char*)g_expr_stage.ptr + out_off;
     SB_TRY(sb_cross_terms_device(prog, degree, cols, p1.data(), p2.data(), p1.size(), challenges1, challenges2, num_challenges, d_out, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     for (uint32_t j = 0; j < degree; j++)
         SB_CUDA_TRY(cudaMemcpyAsync(out_T[j], d_out + (size_t)j * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
@@ -878,6 +882,8 @@ int sb_expr_eval(sb_prog_t prog, sb_columns_t cols, uint32_t num_advice, uint32_
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // ONE critical section: stage -> enqueue -> download -> sync (the stage buffer is shared)
+    Scratch& g_expr_stage = ws_slot(rt.stream, WS_EXPR_STAGE);
     const size_t n = (size_t)1 << cols->log_rows;
     size_t bytes = 0;
     for (size_t r = 0; r < W1_rounds; r++) bytes += align_up(W1_lens[r] * 32, 256);
@@ -886,7 +892,7 @@ int sb_expr_eval(sb_prog_t prog, sb_columns_t cols, uint32_t num_advice, uint32_
     bytes += n * 32;
     std::vector<const void*> p1, p2;
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
+        RtLock lk(rt.mu);
         SB_TRY(g_expr_stage.reserve(bytes));
         size_t off = 0;
         SB_TRY(stage_witness(W1, W1_lens, W1_rounds, num_advice, num_lookup, n, (char*)g_expr_stage.ptr, &off, p1, rt.stream));
@@ -894,7 +900,7 @@ int sb_expr_eval(sb_prog_t prog, sb_columns_t cols, uint32_t num_advice, uint32_
     }
     char* d_out = (char*)g_expr_stage.ptr + out_off;
     SB_TRY(sb_expr_eval_device(prog, cols, p1.data(), W2 ? p2.data() : nullptr, p1.size(), challenges, num_challenges, d_out, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(out, d_out, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;
@@ -926,7 +932,6 @@ int sb_axpy_fold_device(int field, const void* d_w1, const void* d_w2, const uin
     return SB_OK;
 }
 
-static Scratch g_fold_consts;
 
 int sb_error_fold_device(int field, const void* d_e, const void* d_T, uint32_t d, const uint64_t r[4], void* d_out, size_t n, void* stream) {
     if ((!d_e || !d_T || !d_out) && n) {
@@ -939,9 +944,10 @@ int sb_error_fold_device(int field, const void* d_e, const void* d_T, uint32_t d
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     if (!n) return SB_OK;
+    Scratch& g_fold_consts = ws_slot(st, WS_FOLD_CONSTS);
     SB_TRY(g_fold_consts.reserve(64 * 32));
     unsigned blocks = (unsigned)((n + 255) / 256);
     ProfScope ps(st, PROF_FOLD, n);
@@ -964,7 +970,6 @@ int sb_error_fold_device(int field, const void* d_e, const void* d_T, uint32_t d
     return SB_OK;
 }
 
-static Scratch g_fold_stage;
 
 // RelaxedPlonkWitness::fold on host vectors: out_w = w1 + r*w2 (n_w elements); out_e = e + sum r^j T_j (n_e rows)
 int sb_axpy_fold(int field, const uint64_t* w1, const uint64_t* w2, const uint64_t r[4], uint64_t* out, size_t n) {
@@ -974,15 +979,16 @@ int sb_axpy_fold(int field, const uint64_t* w1, const uint64_t* w2, const uint64
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);
+    Scratch& g_fold_stage = ws_slot(rt.stream, WS_FOLD_STAGE);
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
         SB_TRY(g_fold_stage.reserve(n * 96 + 96));
         SB_CUDA_TRY(cudaMemcpyAsync(g_fold_stage.ptr, w1, n * 32, cudaMemcpyHostToDevice, rt.stream));
         SB_CUDA_TRY(cudaMemcpyAsync((char*)g_fold_stage.ptr + n * 32, w2, n * 32, cudaMemcpyHostToDevice, rt.stream));
     }
     char* d = (char*)g_fold_stage.ptr;
     SB_TRY(sb_axpy_fold_device(field, d, d + n * 32, r, d + n * 64, n, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(out, d + n * 64, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;
@@ -995,8 +1001,9 @@ int sb_error_fold(int field, const uint64_t* e, const uint64_t* const* T, uint32
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);
+    Scratch& g_fold_stage = ws_slot(rt.stream, WS_FOLD_STAGE);
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
         SB_TRY(g_fold_stage.reserve(n * 32 * (d + 2) + 96));
         char* dptr = (char*)g_fold_stage.ptr;
         SB_CUDA_TRY(cudaMemcpyAsync(dptr, e, n * 32, cudaMemcpyHostToDevice, rt.stream));
@@ -1005,7 +1012,7 @@ int sb_error_fold(int field, const uint64_t* e, const uint64_t* const* T, uint32
     }
     char* dptr = (char*)g_fold_stage.ptr;
     SB_TRY(sb_error_fold_device(field, dptr, dptr + n * 32, d, r, dptr + (size_t)(d + 1) * n * 32, n, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(out, dptr + (size_t)(d + 1) * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;

@@ -238,6 +238,21 @@ k_sum_diff(const F* __restrict__ a, const F* __restrict__ b, size_t n, F* __rest
     if (threadIdx.x == 0) stc(partial + blockIdx.x, sh[0]);
 }
 
+// count += #{i : a[i] != b[i]} (b == nullptr: a[i] != 0): the filter/count of the deciders (is_sat_accumulation compares the
+// evaluated rows with E, src/nifs/sangria/mod.rs:349-370; PlonkStructure::is_sat compares them with zero, plonk/mod.rs:321-338)
+template <class F>
+__global__ void __launch_bounds__(256)
+k_count_mismatch(const F* __restrict__ a, const F* __restrict__ b, size_t n, unsigned long long* __restrict__ count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < n) {
+        const F x = ldc(a + i);
+        bad = b ? (x != ldc(b + i)) : !x.is_zero();
+    }
+    const uint32_t votes = __ballot_sync(0xFFFFFFFFu, bad);
+    if ((threadIdx.x & 31u) == 0 && votes) atomicAdd(count, (unsigned long long)__popc(votes));
+}
+
 // y = P * Z row by row (CSR), count rows with y != Z[row].  Z = head (first head_len cells) ++ tail.
 template <class F>
 __global__ void __launch_bounds__(256)
@@ -259,8 +274,8 @@ k_sparse_mismatch(const uint32_t* __restrict__ row_ptr, const uint32_t* __restri
     if ((threadIdx.x & 31u) == 0 && votes) atomicAdd(mismatches, (unsigned long long)__popc(votes));
 }
 
-Scratch g_lk_ws;     // hash slots + counts / reduction partials / mismatch counter
-Scratch g_lk_stage;  // host front ends: staged inputs and outputs
+// device scratch (per stream, common.cuh): WS_LK = hash slots + counts / reduction partials / mismatch counter,
+// WS_LK_STAGE = host front ends' staged inputs and outputs, WS_INV_SHIFT = the inversion kernel's shift cell
 
 struct SparseMatrix {
     int field;
@@ -276,6 +291,7 @@ int multiplicity_enqueue(const void* d_l, size_t n_l, const void* d_t, size_t n_
     size_t slots = 1024;
     while (slots < 2 * n_t) slots <<= 1;
     const size_t slot_bytes = align_up(slots * 4, 256);
+    Scratch& g_lk_ws = ws_slot(st, WS_LK);
     SB_TRY(g_lk_ws.reserve(slot_bytes + align_up(n_t * 4, 256)));
     uint32_t* d_slots = (uint32_t*)g_lk_ws.ptr;
     uint32_t* d_counts = (uint32_t*)((char*)g_lk_ws.ptr + slot_bytes);
@@ -293,12 +309,12 @@ int multiplicity_enqueue(const void* d_l, size_t n_l, const void* d_t, size_t n_
     return SB_OK;
 }
 
-Scratch g_inv_shift;  // the 32-byte shift cell of the inversion kernel
 
 template <class F>
 int scaled_inverse_enqueue(const void* const* d_in, const uint64_t* shift, const void* const* d_scale, void* const* d_out, int jobs, size_t n,
                            cudaStream_t st) {
     if (!n) return SB_OK;
+    Scratch& g_inv_shift = ws_slot(st, WS_INV_SHIFT);
     SB_TRY(g_inv_shift.reserve(256));
     uint64_t zero[4] = {0, 0, 0, 0};
     // stream-ordered, so back-to-back calls may reuse the cell
@@ -330,6 +346,7 @@ int sum_diff_enqueue(const void* d_a, const void* d_b, size_t n, void* d_out, cu
     const size_t cap = (size_t)rt.sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
+    Scratch& g_lk_ws = ws_slot(st, WS_LK);
     SB_TRY(g_lk_ws.reserve(blocks * 32));
     F* d_part = (F*)g_lk_ws.ptr;
     k_sum_diff<F><<<(unsigned)blocks, SUM_BLOCK, 0, st>>>((const F*)d_a, (const F*)d_b, n, d_part);
@@ -362,7 +379,7 @@ int sb_lookup_multiplicity_device(int field, const void* d_l, size_t n_l, const 
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     SB_FIELD_DISPATCH(field, multiplicity_enqueue, "sb_lookup_multiplicity_device", d_l, n_l, d_t, n_t, d_m, st);
 }
@@ -374,7 +391,7 @@ int sb_scaled_inverse_device(int field, const void* d_in, const uint64_t shift[4
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     const void* ins[1] = {d_in};
     const void* scales[1] = {d_scale};
@@ -390,7 +407,7 @@ int sb_lookup_inverses_device(int field, const void* d_l, const void* d_t, const
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     const void* ins[2] = {d_l, d_t};       // h = (l + r)^-1 and g = m (t + r)^-1 in one launch
     const void* scales[2] = {nullptr, d_m};
@@ -405,9 +422,27 @@ int sb_sum_diff_device(int field, const void* d_a, const void* d_b, size_t n, vo
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     SB_FIELD_DISPATCH(field, sum_diff_enqueue, "sb_sum_diff_device", d_a, d_b, n, d_out, st);
+}
+
+/* d_count_u64 (device, 8 bytes) = #{i < n : a[i] != b[i]}; b NULL compares with zero.  Not synchronised. */
+int sb_count_mismatch_device(int field, const void* d_a, const void* d_b, size_t n, void* d_count_u64, void* stream) {
+    if (!d_count_u64 || (n && !d_a) || (field != FIELD_FR && field != FIELD_FQ)) {
+        set_error("sb_count_mismatch_device: bad argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    SB_CUDA_TRY(cudaMemsetAsync(d_count_u64, 0, 8, st));
+    if (!n) return SB_OK;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (field == FIELD_FR) k_count_mismatch<Fr><<<blocks, 256, 0, st>>>((const Fr*)d_a, (const Fr*)d_b, n, (unsigned long long*)d_count_u64);
+    else k_count_mismatch<Fq><<<blocks, 256, 0, st>>>((const Fq*)d_a, (const Fq*)d_b, n, (unsigned long long*)d_count_u64);
+    SB_KERNEL_CHECK();
+    return SB_OK;
 }
 
 int sb_sparse_register(int field, const uint64_t* rows, const uint64_t* cols, const uint64_t* values_mont, size_t nnz, size_t N,
@@ -440,7 +475,7 @@ int sb_sparse_register(int field, const uint64_t* rows, const uint64_t* cols, co
     m->field = field;
     m->N = N;
     m->nnz = nnz;
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaError_t e1 = cudaMalloc(&m->d_row_ptr, (N + 1) * 4);
     cudaError_t e2 = cudaMalloc(&m->d_col, col.size() * 4);
     cudaError_t e3 = cudaMalloc(&m->d_val, val.size() * 8);
@@ -484,11 +519,12 @@ int sb_sparse_mismatch_device(sb_sparse_t h, const uint64_t* head, size_t head_l
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     *mismatches = 0;
     if (!m->N) return SB_OK;
     const size_t head_bytes = align_up(head_len * 32, 256);
+    Scratch& g_lk_ws = ws_slot(st, WS_LK);
     SB_TRY(g_lk_ws.reserve(256 + head_bytes));
     unsigned long long* d_cnt = (unsigned long long*)g_lk_ws.ptr;
     char* d_head = (char*)g_lk_ws.ptr + 256;
@@ -522,7 +558,7 @@ int sb_concat_pad_device(const uint64_t* const* columns, const size_t* lens, siz
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     char* dst = (char*)d_out;
     for (size_t c = 0; c < num_columns; c++) {
@@ -552,16 +588,17 @@ int sb_lookup_multiplicity(int field, const uint64_t* l, size_t n_l, const uint6
     if (!n_t) return SB_OK;
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // one critical section from staging to the synchronised download
+    Scratch& g_lk_stage = ws_slot(rt.stream, WS_LK_STAGE);
     char* d;
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
         SB_TRY(g_lk_stage.reserve(256 + (n_l + 2 * n_t) * 32));
         d = (char*)g_lk_stage.ptr + 256;
         if (n_l) SB_CUDA_TRY(cudaMemcpyAsync(d, l, n_l * 32, cudaMemcpyHostToDevice, rt.stream));
         SB_CUDA_TRY(cudaMemcpyAsync(d + n_l * 32, t, n_t * 32, cudaMemcpyHostToDevice, rt.stream));
     }
     SB_TRY(sb_lookup_multiplicity_device(field, d, n_l, d + n_l * 32, n_t, d + (n_l + n_t) * 32, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(m, d + (n_l + n_t) * 32, n_t * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;
@@ -575,16 +612,17 @@ int sb_scaled_inverse(int field, const uint64_t* in, const uint64_t shift[4], co
     if (!n) return SB_OK;
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // one critical section from staging to the synchronised download
+    Scratch& g_lk_stage = ws_slot(rt.stream, WS_LK_STAGE);
     char* d;
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
         SB_TRY(g_lk_stage.reserve(256 + 3 * n * 32));
         d = (char*)g_lk_stage.ptr + 256;
         SB_CUDA_TRY(cudaMemcpyAsync(d, in, n * 32, cudaMemcpyHostToDevice, rt.stream));
         if (scale) SB_CUDA_TRY(cudaMemcpyAsync(d + n * 32, scale, n * 32, cudaMemcpyHostToDevice, rt.stream));
     }
     SB_TRY(sb_scaled_inverse_device(field, d, shift, scale ? d + n * 32 : nullptr, d + 2 * n * 32, n, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(out, d + 2 * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;
@@ -599,9 +637,10 @@ int sb_lookup_inverses(int field, const uint64_t* l, const uint64_t* t, const ui
     if (!n) return SB_OK;
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // one critical section from staging to the synchronised download
+    Scratch& g_lk_stage = ws_slot(rt.stream, WS_LK_STAGE);
     char* d;
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
         SB_TRY(g_lk_stage.reserve(256 + 5 * n * 32));
         d = (char*)g_lk_stage.ptr + 256;
         SB_CUDA_TRY(cudaMemcpyAsync(d, l, n * 32, cudaMemcpyHostToDevice, rt.stream));
@@ -609,7 +648,7 @@ int sb_lookup_inverses(int field, const uint64_t* l, const uint64_t* t, const ui
         SB_CUDA_TRY(cudaMemcpyAsync(d + 2 * n * 32, m, n * 32, cudaMemcpyHostToDevice, rt.stream));
     }
     SB_TRY(sb_lookup_inverses_device(field, d, d + n * 32, d + 2 * n * 32, r, n, d + 3 * n * 32, d + 4 * n * 32, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(h, d + 3 * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaMemcpyAsync(g, d + 4 * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
@@ -623,16 +662,17 @@ int sb_sum_diff(int field, const uint64_t* a, const uint64_t* b, size_t n, uint6
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // one critical section from staging to the synchronised download
+    Scratch& g_lk_stage = ws_slot(rt.stream, WS_LK_STAGE);
     char* d;
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
         SB_TRY(g_lk_stage.reserve(256 + 2 * n * 32));
         d = (char*)g_lk_stage.ptr;
         if (n) SB_CUDA_TRY(cudaMemcpyAsync(d + 256, a, n * 32, cudaMemcpyHostToDevice, rt.stream));
         if (n && b) SB_CUDA_TRY(cudaMemcpyAsync(d + 256 + n * 32, b, n * 32, cudaMemcpyHostToDevice, rt.stream));
     }
     SB_TRY(sb_sum_diff_device(field, d + 256, b ? d + 256 + n * 32 : nullptr, n, d + 64, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(out, d + 64, 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;
@@ -645,9 +685,10 @@ int sb_sparse_mismatch(sb_sparse_t h, const uint64_t* Z, size_t N, uint64_t* mis
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // one critical section from staging to the synchronised download
+    Scratch& g_lk_stage = ws_slot(rt.stream, WS_LK_STAGE);
     char* d;
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
         SB_TRY(g_lk_stage.reserve(256 + N * 32));
         d = (char*)g_lk_stage.ptr + 256;
         if (N) SB_CUDA_TRY(cudaMemcpyAsync(d, Z, N * 32, cudaMemcpyHostToDevice, rt.stream));

@@ -281,7 +281,7 @@ using namespace sb;
 extern "C" int sb_microbench(int which, int iters, int blocks, int threads, double* out_ms) {
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     size_t n = (size_t)blocks * threads;
     char* d = nullptr;
     SB_CUDA_TRY(cudaMalloc(&d, n * 256 + 1024));

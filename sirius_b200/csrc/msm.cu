@@ -908,7 +908,6 @@ struct sb_ck {
 
 namespace sb {
 
-static Scratch g_ws;
 
 // Window width per key size, measured on B200 (profiles/r1_window_tuning.txt).  Only widths at which the window
 // count W = floor(254/c)+1 drops are worth having (c = 13, 15, 16, 17, 19, 20): a wider window with the same W only
@@ -995,7 +994,8 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
         // many partitions that its runs shrink to a few entries (scattered stores again): at 2^23 scalars, c = 19,
         // 1024 partitions the commit takes 34.4 ms against 23.0 ms with the counting sort (profiles/r1_large_msm_check.txt)
         const bool want = g_sort_mode == 2 || (g_sort_mode == 0 && p.nW >= ((size_t)1 << 18) && P <= 256);
-        p.parts = (legal && want) ? (uint32_t)P : 0u;
+        const size_t part_smem = ((size_t)3 * P + 256 + 2) * 4 + (size_t)256 * p.W * 8;   // k_partition's staging area
+        p.parts = (legal && want && part_smem <= 200 * 1024) ? (uint32_t)P : 0u;
     }
     p.rounds = g_affine_rounds >= 0 ? std::min(g_affine_rounds, MAX_AFFINE_ROUNDS) : auto_affine_rounds();
     p.pair_b = g_pair_b == 8 ? 8 : 16;
@@ -1058,6 +1058,8 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     return SB_OK;
 }
 
+static size_t g_part_smem_set = 0;   // largest dynamic shared-memory size k_partition has been opted into (under rt.mu)
+
 template <class F, class S>
 static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, size_t stride, void* d_out_xy,
                        void* d_out_xyzz, cudaStream_t st) {
@@ -1101,10 +1103,9 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         k_scan_small<<<1, 1024, 0, st>>>(part_count, P, part_off);
         SB_KERNEL_CHECK();
         const size_t part_smem = ((size_t)3 * P + 256 + 2) * 4 + (size_t)256 * p.W * 8;
-        static size_t part_smem_set = 0;
-        if (part_smem > part_smem_set) {
+        if (part_smem > g_part_smem_set) {   // ONE tracker for the one (non-template) kernel: the attribute only ever grows
             SB_CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
-            part_smem_set = part_smem;
+            g_part_smem_set = part_smem;
         }
         k_partition<<<(total + 255) / 256, 256, part_smem, st>>>((const uint32_t*)dig, n, total, K, (uint32_t)ck->n, p.W, P, part_off, part_cursor, out1);
         SB_KERNEL_CHECK();
@@ -1300,7 +1301,7 @@ int sb_ck_register(int curve, const uint64_t* bases_xy, size_t n, int window_bit
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     void* d_bases = nullptr;
     if (n) {
         SB_CUDA_TRY(cudaMalloc(&d_bases, n * 64));
@@ -1323,7 +1324,7 @@ int sb_ck_register_device(int curve, const void* d_bases_xy, size_t n, int windo
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     return ck_build(curve, d_bases_xy, n, window_bits, stream ? (cudaStream_t)stream : rt.stream, out);
 }
 
@@ -1343,7 +1344,7 @@ int sb_ck_add_window(sb_ck_t ck, int window_bits, void* stream) {
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     return ck_add_table(ck, ck->tables[0].table, window_bits, stream ? (cudaStream_t)stream : rt.stream);
 }
 
@@ -1381,11 +1382,13 @@ int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t
     SB_TRY(check_len(ck, n));
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     MsmPlan p;
     SB_TRY(make_plan(ck, n, batch, false, p));
-    SB_TRY(g_ws.reserve(p.total_bytes));
-    return msm_dispatch(ck, p, (char*)g_ws.ptr, d_scalars_mont, stride, d_out_xy, d_out_xyzz, stream ? (cudaStream_t)stream : rt.stream);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    Scratch& ws = ws_slot(st, WS_MSM);
+    SB_TRY(ws.reserve(p.total_bytes));
+    return msm_dispatch(ck, p, (char*)ws.ptr, d_scalars_mont, stride, d_out_xy, d_out_xyzz, st);
 }
 
 int sb_msm_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, void* d_out_xy, void* d_out_xyzz, void* stream) {
@@ -1400,12 +1403,13 @@ int sb_msm_batch(sb_ck_t ck, const uint64_t* const* scalars_mont, size_t n, size
     SB_TRY(check_len(ck, n));
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     if (batch == 0) return SB_OK;
     MsmPlan p;
     SB_TRY(make_plan(ck, n, batch, true, p));
-    SB_TRY(g_ws.reserve(p.total_bytes));
-    char* ws = (char*)g_ws.ptr;
+    Scratch& wss = ws_slot(rt.stream, WS_MSM);
+    SB_TRY(wss.reserve(p.total_bytes));
+    char* ws = (char*)wss.ptr;
     for (size_t b = 0; b < batch && n; b++) {
         if (!scalars_mont[b]) {
             set_error("sb_msm_batch: null scalar vector %zu", b);

@@ -186,8 +186,6 @@ struct NttKey {
 };
 
 static std::map<NttKey, NttTables> g_ntt_cache;
-static Scratch g_ntt_tmp;
-static Scratch g_ntt_stage;
 
 template <class F>
 static F host_pow(F g, uint64_t e) {  // runs on the host only to derive per-pass twiddle bases
@@ -281,9 +279,11 @@ static int ntt_enqueue(F* d_a, int log_n, const uint64_t omega[4], const uint64_
     if (it == g_ntt_cache.end()) {
         NttTables T;
         SB_TRY(build_tables<F>(log_n, omega, st, T));
+        SB_CUDA_TRY(cudaStreamSynchronize(st));   // the cached tables are read by later calls on ANY stream
         it = g_ntt_cache.emplace(key, T).first;
     }
     NttTables& T = it->second;
+    Scratch& g_ntt_tmp = ws_slot(st, WS_NTT_TMP);
     SB_TRY(g_ntt_tmp.reserve(n * sizeof(F)));
     F* src = d_a;
     F* dst = (F*)g_ntt_tmp.ptr;
@@ -327,7 +327,7 @@ int sb_ntt_device(int field, void* d_a, uint32_t log_n, const uint64_t omega[4],
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     return ntt_enqueue<Fr>((Fr*)d_a, (int)log_n, omega, scale, stream ? (cudaStream_t)stream : rt.stream);
 }
 
@@ -346,8 +346,9 @@ int sb_ntt(int field, uint64_t* a, uint32_t log_n, const uint64_t omega[4], cons
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     const size_t bytes = ((size_t)1 << log_n) * 32;
+    Scratch& g_ntt_stage = ws_slot(rt.stream, WS_NTT_STAGE);
     SB_TRY(g_ntt_stage.reserve(bytes));
     SB_CUDA_TRY(cudaMemcpyAsync(g_ntt_stage.ptr, a, bytes, cudaMemcpyHostToDevice, rt.stream));
     SB_TRY(ntt_enqueue<Fr>((Fr*)g_ntt_stage.ptr, (int)log_n, omega, scale, rt.stream));
@@ -374,7 +375,7 @@ int sb_coset_scale_device(int field, void* d_a, size_t n, const uint64_t z[4], c
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     return coset_scale_impl((Fr*)d_a, n, z, z2, stream ? (cudaStream_t)stream : rt.stream);
 }
 
@@ -385,7 +386,8 @@ int sb_coset_scale(int field, uint64_t* a, size_t n, const uint64_t z[4], const 
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
+    Scratch& g_ntt_stage = ws_slot(rt.stream, WS_NTT_STAGE);
     SB_TRY(g_ntt_stage.reserve(n * 32 + 32));
     SB_CUDA_TRY(cudaMemcpyAsync(g_ntt_stage.ptr, a, n * 32, cudaMemcpyHostToDevice, rt.stream));
     SB_TRY(coset_scale_impl((Fr*)g_ntt_stage.ptr, n, z, z2, rt.stream));

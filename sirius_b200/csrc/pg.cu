@@ -87,7 +87,6 @@ __global__ void k_lincomb(const F* const* __restrict__ ins, const F* __restrict_
     st32(out + i, acc);
 }
 
-static Scratch g_pg_ws;
 
 template <class F>
 static int beta_tree_enqueue(const void* d_leaves, uint32_t log_n, size_t num_points, size_t leaf_stride,
@@ -96,6 +95,7 @@ static int beta_tree_enqueue(const void* d_leaves, uint32_t log_n, size_t num_po
     const size_t groups0 = log_n > (uint32_t)TREE_GROUP_LOG ? (n >> TREE_GROUP_LOG) : 1;
     const size_t c_bytes = align_up(32 * num_points * (log_n ? log_n : 1), 256);
     const size_t tmp_elems = num_points * groups0;
+    Scratch& g_pg_ws = ws_slot(st, WS_PG);
     SB_TRY(g_pg_ws.reserve(c_bytes + 2 * align_up(tmp_elems * 32, 256)));
     char* ws = (char*)g_pg_ws.ptr;
     F* d_c = (F*)ws;
@@ -130,11 +130,11 @@ static int beta_tree_enqueue(const void* d_leaves, uint32_t log_n, size_t num_po
     return SB_OK;
 }
 
-static Scratch g_lincomb_args;
 
 template <class F>
 static int lincomb_enqueue(const void* const* d_inputs, const uint64_t* coef, size_t J, size_t n, void* d_out, cudaStream_t st) {
     const size_t ptr_bytes = align_up(sizeof(void*) * J, 32);
+    Scratch& g_lincomb_args = ws_slot(st, WS_LINCOMB_ARGS);
     SB_TRY(g_lincomb_args.reserve(ptr_bytes + 32 * J));
     char* d = (char*)g_lincomb_args.ptr;
     SB_CUDA_TRY(cudaMemcpyAsync(d, d_inputs, sizeof(void*) * J, cudaMemcpyHostToDevice, st));
@@ -160,7 +160,7 @@ int sb_beta_tree_device(int field, const void* d_leaves, uint32_t log_n, size_t 
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     if (field == FIELD_FR) return beta_tree_enqueue<Fr>(d_leaves, log_n, num_points, leaf_stride, multipliers, d_out, st);
     if (field == FIELD_FQ) return beta_tree_enqueue<Fq>(d_leaves, log_n, num_points, leaf_stride, multipliers, d_out, st);
@@ -175,7 +175,7 @@ int sb_lincomb_device(int field, const void* const* d_inputs, const uint64_t* co
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     if (field == FIELD_FR) return lincomb_enqueue<Fr>(d_inputs, coef, num_inputs, n, d_out, st);
     if (field == FIELD_FQ) return lincomb_enqueue<Fq>(d_inputs, coef, num_inputs, n, d_out, st);
@@ -183,7 +183,6 @@ int sb_lincomb_device(int field, const void* const* d_inputs, const uint64_t* co
     return SB_ERR_ARG;
 }
 
-static Scratch g_pg_stage;
 
 /* Host-memory front end: leaves for `num_blends` Lagrange blends of `num_traces` witnesses (single round each),
  * then the beta tree for `num_points` points (point p reads blend point_blend[p]). */
@@ -197,6 +196,8 @@ int sb_pg_tree(sb_prog_t const* gates, size_t num_gates, sb_columns_t cols, uint
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);   // one critical section from staging to the synchronised download (the stage buffer is shared)
+    Scratch& g_pg_stage = ws_slot(rt.stream, WS_PG_STAGE);
     const size_t n = (size_t)1 << sb_columns_log_rows(cols);
     const size_t leaves = (size_t)1 << log_leaves;
     const size_t w_bytes = align_up((size_t)num_advice * n * 32, 256);
@@ -205,7 +206,7 @@ int sb_pg_tree(sb_prog_t const* gates, size_t num_gates, sb_columns_t cols, uint
     const int field = sb_expr_field(gates[0]);
     std::vector<const void*> tables((size_t)num_advice * num_traces);
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
+        RtLock lk(rt.mu);
         SB_TRY(g_pg_stage.reserve(out_off + 32 * num_points + 256));
         char* base = (char*)g_pg_stage.ptr;
         for (size_t j = 0; j < num_traces; j++) {
@@ -232,7 +233,7 @@ int sb_pg_tree(sb_prog_t const* gates, size_t num_gates, sb_columns_t cols, uint
         }
         p = q + 1;
     }
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(out, base + out_off, 32 * num_points, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;
@@ -246,9 +247,11 @@ int sb_lincomb(int field, const uint64_t* const* inputs, const uint64_t* coef, s
     }
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
+    RtLock lk_call(rt.mu);
+    Scratch& g_pg_stage = ws_slot(rt.stream, WS_PG_STAGE);
     std::vector<const void*> ptrs(num_inputs);
     {
-        std::lock_guard<std::mutex> lk(rt.mu);
+        RtLock lk(rt.mu);
         SB_TRY(g_pg_stage.reserve((num_inputs + 1) * n * 32 + 256));
         char* base = (char*)g_pg_stage.ptr;
         for (size_t j = 0; j < num_inputs; j++) {
@@ -258,7 +261,7 @@ int sb_lincomb(int field, const uint64_t* const* inputs, const uint64_t* coef, s
     }
     char* base = (char*)g_pg_stage.ptr;
     SB_TRY(sb_lincomb_device(field, ptrs.data(), coef, num_inputs, n, base + num_inputs * n * 32, nullptr));
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     SB_CUDA_TRY(cudaMemcpyAsync(out, base + num_inputs * n * 32, n * 32, cudaMemcpyDeviceToHost, rt.stream));
     SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
     return SB_OK;

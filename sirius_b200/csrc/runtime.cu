@@ -2,6 +2,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
@@ -22,12 +24,14 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct ProfileRec { cudaEvent_t e0, e1; uint64_t units; int tag; };
-static bool g_profile = false;
+static std::atomic<bool> g_profile{false};
+static std::mutex g_prof_mu;   // the records are touched from any thread that enqueues (ProfScope) and by sb_profile_collect
 static std::vector<ProfileRec> g_prof;
 static std::vector<ProfileRec> g_prof_pool;
-bool profile_enabled() { return g_profile; }
+bool profile_enabled() { return g_profile.load(std::memory_order_relaxed); }
 int profile_begin(cudaStream_t st, int tag, uint64_t units) {
-    if (!g_profile) return -1;
+    if (!profile_enabled()) return -1;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     ProfileRec rec;
     if (!g_prof_pool.empty()) {
         rec = g_prof_pool.back();
@@ -43,7 +47,9 @@ int profile_begin(cudaStream_t st, int tag, uint64_t units) {
     return (int)g_prof.size() - 1;
 }
 void profile_end(cudaStream_t st, int handle) {
-    if (handle < 0 || handle >= (int)g_prof.size()) return;
+    if (handle < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (handle >= (int)g_prof.size()) return;
     cudaEventRecord(g_prof[handle].e1, st);
 }
 
@@ -64,24 +70,28 @@ static int init_locked(Runtime& rt, int device) {
     }
     int cur = 0;
     SB_CUDA_TRY(cudaGetDevice(&cur));
-    if (rt.ready && rt.device == cur) return SB_OK;
+    if (rt.ready.load() && rt.device == cur) return SB_OK;
     cudaDeviceProp prop;
     SB_CUDA_TRY(cudaGetDeviceProperties(&prop, cur));
     if (prop.major < 10) {
         set_error("device %d is sm_%d%d; this library is built for sm_100a only", cur, prop.major, prop.minor);
         return SB_ERR_CUDA;
     }
-    if (rt.stream) cudaStreamDestroy(rt.stream);
+    if (rt.stream) {   // re-initialisation on another device: the old device's scratch goes with its stream
+        cudaStreamSynchronize(rt.stream);
+        ws_release_all();
+        cudaStreamDestroy(rt.stream);
+    }
     SB_CUDA_TRY(cudaStreamCreateWithFlags(&rt.stream, cudaStreamNonBlocking));
     rt.device = cur;
     rt.sm_count = prop.multiProcessorCount;
-    rt.ready = true;
+    rt.ready.store(true, std::memory_order_release);
     return SB_OK;
 }
 
 int ensure_runtime() {
     Runtime& rt = runtime();
-    if (rt.ready) {
+    if (rt.ready.load(std::memory_order_acquire)) {
         // calls may come from any host thread (cargo test): bind the thread to the library's device
         cudaError_t e = cudaSetDevice(rt.device);
         if (e != cudaSuccess) {
@@ -90,7 +100,7 @@ int ensure_runtime() {
         }
         return SB_OK;
     }
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     return init_locked(rt, -1);
 }
 
@@ -123,6 +133,26 @@ void Scratch::release() {
     if (ptr) cudaFree(ptr);
     ptr = nullptr;
     cap = 0;
+}
+
+// per-stream scratch slots (callers hold runtime().mu)
+struct StreamSlots { Scratch slot[WS_NUM_SLOTS]; };
+static std::map<cudaStream_t, std::unique_ptr<StreamSlots>> g_stream_ws;
+Scratch& ws_slot(cudaStream_t st, int slot) {
+    auto it = g_stream_ws.find(st);
+    if (it == g_stream_ws.end()) it = g_stream_ws.emplace(st, std::unique_ptr<StreamSlots>(new StreamSlots())).first;
+    return it->second->slot[slot];
+}
+void ws_release_stream(cudaStream_t st) {
+    auto it = g_stream_ws.find(st);
+    if (it == g_stream_ws.end()) return;
+    for (int i = 0; i < WS_NUM_SLOTS; i++) it->second->slot[i].release();
+    g_stream_ws.erase(it);
+}
+void ws_release_all() {
+    for (auto& kv : g_stream_ws)
+        for (int i = 0; i < WS_NUM_SLOTS; i++) kv.second->slot[i].release();
+    g_stream_ws.clear();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -163,7 +193,7 @@ int sb_version(void) { return 1; }
 
 uint64_t sb_launch_count(void) { return g_launches.load(); }
 
-void sb_profile_enable(int on) { g_profile = on != 0; }
+void sb_profile_enable(int on) { g_profile.store(on != 0); }
 
 /* Per-tag sums of the instrumented launch groups since the last call (synchronises the recorded events).
  * Arrays of SB_PROF_NUM_TAGS entries each; any may be NULL. */
@@ -173,6 +203,7 @@ int sb_profile_collect(double* total_ms, uint64_t* total_units, uint64_t* launch
         if (total_units) total_units[t] = 0;
         if (launches) launches[t] = 0;
     }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& rec : g_prof) {
         cudaError_t e = cudaEventSynchronize(rec.e1);
         float ms = 0;
@@ -198,26 +229,37 @@ int sb_device_count(void) {
 
 int sb_init(int device) {
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     return init_locked(rt, device);
 }
 
 void sb_shutdown(void) {
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     if (rt.stream) {
         cudaStreamSynchronize(rt.stream);
+        cudaDeviceSynchronize();
+        ws_release_all();
         cudaStreamDestroy(rt.stream);
         rt.stream = nullptr;
     }
-    rt.ready = false;
+    rt.ready.store(false);
+}
+
+/* Frees the per-stream device scratch the library keeps for `stream` (call before destroying a stream that was
+ * passed to _device entry points; the stream must be idle). */
+void sb_stream_release(void* stream) {
+    Runtime& rt = runtime();
+    RtLock lk(rt.mu);
+    if (stream) cudaStreamSynchronize((cudaStream_t)stream);
+    ws_release_stream((cudaStream_t)stream);
 }
 
 int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul_ptx, uint64_t* out_mul_portable,
                       uint64_t* out_add, uint64_t* out_sub, uint64_t* out_inv) {
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     char* d = nullptr;
     size_t bytes = n * 32;
     SB_CUDA_TRY(cudaMalloc(&d, bytes * 7));
@@ -253,7 +295,7 @@ int sb_selftest_lazy(int field, const uint64_t* a, const uint64_t* b, size_t n, 
                      uint64_t* out_canon) {
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
-    std::lock_guard<std::mutex> lk(rt.mu);
+    RtLock lk(rt.mu);
     char* d = nullptr;
     size_t bytes = n * 32;
     SB_CUDA_TRY(cudaMalloc(&d, bytes * 6));

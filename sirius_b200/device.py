@@ -35,14 +35,17 @@ class DeviceSangriaSide:
         self.d = S.degree
         dev = torch.device("cuda", torch.cuda.current_device())
         i64 = torch.int64
-        self.W_acc = torch.zeros((self.A * self.n, 4), dtype=i64, device=dev)
-        self.W_new = torch.zeros_like(self.W_acc)
-        self.W_in = torch.zeros_like(self.W_acc)
-        self.E_acc = torch.zeros((self.n, 4), dtype=i64, device=dev)
-        self.E_new = torch.zeros_like(self.E_acc)
-        self.T = torch.zeros((self.d, self.n, 4), dtype=i64, device=dev)
-        self.commit_W = torch.zeros(8, dtype=i64, device=dev)
-        self.commit_T = torch.zeros((self.d, 8), dtype=i64, device=dev)
+        # allocated AND zero-filled on the session's stream: every later kernel / copy touching them runs there too
+        with torch.cuda.stream(stream):
+            self.W_acc = torch.zeros((self.A * self.n, 4), dtype=i64, device=dev)
+            self.W_new = torch.zeros_like(self.W_acc)
+            self.W_in = torch.zeros_like(self.W_acc)
+            self.E_acc = torch.zeros((self.n, 4), dtype=i64, device=dev)
+            self.E_new = torch.zeros_like(self.E_acc)
+            self.T = torch.zeros((self.d, self.n, 4), dtype=i64, device=dev)
+            self.commit_W = torch.zeros(8, dtype=i64, device=dev)
+            self.commit_T = torch.zeros((self.d, 8), dtype=i64, device=dev)
+        stream.synchronize()
         self.h_commit_W = torch.zeros(8, dtype=i64).pin_memory()
         self.h_commit_T = torch.zeros((self.d, 8), dtype=i64).pin_memory()
         self.one = _to_mont([1], S.modulus)
@@ -124,7 +127,8 @@ def synthetic_key(curve: int, n: int, window_bits: int = 0, stream=None) -> Comm
     from .curves import generator_limbs
 
     lib = _lib.load()
-    d = torch.zeros((n, 8), dtype=torch.int64, device="cuda")
+    d = torch.empty((n, 8), dtype=torch.int64, device="cuda")   # fully written by the kernel below (no fill on another stream)
+    torch.cuda.synchronize()
     g = generator_limbs(curve)
     st = stream.cuda_stream if stream is not None else 0
     _lib.check(lib.sb_index_multiples_device(curve, g.ctypes.data_as(_lib.u64p), 0, n, ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(st or None)))
@@ -144,4 +148,4 @@ def random_field_device(n: int, seed: int):
     g.manual_seed(seed)
     t = torch.randint(-(2**63), 2**63 - 1, (n, 4), dtype=torch.int64, device="cuda", generator=g)
     t[:, 3] &= 0x0FFFFFFFFFFFFFFF
-    return t
+    return t   # produced on torch's CURRENT stream: call inside `with torch.cuda.stream(s)` or synchronise before cross-stream use

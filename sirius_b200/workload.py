@@ -1,0 +1,304 @@
+"""The Sangria `fold_step` prover hot path at the shapes of benches/sangria_poseidon, as a device-resident session.
+
+One `step()` is the hot path of `IVC::fold_step` (reference src/ivc/sangria/incrementally_verifiable_computation.rs:428-635,
+SURVEY 3.1), in the reference's call order:
+
+  1. VanillaFS::prove, secondary side (grumpkin; A=7, F=15, 1 gate, d=5): 5 cross-term vectors + 5 commits, W/E fold
+  2. generate_plonk_trace, primary side (bn256): commit W, 12 * 2^k scalars
+  3. VanillaFS::prove, primary side (bn256; A=12, F=26, 2 gates, d=6): 6 cross terms + 6 commits + folds
+  4. generate_plonk_trace, secondary side: commit W, 7 * 2^k scalars
+
+plus, as separately timed stages, the rest of the measured bench iteration (benches/sangria_poseidon.rs:159-175,
+`IVC::fold(.., 1)` = `new` + `fold_step` + `verify`): `new_leg()` = the two W commits of `IVC::new`, `verify_leg()` = the
+deciders (src/nifs/sangria/mod.rs:334-383, 455-474; src/plonk/mod.rs:304-361).
+
+This module is what bench.py times AND what tests/test_gpu_workload.py checks against the oracle (it never imports the
+oracle itself).  N > 1: rows are sharded over the ranks (sharding.py), every commitment group is one exchange of 128-byte
+XYZZ partial sums + a combine kernel.  torch is used for device memory, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import _lib, curves, device, sharding
+from . import polynomial as P
+from . import sangria as SG
+from .commitment import CommitmentKey
+
+PRIMARY = dict(name="primary", curve=0, field=0, T_list=[5, 3])   # bn256 / Fr : MainGate<5> + Poseidon MainGate<3>
+SECONDARY = dict(name="secondary", curve=1, field=1, T_list=[5])  # grumpkin / Fq : MainGate<5> (trivial step circuit)
+SEED = 0x5349524955530000
+
+
+def shapes(side):
+    nfix = sum(2 * T + 5 for T in side["T_list"])
+    nadv = sum(T + 2 for T in side["T_list"])
+    return nfix, nadv
+
+
+def compressed_gates(side, mod=P):
+    """The compressed MainGate expressions of one side, built with `mod` = sirius_b200.polynomial (product) or the
+    oracle's expr_ref (same constructor names) -- the callers pass their own module so this file never imports oracle/."""
+    nfix, nadv = shapes(side)
+    gates, fb, ab = [], 0, 0
+    for T in side["T_list"]:
+        gates.append(mod.main_gate_expression(T, fb, ab, 0, nfix))
+        fb += 2 * T + 5
+        ab += T + 2
+    return gates, nfix, nadv
+
+
+def default_windows(k: int) -> List[int]:
+    """Window widths registered per key: the W commits want wide windows, the batched 2^k cross-term commits narrower ones."""
+    env = os.environ.get("SB_BENCH_WINDOWS")
+    if env:
+        return [int(x) for x in env.split(",")]
+    if k >= 19:
+        return [17, 20]
+    return [16, 13, 15, 17]
+
+
+class Combiner:
+    """N > 1: all-gather the XYZZ partial sums of a commitment group and add them."""
+
+    def __init__(self, world, stream):
+        import torch
+
+        self.world, self.stream, self.torch = world, stream, torch
+        self.bufs = {}
+
+    def _buffers(self, batch):
+        torch = self.torch
+        if batch not in self.bufs:
+            with torch.cuda.stream(self.stream):
+                self.bufs[batch] = (torch.zeros((batch, 16), dtype=torch.int64, device="cuda"),
+                                    torch.zeros((self.world, batch, 16), dtype=torch.int64, device="cuda"),
+                                    torch.zeros((batch, 8), dtype=torch.int64, device="cuda"))
+        return self.bufs[batch]
+
+    def commit(self, ck: CommitmentKey, d_scalars: int, n: int, batch: int, h_out) -> None:
+        import torch
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        part, gathered, out = self._buffers(batch)
+        ck.commit_batch_device(d_scalars, n, n, batch, 0, part.data_ptr(), self.stream.cuda_stream)
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(gathered, part)
+        _lib.check(lib.sb_msm_combine_batch_device(ck.curve, ctypes.c_void_p(gathered.data_ptr()), self.world, batch, batch,
+                                                   ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(self.stream.cuda_stream)))
+        with torch.cuda.stream(self.stream):
+            h_out.copy_(out.view(h_out.shape), non_blocking=True)
+        self.stream.synchronize()
+
+
+class SangriaStepWorkload:
+    """Both sides of the cycle, device-resident, restricted to this rank's rows."""
+
+    def __init__(self, k: int, rank: int = 0, world: int = 1, stream=None, windows: Optional[List[int]] = None, seed: int = SEED):
+        import torch
+
+        self.torch = torch
+        self.k, self.rank, self.world, self.seed = k, rank, world, seed
+        self.stream = stream if stream is not None else torch.cuda.Stream()
+        self.windows = windows or default_windows(k)
+        self.lib = _lib.load()
+        self.sides: List[device.DeviceSangriaSide] = []
+        self.extras: List[Dict] = []
+        for side in (PRIMARY, SECONDARY):
+            sess, ex = self._build_side(side)
+            self.sides.append(sess)
+            self.extras.append(ex)
+        self.combiner = Combiner(world, self.stream) if world > 1 else None
+        self.stream.synchronize()
+
+    # ------------------------------------------------------------------ construction
+    def _build_side(self, side):
+        torch = self.torch
+        stream, rank, world, k = self.stream, self.rank, self.world, self.k
+        gates, nfix, nadv = compressed_gates(side)
+        cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_fixed=nfix, num_advice=nadv))
+        n = 1 << k
+        row0, n_loc = sharding.row_slice(rank, world, n)
+        k_loc = n_loc.bit_length() - 1
+        modulus = curves.SCALAR_FIELD[side["curve"]]
+        seed = self.seed
+        with torch.cuda.stream(stream):
+            d_fixed = [device.random_field_device(n_loc, seed + 1000 * side["curve"] + 10 * rank + j) for j in range(nfix)]
+        stream.synchronize()   # .cpu() below runs on the default stream
+        fixed = [t.cpu().numpy().view(np.uint64) for t in d_fixed]
+        del d_fixed
+        S = SG.PlonkStructure(side["field"], modulus, k_loc, [], fixed, nadv, 0, cg)
+        if world > 1:
+            sharding.check_rotations_row_local(P.GraphEvaluator.new(cg.homogeneous, modulus).rotations)
+        # commitment key restricted to this rank's rows: ck[col * n + row] for row in the slice, column-major
+        # (the benches' key has 2^(k+4) generators, benches/sangria_poseidon.rs:26-30; only the prefix W needs is materialised)
+        assert nadv * n <= (1 << (k + 4))
+        with torch.cuda.stream(stream):
+            d_bases = torch.empty((nadv * n_loc, 8), dtype=torch.int64, device="cuda")
+        g = curves.generator_limbs(side["curve"])
+        for col, (first, count) in enumerate(sharding.key_segments(nadv, n, rank, world)):
+            _lib.check(self.lib.sb_index_multiples_device(side["curve"], g.ctypes.data_as(_lib.u64p), first, count,
+                                                          ctypes.c_void_p(d_bases.data_ptr() + col * n_loc * 64), ctypes.c_void_p(stream.cuda_stream)))
+        stream.synchronize()
+        ck = CommitmentKey.from_device(side["curve"], d_bases.data_ptr(), nadv * n_loc, window_bits=self.windows[0], stream=stream.cuda_stream)
+        for wb in self.windows[1:]:
+            ck.add_window(wb, stream.cuda_stream)
+        stream.synchronize()
+        del d_bases
+        sess = device.DeviceSangriaSide(S, ck, stream)
+        with torch.cuda.stream(stream):
+            sess.W_acc.copy_(device.random_field_device(nadv * n_loc, seed + 7 + side["curve"] + 100 * rank))
+            sess.E_acc.copy_(device.random_field_device(n_loc, seed + 8 + side["curve"] + 100 * rank))
+            sess.W_in.copy_(device.random_field_device(nadv * n_loc, seed + 9 + side["curve"] + 100 * rank))
+        stream.synchronize()
+        host_W = torch.empty(sess.W_in.shape, dtype=torch.int64).pin_memory()
+        host_W.copy_(sess.W_in)
+        torch.cuda.synchronize()
+        nch = cg.ctx.num_challenges - 1
+        with torch.cuda.stream(stream):
+            d_ch = device.random_field_device(2 * nch + 2, seed + 11 + side["curve"])   # identical on every rank
+        stream.synchronize()
+        ch = d_ch.cpu().numpy().view(np.uint64)
+        extra = dict(side=side, host_W=host_W, c1=ch[:nch], c2=ch[nch:2 * nch], u1=ch[2 * nch], r=ch[2 * nch + 1], nadv=nadv, nfix=nfix,
+                     n_loc=n_loc, fixed=fixed)
+        return sess, extra
+
+    # ------------------------------------------------------------------ the timed step
+    def _prove(self, sess, ex):
+        if self.combiner is None:
+            sess.commit_cross_terms(ex["c1"], ex["u1"], ex["c2"])
+        else:
+            c1, c2 = sess.challenge_vectors(ex["c1"], ex["u1"], ex["c2"])
+            _lib.check(self.lib.sb_cross_terms_device(sess.S._hom_prog._h, sess.d, sess.S._cols, sess._cols(sess.W_acc), sess._cols(sess.W_in), sess.A,
+                                                      c1.ctypes.data_as(_lib.u64p), c2.ctypes.data_as(_lib.u64p), c1.shape[0],
+                                                      ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(sess.stream.cuda_stream)))
+            self.combiner.commit(sess.ck, sess.T.data_ptr(), sess.n, sess.d, sess.h_commit_T)
+        sess.fold(ex["r"])
+
+    def _commit_w(self, sess, ex, upload) -> int:
+        h2d = 0
+        if upload:
+            h2d = sess.upload_incoming(ex["host_W"])
+        if self.combiner is None:
+            sess.commit_incoming()
+        else:
+            self.combiner.commit(sess.ck, sess.W_in.data_ptr(), sess.A * sess.n, 1, sess.h_commit_W)
+        return h2d
+
+    def step(self, upload: bool = False) -> int:
+        """One fold_step hot path.  Returns the bytes copied host -> device."""
+        prim, sec = self.sides
+        ep, es = self.extras
+        h2d = 0
+        self._prove(sec, es)                     # 1. fold the secondary accumulator
+        h2d += self._commit_w(prim, ep, upload)  # 2. primary trace: commit W
+        self._prove(prim, ep)                    # 3. fold the primary accumulator
+        h2d += self._commit_w(sec, es, upload)   # 4. secondary trace: commit W
+        return h2d
+
+    # ------------------------------------------------------------------ the rest of the bench iteration
+    def new_leg(self) -> None:
+        """`IVC::new`: the first traces' W commits on both sides (incrementally_verifiable_computation.rs:240-330)."""
+        for sess, ex in zip(self.sides, self.extras):
+            self._commit_w(sess, ex, False)
+
+    def verify_leg(self) -> Dict[str, int]:
+        """`IVC::verify` deciders on both sides: is_sat_accumulation (homogeneous gate polynomial on (W_acc, challenges ++ [u])
+        against E, row by row), is_sat_witness_commit (re-commit W_acc and E), PlonkStructure::is_sat of the incoming trace
+        (compressed gate on W_in against zero + re-commit W_in).  Returns the mismatch counts this rank saw (the synthetic
+        columns do not satisfy the relation; the work is the same)."""
+        torch = self.torch
+        out = {}
+        for sess, ex in zip(self.sides, self.extras):
+            S, st = sess.S, sess.stream.cuda_stream
+            if getattr(sess, "_rows", None) is None:
+                with torch.cuda.stream(sess.stream):
+                    sess._rows = torch.empty((sess.n, 4), dtype=torch.int64, device="cuda")
+                    sess._cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+                    sess._h_cnt = torch.zeros(2, dtype=torch.int64).pin_memory()
+                    sess._E_commit = torch.zeros(8, dtype=torch.int64, device="cuda")
+                    sess._h_E_commit = torch.zeros(8, dtype=torch.int64).pin_memory()
+                if getattr(S, "_compressed_prog", None) is None:
+                    S._compressed_prog = SG.Program(S.field, P.GraphEvaluator.new(S.custom_gates_lookup_compressed.compressed, S.modulus))
+            ch_acc = np.ascontiguousarray(np.concatenate([ex["c1"].reshape(-1, 4), ex["u1"].reshape(1, 4)]), dtype=np.uint64)
+            ch_in = np.ascontiguousarray(ex["c2"].reshape(-1, 4), dtype=np.uint64)
+            # is_sat_accumulation: evaluate, compare with E
+            _lib.check(self.lib.sb_expr_eval_device(S._hom_prog._h, S._cols, sess._cols(sess.W_acc), None, sess.A, ch_acc.ctypes.data_as(_lib.u64p), ch_acc.shape[0],
+                                                    ctypes.c_void_p(sess._rows.data_ptr()), ctypes.c_void_p(st)))
+            _lib.check(self.lib.sb_count_mismatch_device(S.field, ctypes.c_void_p(sess._rows.data_ptr()), ctypes.c_void_p(sess.E_acc.data_ptr()), sess.n,
+                                                         ctypes.c_void_p(sess._cnt.data_ptr()), ctypes.c_void_p(st)))
+            # PlonkStructure::is_sat of the incoming trace: compressed gate == 0 on every row
+            _lib.check(self.lib.sb_expr_eval_device(S._compressed_prog._h, S._cols, sess._cols(sess.W_in), None, sess.A,
+                                                    ch_in.ctypes.data_as(_lib.u64p) if ch_in.shape[0] else None, ch_in.shape[0],
+                                                    ctypes.c_void_p(sess._rows.data_ptr()), ctypes.c_void_p(st)))
+            _lib.check(self.lib.sb_count_mismatch_device(S.field, ctypes.c_void_p(sess._rows.data_ptr()), None, sess.n,
+                                                         ctypes.c_void_p(sess._cnt.data_ptr() + 8), ctypes.c_void_p(st)))
+            with torch.cuda.stream(sess.stream):
+                sess._h_cnt.copy_(sess._cnt, non_blocking=True)
+            # is_sat_witness_commit: W_acc, E, and the incoming W re-open
+            self._recommit(sess, sess.W_acc.data_ptr(), sess.A * sess.n, sess.h_commit_W, sess.commit_W)
+            self._recommit(sess, sess.E_acc.data_ptr(), sess.n, sess._h_E_commit, sess._E_commit)
+            self._recommit(sess, sess.W_in.data_ptr(), sess.A * sess.n, sess.h_commit_W, sess.commit_W)
+            out[ex["side"]["name"]] = (int(sess._h_cnt[0]), int(sess._h_cnt[1]))
+        return out
+
+    def _recommit(self, sess, d_scalars, n, h_out, d_out):
+        if self.combiner is None:
+            sess.ck.commit_device(d_scalars, n, d_out.data_ptr(), 0, sess.stream.cuda_stream)
+            with self.torch.cuda.stream(sess.stream):
+                h_out.copy_(d_out, non_blocking=True)
+            sess.stream.synchronize()
+        else:
+            self.combiner.commit(sess.ck, d_scalars, n, 1, h_out)
+
+    # ------------------------------------------------------------------ state in/out for verification
+    def _gather_cm(self, t, ncols):
+        """local column-major [ncols * n_loc, 4] -> global column-major host array [ncols * n, 4] (every rank gets it)."""
+        torch = self.torch
+        self.stream.synchronize()
+        if self.world == 1:
+            return t.cpu().numpy().view(np.uint64).copy()
+        import torch.distributed as dist
+
+        n_loc = t.shape[0] // ncols
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        torch.cuda.synchronize()
+        full = out.view(self.world, ncols, n_loc, 4).permute(1, 0, 2, 3).contiguous().view(ncols * self.world * n_loc, 4)
+        return full.cpu().numpy().view(np.uint64).copy()
+
+    def snapshot_inputs(self) -> Dict[str, Dict]:
+        """Host copies of everything one step reads, in the reference's global layout (all ranks must call)."""
+        torch = self.torch
+        snap = {}
+        for sess, ex in zip(self.sides, self.extras):
+            fixed_loc = torch.from_numpy(np.concatenate([f.reshape(-1, 4) for f in ex["fixed"]]).view(np.int64)).cuda()
+            fixed = self._gather_cm(fixed_loc, ex["nfix"])
+            n = 1 << self.k
+            snap[ex["side"]["name"]] = dict(
+                side=ex["side"], k=self.k, nadv=ex["nadv"], nfix=ex["nfix"],
+                fixed=[fixed[j * n:(j + 1) * n] for j in range(ex["nfix"])],
+                W1=self._gather_cm(sess.W_acc, ex["nadv"]), E1=self._gather_cm(sess.E_acc, 1), W2=self._gather_cm(sess.W_in, ex["nadv"]),
+                c1=ex["c1"].copy(), c2=ex["c2"].copy(), u1=ex["u1"].copy(), r=ex["r"].copy(),
+            )
+        return snap
+
+    def snapshot_results(self) -> Dict[str, Dict]:
+        """Host copies of what the last step produced: the commitments the host read back and the folded accumulator."""
+        res = {}
+        for sess, ex in zip(self.sides, self.extras):
+            res[ex["side"]["name"]] = dict(
+                commits_T=sess.h_commit_T.numpy().view(np.uint64).copy(), commit_W=sess.h_commit_W.numpy().view(np.uint64).copy(),
+                W=self._gather_cm(sess.W_acc, ex["nadv"]), E=self._gather_cm(sess.E_acc, 1),
+            )
+        return res
+
+    def close(self):
+        for sess in self.sides:
+            sess.S.close()
+            sess.ck.close()

@@ -1,0 +1,200 @@
+"""The objects bench.py times (`sirius_b200.workload.SangriaStepWorkload` over `device.DeviceSangriaSide`), checked bit for
+bit against the CPU restatement of the reference at the bench's own shapes: A=12,F=26,d=6 (bn256) and A=7,F=15,d=5
+(grumpkin) at k=17 with the bench's four-width key, plus the `new` / `verify` legs and the multi-GPU path (torchrun)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _check_step(k, windows=None, steps=1):
+    import torch
+
+    from oracle import step_ref
+    from sirius_b200 import workload as WL
+
+    wl = WL.SangriaStepWorkload(k, 0, 1, torch.cuda.Stream(), windows=windows)
+    try:
+        for i in range(steps):
+            snap = wl.snapshot_inputs()
+            wl.step(upload=(i % 2 == 0))
+            got = wl.snapshot_results()
+            exp = step_ref.fold_step(snap, step_ref.bases_for(snap))
+            rep = step_ref.compare(got, exp)
+            assert rep["ok"], rep["bad"]
+            assert len(rep["checked"]) == 8
+    finally:
+        wl.close()
+
+
+def test_fold_step_small_two_steps(oracle):
+    _check_step(10, windows=[11, 8], steps=2)   # the second step folds the first step's accumulator
+
+
+def test_fold_step_bench_shapes_k17(oracle):
+    from sirius_b200 import workload as WL
+
+    assert WL.default_windows(17) == [16, 13, 15, 17]
+    _check_step(17)
+
+
+def test_new_and_verify_legs(oracle):
+    import torch
+
+    from sirius_b200 import sangria as SG
+    from sirius_b200 import workload as WL
+    import oracle as O
+
+    wl = WL.SangriaStepWorkload(9, 0, 1, torch.cuda.Stream(), windows=[10])
+    try:
+        wl.new_leg()
+        for sess, ex in zip(wl.sides, wl.extras):   # IVC::new commits the incoming W
+            W = sess.W_in.cpu().numpy().view(np.uint64)
+            bases = O.running_bases(ex["side"]["curve"], W.shape[0])
+            assert np.array_equal(sess.h_commit_W.numpy().view(np.uint64), O.msm(ex["side"]["curve"], W, bases))
+        counts = wl.verify_leg()
+        n = 1 << 9
+        assert counts == {"primary": (n, n), "secondary": (n, n)}   # uniform synthetic columns satisfy no row
+        # make the accumulator satisfy the relaxed relation: E := the evaluated rows -> is_sat_accumulation sees 0 mismatches
+        for sess, ex in zip(wl.sides, wl.extras):
+            ch = np.concatenate([ex["c1"].reshape(-1, 4), ex["u1"].reshape(1, 4)])
+            rows = SG.evaluate_rows(sess.S, sess.S._hom_prog, [sess.W_acc.cpu().numpy().view(np.uint64)], ch)
+            sess.E_acc.copy_(torch.from_numpy(rows.view(np.int64)).cuda())
+            torch.cuda.synchronize()
+        counts = wl.verify_leg()
+        assert counts["primary"][0] == 0 and counts["secondary"][0] == 0
+        for sess, ex in zip(wl.sides, wl.extras):   # the last re-commit of the leg is W_in again; E's commitment is checked too
+            E = sess.E_acc.cpu().numpy().view(np.uint64)
+            bases = O.running_bases(ex["side"]["curve"], E.shape[0])
+            assert np.array_equal(sess._h_E_commit.numpy().view(np.uint64), O.msm(ex["side"]["curve"], E, bases))
+    finally:
+        wl.close()
+
+
+def test_count_mismatch_device():
+    import ctypes
+
+    import torch
+
+    from sirius_b200 import _lib
+
+    lib = _lib.load()
+    a = torch.randint(0, 2**62, (1000, 4), dtype=torch.int64, device="cuda")
+    a[:, 3] &= 0x0FFFFFFFFFFFFFFF
+    b = a.clone()
+    b[17, 0] += 1
+    b[999, 3] ^= 1
+    a[5] = 0
+    b[5] = 0
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    st.synchronize()
+    _lib.check(lib.sb_count_mismatch_device(0, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), 1000, ctypes.c_void_p(cnt.data_ptr()), ctypes.c_void_p(st.cuda_stream)))
+    st.synchronize()
+    assert int(cnt.item()) == 2
+    _lib.check(lib.sb_count_mismatch_device(1, ctypes.c_void_p(a.data_ptr()), None, 1000, ctypes.c_void_p(cnt.data_ptr()), ctypes.c_void_p(st.cuda_stream)))
+    st.synchronize()
+    assert int(cnt.item()) == 999   # row 5 is the only zero row
+    lib.sb_stream_release(ctypes.c_void_p(st.cuda_stream))
+
+
+def test_multi_gpu_step_torchrun(oracle):
+    """The N > 1 path of the bench (row sharding + partial-sum exchange + combine) at the bench shapes, on real GPUs."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs on the box (run with gpurun --gpus 2)")
+    world = 2
+    port = 29600 + (os.getpid() % 1000)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tools", "check_multi_gpu.py"), "--k", "17"],
+                       capture_output=True, text=True, timeout=1500, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert "fold_step over 2 ranks == oracle" in r.stdout
+
+
+def test_two_threads_two_streams_reentrant(oracle):
+    """SURVEY 8b "Threading": CommitmentKey is Sync and cargo test is multi-threaded.  Two host threads drive two CUDA
+    streams through the _device entry points (commit, cross terms, folds) and two more call the blocking host entry
+    points at the same time; every result must equal the oracle's (the per-stream scratch and the one-critical-section
+    host wrappers are what is under test)."""
+    import ctypes
+    import threading
+
+    import torch
+
+    import oracle as O
+    import sirius_b200
+    from oracle import pyref as R
+    from sirius_b200 import _lib
+
+    lib = _lib.load()
+    n = 1 << 14
+    errors = []
+    keys = {}
+    for curve in (0, 1):
+        bases = O.running_bases(curve, n)
+        keys[curve] = (sirius_b200.CommitmentKey(curve, bases, window_bits=11), bases)
+
+    def device_worker(tid):
+        try:
+            curve = tid & 1
+            ck, bases = keys[curve]
+            st = torch.cuda.Stream()
+            for it in range(6):
+                m = n - 37 * it - tid
+                s = O.random_field(curve, 1000 * tid + it, m)
+                with torch.cuda.stream(st):
+                    d_s = torch.from_numpy(s.view(np.int64)).cuda()
+                    d_o = torch.zeros(8, dtype=torch.int64, device="cuda")
+                st.synchronize()
+                ck.commit_device(d_s.data_ptr(), m, d_o.data_ptr(), 0, st.cuda_stream)
+                # a fold on the same stream in between (shares nothing with the other thread's stream)
+                r = O.random_field(curve, 77 + it, 1).reshape(4)
+                with torch.cuda.stream(st):
+                    d_w = torch.empty_like(d_s)
+                _lib.check(lib.sb_axpy_fold_device(curve, ctypes.c_void_p(d_s.data_ptr()), ctypes.c_void_p(d_s.data_ptr()), r.ctypes.data_as(_lib.u64p),
+                                                   ctypes.c_void_p(d_w.data_ptr()), m, ctypes.c_void_p(st.cuda_stream)))
+                st.synchronize()
+                got = d_o.cpu().numpy().view(np.uint64)
+                if not np.array_equal(got, O.msm(curve, s, bases)):
+                    errors.append(f"device thread {tid} iteration {it}: commitment mismatch")
+                exp_w = O.field_binop("add", curve, s, O.field_binop("mul", curve, np.tile(r, (m, 1)), s))
+                if not np.array_equal(d_w.cpu().numpy().view(np.uint64), exp_w):
+                    errors.append(f"device thread {tid} iteration {it}: fold mismatch")
+            lib.sb_stream_release(ctypes.c_void_p(st.cuda_stream))
+        except Exception as exc:  # noqa: BLE001
+            errors.append(f"device thread {tid}: {exc!r}")
+
+    def host_worker(tid):
+        try:
+            curve = tid & 1
+            ck, bases = keys[curve]
+            for it in range(6):
+                m = n // 2 + 11 * it + tid
+                s = O.random_field(curve, 5000 * tid + it, m)
+                if not np.array_equal(ck.commit(s), O.msm(curve, s, bases)):
+                    errors.append(f"host thread {tid} iteration {it}: commitment mismatch")
+                r = O.random_field(curve, 9 + it, 1).reshape(4)
+                out = np.zeros_like(s)
+                _lib.check(lib.sb_axpy_fold(curve, s.ctypes.data_as(_lib.u64p), s.ctypes.data_as(_lib.u64p), r.ctypes.data_as(_lib.u64p), out.ctypes.data_as(_lib.u64p), m))
+                exp = O.field_binop("add", curve, s, O.field_binop("mul", curve, np.tile(r, (m, 1)), s))
+                if not np.array_equal(out, exp):
+                    errors.append(f"host thread {tid} iteration {it}: fold mismatch")
+        except Exception as exc:  # noqa: BLE001
+            errors.append(f"host thread {tid}: {exc!r}")
+
+    threads = [threading.Thread(target=device_worker, args=(t,)) for t in range(2)] + [threading.Thread(target=host_worker, args=(t,)) for t in range(2, 4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    for ck, _ in keys.values():
+        ck.close()
+    assert not errors, errors

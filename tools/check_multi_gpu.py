@@ -1,46 +1,45 @@
-"""torchrun check of the N>1 commit path: row-sharded MSM on each rank + NCCL all-gather of XYZZ partials +
-combine kernel == the CPU oracle's full commitment (bit-exact).  Run: torchrun --nproc-per-node N tools/check_multi_gpu.py"""
-import ctypes, os, sys
+"""torchrun check of the N>1 path bench.py times: the row-sharded SangriaStepWorkload (per-rank MSM + exchange of XYZZ
+partials + combine kernel, row-local cross terms and folds) against the CPU oracle's full step, bit for bit.
+Run: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/check_multi_gpu.py [--k 17]
+(launched by tests/test_gpu_workload.py::test_multi_gpu_step_torchrun when the box has >= 2 GPUs)."""
+import argparse
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 import torch.distributed as dist
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--k", type=int, default=12)
+ap.add_argument("--steps", type=int, default=2)
+args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 import oracle
 import sirius_b200
-from oracle import pyref as R
-from sirius_b200 import _lib, sharding
+from oracle import step_ref
+from sirius_b200 import _lib
+from sirius_b200 import workload as WL
 
 lib = sirius_b200.load()
 _lib.check(lib.sb_init(local))
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+oracle.build()
+wl = WL.SangriaStepWorkload(args.k, rank, world, torch.cuda.Stream())
 ok = True
-for curve in (R.CURVE_BN256, R.CURVE_GRUMPKIN):
-    ncols, n = 3, 1 << 12
-    sf = 0 if curve == R.CURVE_BN256 else 1
-    W = oracle.random_field(sf, 5 + curve, ncols * n)
-    bases = oracle.running_bases(curve, ncols * n)
-    W_loc = sharding.shard_column_major(W, ncols, n, rank, world)
-    ck_loc = sharding.shard_column_major(bases, ncols, n, rank, world)
-    ck = sirius_b200.CommitmentKey(curve, ck_loc)
-    d_s = torch.from_numpy(W_loc.view(np.int64)).cuda()
-    part = torch.zeros(16, dtype=torch.int64, device="cuda")
-    st = torch.cuda.Stream()
-    ck.commit_device(d_s.data_ptr(), W_loc.shape[0], 0, part.data_ptr(), st.cuda_stream)
-    gathered = torch.zeros((world, 16), dtype=torch.int64, device="cuda")
-    with torch.cuda.stream(st):
-        dist.all_gather_into_tensor(gathered, part)
-    out = torch.zeros(8, dtype=torch.int64, device="cuda")
-    _lib.check(lib.sb_msm_combine_device(curve, ctypes.c_void_p(gathered.data_ptr()), world, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st.cuda_stream)))
-    st.synchronize()
-    got = out.cpu().numpy().view(np.uint64)
-    exp = oracle.msm(curve, W, bases)
-    good = bool(np.array_equal(got, exp))
-    ok &= good
+for i in range(args.steps):
+    snap = wl.snapshot_inputs()
+    wl.step(upload=(i % 2 == 0))
+    got = wl.snapshot_results()
     if rank == 0:
-        print(f"curve {curve}: sharded commit over {world} ranks {'==' if good else '!='} oracle", flush=True)
-dist.barrier()
+        exp = step_ref.fold_step(snap, step_ref.bases_for(snap))
+        rep = step_ref.compare(got, exp)
+        ok &= rep["ok"]
+        print(f"step {i}: fold_step over {world} ranks {'==' if rep['ok'] else '!='} oracle {rep['bad']}", flush=True)
+    dist.barrier()
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.broadcast(flag, 0)
 dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+sys.exit(0 if int(flag.item()) else 1)
