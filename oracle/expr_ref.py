@@ -526,3 +526,12 @@ def c_graph_evaluate(field: int, ev: GraphEvaluator, selectors: np.ndarray, fixe
     if rc != 0:
         raise IndexError(f"so_graph_evaluate error {rc} (EvalError)")
     return out
+
+
+def tiny_gate_expression():
+    """src/ivc/cyclefold/support_circuit/tiny_gate.rs:55-81 through Expression::from_halo2_expr: 1 selector, fixed
+    [mul, sum0, sum1, rc], advice [state0, state1, output]."""
+    s = Poly(0)
+    mul, sum0, sum1, rc = (Poly(1 + j) for j in range(4))
+    state0, state1, output = (Poly(5 + j) for j in range(3))
+    return Mul(s, Sub(Sum(Sum(Sum(Mul(Mul(state0, state1), mul), Mul(state0, sum0)), Mul(state1, sum1)), rc), output))

@@ -581,11 +581,13 @@ int so_coset_scale(int field, u64 *a_mont, size_t n, const u64 z_mont[4], const 
 
 int so_field_mul(int field, const u64 *a, const u64 *b, u64 *o, size_t n) {
     const field_t *F = &FIELDS[field];
+#pragma omp parallel for schedule(static) if (n > 65536)
     for (size_t i = 0; i < n; i++) fe_mul((fe *)o + i, (const fe *)a + i, (const fe *)b + i, F);
     return 0;
 }
 int so_field_add(int field, const u64 *a, const u64 *b, u64 *o, size_t n) {
     const field_t *F = &FIELDS[field];
+#pragma omp parallel for schedule(static) if (n > 65536)
     for (size_t i = 0; i < n; i++) fe_add((fe *)o + i, (const fe *)a + i, (const fe *)b + i, F);
     return 0;
 }
@@ -594,6 +596,60 @@ int so_field_sub(int field, const u64 *a, const u64 *b, u64 *o, size_t n) {
     for (size_t i = 0; i < n; i++) fe_sub((fe *)o + i, (const fe *)a + i, (const fe *)b + i, F);
     return 0;
 }
+/* Perfect binary tree over n = 2^log_n leaves with node(h) = left + right * mult[h]: the tree_reduce of compute_F
+ * (src/nifs/protogalaxy/poly/mod.rs:100-185), compute_G (:330-413) and evaluate_e_from_trace (mod.rs:586-639) for one
+ * evaluation point.  Level by level; exact arithmetic, so the grouping of the (independent) nodes of a level is free. */
+int so_beta_tree(int field, const u64 *leaves, uint32_t log_n, const u64 *mult, u64 out[4]) {
+    const field_t *F = &FIELDS[field];
+    size_t n = (size_t)1 << log_n;
+    if (log_n == 0) {
+        memcpy(out, leaves, sizeof(fe));
+        return 0;
+    }
+    /* two buffers: a level is written to the one it does not read (the nodes of a level are computed in parallel) */
+    fe *buf[2] = {(fe *)malloc((n / 2) * sizeof(fe)), (fe *)malloc((n / 4 + 1) * sizeof(fe))};
+    if (!buf[0] || !buf[1]) {
+        free(buf[0]);
+        free(buf[1]);
+        return -1;
+    }
+    const fe *src = (const fe *)leaves;
+    fe *dst = buf[0];
+    for (uint32_t h = 0; h < log_n; h++) {
+        const size_t m = n >> (h + 1);
+        const fe *c = (const fe *)mult + h;
+        dst = buf[h & 1];
+#pragma omp parallel for schedule(static) if (m > 4096)
+        for (size_t j = 0; j < m; j++) {
+            fe t;
+            fe_mul(&t, &src[2 * j + 1], c, F);
+            fe_add(&dst[j], &src[2 * j], &t, F);
+        }
+        src = dst;
+    }
+    memcpy(out, dst, sizeof(fe));
+    free(buf[0]);
+    free(buf[1]);
+    return 0;
+}
+
+/* out[i] = sum_j coef[j] * in_j[i]: FoldedWitness::new (poly/folded_witness.rs:66-143) and ProtoGalaxy::fold_witness
+ * (src/nifs/protogalaxy/mod.rs:176-210), cell by cell. */
+int so_lincomb(int field, const u64 *const *ins, const u64 *coef, size_t J, size_t n, u64 *out) {
+    const field_t *F = &FIELDS[field];
+#pragma omp parallel for schedule(static) if (n > 4096)
+    for (size_t i = 0; i < n; i++) {
+        fe acc, t;
+        fe_mul(&acc, (const fe *)ins[0] + i, (const fe *)coef, F);
+        for (size_t j = 1; j < J; j++) {
+            fe_mul(&t, (const fe *)ins[j] + i, (const fe *)coef + j, F);
+            fe_add(&acc, &acc, &t, F);
+        }
+        ((fe *)out)[i] = acc;
+    }
+    return 0;
+}
+
 int so_field_inv(int field, const u64 *a, u64 *o, size_t n) {
     const field_t *F = &FIELDS[field];
     for (size_t i = 0; i < n; i++) fe_inv((fe *)o + i, (const fe *)a + i, F);

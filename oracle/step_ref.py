@@ -23,16 +23,20 @@ _EV_CACHE = {}
 
 def evaluators(side):
     """GraphEvaluator per cross term T_1..T_d of one side's compressed MainGate expression (None = zero term)."""
-    key = (side["name"], tuple(side["T_list"]))
+    key = (side["name"], side.get("kind"), tuple(side["T_list"]))
     if key not in _EV_CACHE:
-        nfix = sum(2 * T + 5 for T in side["T_list"])
-        nadv = sum(T + 2 for T in side["T_list"])
-        gates, fb, ab = [], 0, 0
-        for T in side["T_list"]:
-            gates.append(E.main_gate_expression(T, fb, ab, 0, nfix))
-            fb += 2 * T + 5
-            ab += T + 2
-        cg = E.CompressedGates(gates, E.Ctx(num_fixed=nfix, num_advice=nadv))
+        if side.get("kind") == "tiny":   # the Cyclefold support circuit's gate (tiny_gate.rs:38-84)
+            nsel, nfix, nadv, gates = 1, 4, 3, [E.tiny_gate_expression()]
+        else:
+            nsel = 0
+            nfix = sum(2 * T + 5 for T in side["T_list"])
+            nadv = sum(T + 2 for T in side["T_list"])
+            gates, fb, ab = [], 0, 0
+            for T in side["T_list"]:
+                gates.append(E.main_gate_expression(T, fb, ab, 0, nfix))
+                fb += 2 * T + 5
+                ab += T + 2
+        cg = E.CompressedGates(gates, E.Ctx(num_selectors=nsel, num_fixed=nfix, num_advice=nadv))
         f = side["field"]
         evs = [None if ex is None else E.GraphEvaluator(ex, R.MODULUS[f]) for ex in cg.grouped()[1:]]
         _EV_CACHE[key] = (evs, cg.ctx.num_challenges - 1)
@@ -50,7 +54,8 @@ def prove(inp: Dict, bases: np.ndarray, threads: int) -> Dict:
     ch = np.ascontiguousarray(np.concatenate([inp["c1"].reshape(-1, 4), inp["u1"].reshape(1, 4), inp["c2"].reshape(-1, 4), one]), dtype=np.uint64)
     W1, W2, E1 = (np.ascontiguousarray(inp[x], dtype=np.uint64).reshape(-1, 4) for x in ("W1", "W2", "E1"))
     adv = [W1[i * n:(i + 1) * n] for i in range(nadv)] + [W2[i * n:(i + 1) * n] for i in range(nadv)]
-    T = [np.zeros((n, 4), dtype=np.uint64) if ev is None else E.c_graph_evaluate(f, ev, [], inp["fixed"], adv, ch, k, threads=threads) for ev in evs]
+    sel = inp.get("selectors", [])
+    T = [np.zeros((n, 4), dtype=np.uint64) if ev is None else E.c_graph_evaluate(f, ev, sel, inp["fixed"], adv, ch, k, threads=threads) for ev in evs]
     commits = np.stack([oracle.msm(curve, t, bases, threads=threads) for t in T])
     r = np.ascontiguousarray(inp["r"], dtype=np.uint64).reshape(4)
     outw = np.zeros_like(W1)
@@ -108,4 +113,77 @@ def compare(results_gpu: Dict[str, Dict], results_cpu: Dict[str, Dict]) -> Dict:
             checked.append(tag)
             if a.shape != b.shape or not np.array_equal(a, b):
                 bad.append(tag)
+    return {"ok": not bad, "checked": checked, "bad": bad}
+
+
+# ------------------------------------------------------------------------------------------------ Cyclefold next()
+class _PgCtx:
+    """The PolyContext values compute_K_from_G reads (poly/mod.rs:205-269, incl. the point-count-as-log of SURVEY F5)."""
+
+    def __init__(self, traces_len: int, max_degree: int):
+        self.instances_to_fold = traces_len + 1
+        p = 1
+        while p < traces_len * max_degree + 1:
+            p <<= 1
+        self.fft_points_count_G = p
+
+    def lagrange_domain(self):
+        return self.instances_to_fold.bit_length() - 1
+
+    def fft_log_domain_size_K(self):
+        v, p = max(self.fft_points_count_G + 1 - self.instances_to_fold, 0), 1
+        while p < v:
+            p <<= 1
+        return p
+
+
+def cyclefold_step(inp: Dict, threads: int = 0) -> Dict:
+    """The prover hot path of cyclefold::IVC::next (src/ivc/cyclefold/incrementally_verifiable_computation/mod.rs:210-335) on the
+    inputs of sirius_b200.workload.CyclefoldStepWorkload.snapshot_inputs(): ProtoGalaxy::prove (F, G, K, fold_witness,
+    src/nifs/protogalaxy/mod.rs:400-481), fold_support_circuit (:404-473), commit of the next primary trace."""
+    from oracle import pg_fast as PF
+    from oracle import pg_ref as PG
+    from sirius_b200 import workload as WL   # side descriptions only (shapes), no device code
+
+    k, nadv = inp["k"], inp["nadv"]
+    mode = "correct" if inp["row_mode"] == 1 else "compat"
+    gates, nfix, _ = WL.compressed_gates(WL.PRIMARY, E)
+    S = PF.Structure(k, [], inp["fixed"], nadv, gates)
+    ctx = E.Ctx(num_fixed=nfix, num_advice=nadv)
+    max_degree = max(PG.gate_degree(g, ctx) for g in gates)
+    t = S.betas_count()
+    betas, delta, alpha, gamma = inp["betas"][:t], inp["delta"], inp["alpha"], inp["gamma"]
+    poly_F = PF.compute_F(S, betas, delta, inp["W_acc"], [], mode, threads)
+    bs = PG.beta_stroke(betas, alpha, delta)
+    poly_G = PF.compute_G(S, max_degree, bs, inp["W_acc"], [], [inp["W_in"]], [[]], mode, threads)
+    pctx = _PgCtx(1, max_degree)
+    poly_K = PG.compute_K_from_G(pctx, poly_G, PG.poly_eval(poly_F, alpha))
+    Lg = R.eval_lagrange_polys(pctx.lagrange_domain(), gamma)
+    W = PF.fold_witness(inp["W_acc"], [inp["W_in"]], Lg)
+    sup = inp["support"]
+    sup_bases = oracle.running_bases(sup["side"]["curve"], sup["nadv"] << sup["k"])
+    sres = prove(sup, sup_bases, threads)
+    sres["commit_W"] = oracle.msm(sup["side"]["curve"], sup["W2"], sup_bases, threads=threads)
+    bases = oracle.running_bases(WL.PRIMARY["curve"], nadv << k)
+    commit_W = oracle.msm(WL.PRIMARY["curve"], inp["W_in"], bases, threads=threads)
+    return dict(poly_F=poly_F, poly_G=poly_G, poly_K=poly_K, W=W, commit_W=commit_W, support=sres)
+
+
+def compare_cyclefold(g: Dict, c: Dict) -> Dict:
+    checked, bad = [], []
+
+    def chk(tag, a, b):
+        checked.append(tag)
+        if isinstance(a, list):
+            ok = list(a) == list(b)
+        else:
+            a, b = np.asarray(a, dtype=np.uint64).reshape(-1), np.asarray(b, dtype=np.uint64).reshape(-1)
+            ok = a.shape == b.shape and np.array_equal(a, b)
+        if not ok:
+            bad.append(tag)
+
+    for key in ("poly_F", "poly_G", "poly_K", "W", "commit_W"):
+        chk(key, g[key], c[key])
+    for key in ("commits_T", "commit_W", "W", "E"):
+        chk(f"support.{key}", g["support"][key], c["support"][key])
     return {"ok": not bad, "checked": checked, "bad": bad}

@@ -406,6 +406,7 @@ static int pg_leaves_enqueue(sb_prog* const* gates, size_t num_gates, sb_columns
         set_error("sb_pg_leaves: 2^%u leaves cannot hold %zu gates x %u rows", log_leaves, num_gates, n);
         return SB_ERR_ARG;
     }
+    ProfScope ps(st, PROF_PG, leaves * num_blends);
     SB_CUDA_TRY(cudaMemsetAsync(d_leaves, 0, leaves * num_blends * 32, st));
     const size_t ptr_bytes = align_up(sizeof(void*) * nfv * num_traces, 32);
     const size_t coef_bytes = align_up(32 * num_blends * num_traces, 32);

@@ -106,6 +106,7 @@ static int beta_tree_enqueue(const void* d_leaves, uint32_t log_n, size_t num_po
         return SB_OK;
     }
     SB_CUDA_TRY(cudaMemcpyAsync(d_c, multipliers, 32 * num_points * log_n, cudaMemcpyHostToDevice, st));
+    ProfScope ps(st, PROF_PG, n * num_points);
     const F* in = (const F*)d_leaves;
     size_t in_stride = leaf_stride;
     uint32_t log_cur = log_n, h0 = 0;
@@ -139,6 +140,7 @@ static int lincomb_enqueue(const void* const* d_inputs, const uint64_t* coef, si
     char* d = (char*)g_lincomb_args.ptr;
     SB_CUDA_TRY(cudaMemcpyAsync(d, d_inputs, sizeof(void*) * J, cudaMemcpyHostToDevice, st));
     SB_CUDA_TRY(cudaMemcpyAsync(d + ptr_bytes, coef, 32 * J, cudaMemcpyHostToDevice, st));
+    ProfScope ps(st, PROF_PG, n);
     if (n) {
         k_lincomb<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const F* const*)d, (const F*)(d + ptr_bytes), (uint32_t)J, (F*)d_out, n);
         SB_KERNEL_CHECK();

@@ -149,3 +149,133 @@ def random_field_device(n: int, seed: int):
     t = torch.randint(-(2**63), 2**63 - 1, (n, 4), dtype=torch.int64, device="cuda", generator=g)
     t[:, 3] &= 0x0FFFFFFFFFFFFFFF
     return t   # produced on torch's CURRENT stream: call inside `with torch.cuda.stream(s)` or synchronise before cross-stream use
+
+
+def ints_to_mont(vals, modulus: int) -> np.ndarray:
+    """Python ints -> uint64 [len,4] Montgomery limbs (host glue; one bytes join instead of per-limb Python loops)."""
+    if not len(vals):
+        return np.zeros((0, 4), dtype=np.uint64)
+    buf = b"".join((((int(v) % modulus) << 256) % modulus).to_bytes(32, "little") for v in vals)
+    return np.frombuffer(buf, dtype=np.uint64).reshape(-1, 4).copy()
+
+
+def mont_to_ints(arr: np.ndarray, modulus: int):
+    rinv = pow(1 << 256, -1, modulus)
+    raw = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4).tobytes()
+    return [int.from_bytes(raw[i:i + 32], "little") * rinv % modulus for i in range(0, len(raw), 32)]
+
+
+class DeviceProtogalaxySide:
+    """Device-resident Protogalaxy prover state (src/nifs/protogalaxy): accumulator witness + one incoming trace (L = 1),
+    single witness round, bn256 Fr.  compute_F / compute_G leaf evaluation and beta trees, fold_witness and the trace
+    commitment run on the device; the O(#points) scalar glue (Lagrange values, ifft of 32 / 8 points, K on 256 points)
+    is host integer arithmetic, as it stays host Rust in the integration."""
+
+    def __init__(self, S: PlonkStructure, ck: CommitmentKey, stream, row_mode: int = 1):
+        import torch
+
+        from . import fft, protogalaxy as PGX
+
+        self.torch, self.S, self.ck, self.stream, self.row_mode = torch, S, ck, stream, row_mode
+        self.PGX, self.fft = PGX, fft
+        self.M = S.modulus
+        self.n, self.A = 1 << S.k, S.num_advice_columns
+        self.ctx = PGX.PolyContext(S, 1)
+        self.t = self.ctx.betas_count()
+        self.nF, self.nG = self.ctx.fft_points_count_F(), self.ctx.fft_points_count_G
+        self.leaves_n = 1 << self.t
+        dev = torch.device("cuda", torch.cuda.current_device())
+        i64 = torch.int64
+        with torch.cuda.stream(stream):
+            self.W_acc = torch.zeros((self.A * self.n, 4), dtype=i64, device=dev)
+            self.W_in = torch.zeros_like(self.W_acc)
+            self.W_new = torch.zeros_like(self.W_acc)
+            self.leaves = torch.zeros((self.nG, self.leaves_n, 4), dtype=i64, device=dev)
+            self.d_out = torch.zeros((max(self.nF, self.nG), 4), dtype=i64, device=dev)
+            self.commit_W = torch.zeros(8, dtype=i64, device=dev)
+        self.h_out = torch.zeros((max(self.nF, self.nG), 4), dtype=i64).pin_memory()
+        self.h_commit_W = torch.zeros(8, dtype=i64).pin_memory()
+        stream.synchronize()
+        progs = S.gate_programs()
+        self._gates = (ctypes.c_void_p * len(progs))(*[p._h for p in progs])
+        self._ng = len(progs)
+        self._XsF = PGX.iter_cyclic_subgroup(self.nF.bit_length() - 1)
+        self._XsG = PGX.iter_cyclic_subgroup(self.ctx.fft_log_domain_size_G())[: self.nG]
+        self._LsG = [PGX.eval_lagrange_polys(X, self.ctx.lagrange_domain()) for X in self._XsG]
+        self._coefG = ints_to_mont([c for L in self._LsG for c in L[:2]], self.M)
+        self._one = ints_to_mont([1], self.M)
+
+    def _cols(self, t):
+        base = t.data_ptr()
+        return [base + j * self.n * 32 for j in range(self.A)]
+
+    def _tree(self, num_points, leaf_stride, mult):
+        lib = _lib.load()
+        st = self.stream.cuda_stream
+        m = ints_to_mont(mult, self.M)
+        _lib.check(lib.sb_beta_tree_device(self.S.field, ctypes.c_void_p(self.leaves.data_ptr()), self.t, num_points, leaf_stride,
+                                           m.ctypes.data_as(_lib.u64p), ctypes.c_void_p(self.d_out.data_ptr()), ctypes.c_void_p(st)))
+        with self.torch.cuda.stream(self.stream):
+            self.h_out[:num_points].copy_(self.d_out[:num_points], non_blocking=True)
+        self.stream.synchronize()   # the polynomial is absorbed by the host-side random oracle (mod.rs:416-447)
+        return mont_to_ints(self.h_out[:num_points].numpy().view(np.uint64), self.M)
+
+    def compute_F_evals(self, betas, delta):
+        """compute_F (poly/mod.rs:68-203) up to the ifft: F on the order-32 subgroup, from the ACCUMULATOR's trace."""
+        lib = _lib.load()
+        st = self.stream.cuda_stream
+        tab = _vp_array(self._cols(self.W_acc))
+        _lib.check(lib.sb_pg_leaves_device(self._gates, self._ng, self.S._cols, tab, 1, self.A, self._one.ctypes.data_as(_lib.u64p), None, 0, 1,
+                                           self.row_mode, self.t, ctypes.c_void_p(self.leaves.data_ptr()), ctypes.c_void_p(st)))
+        M = self.M
+        deltas = [delta % M]
+        for _ in range(self.t - 1):
+            deltas.append(deltas[-1] * deltas[-1] % M)
+        mult = [(b + X * d) % M for X in self._XsF for b, d in zip(betas[: self.t], deltas)]
+        return self._tree(self.nF, 0, mult)
+
+    def compute_G_evals(self, betas_stroke):
+        """compute_G (poly/mod.rs:308-425) up to the ifft: the 8 Lagrange blends of (accumulator, incoming) are evaluated on the
+        fly (no FoldedWitness copies, folded_witness.rs:66-143), one beta* tree per blend."""
+        lib = _lib.load()
+        st = self.stream.cuda_stream
+        tab = _vp_array(self._cols(self.W_acc) + self._cols(self.W_in))
+        _lib.check(lib.sb_pg_leaves_device(self._gates, self._ng, self.S._cols, tab, 2, self.A, self._coefG.ctypes.data_as(_lib.u64p), None, 0, self.nG,
+                                           self.row_mode, self.t, ctypes.c_void_p(self.leaves.data_ptr()), ctypes.c_void_p(st)))
+        bs = [b % self.M for b in betas_stroke[: self.t]]
+        return self._tree(self.nG, self.leaves_n, bs * self.nG)
+
+    def fold_witness(self, gamma: int) -> None:
+        """ProtoGalaxy::fold_witness (mod.rs:176-210): W_acc <- L0(gamma) W_acc + L1(gamma) W_in (buffers swapped, not copied)."""
+        lib = _lib.load()
+        Lg = self.PGX.eval_lagrange_polys(gamma, self.ctx.lagrange_domain())[:2]
+        coef = ints_to_mont(Lg, self.M)
+        ins = _vp_array([self.W_acc.data_ptr(), self.W_in.data_ptr()])
+        _lib.check(lib.sb_lincomb_device(self.S.field, ins, coef.ctypes.data_as(_lib.u64p), 2, self.A * self.n, ctypes.c_void_p(self.W_new.data_ptr()),
+                                         ctypes.c_void_p(self.stream.cuda_stream)))
+        self.W_acc, self.W_new = self.W_new, self.W_acc
+
+    def prove(self, betas, delta: int, alpha: int, gamma: int):
+        """ProtoGalaxy::prove (mod.rs:400-481) with the random oracle's challenges supplied by the caller.
+        Returns (poly_F, poly_G, poly_K) as coefficient lists."""
+        PGX = self.PGX
+        poly_F = PGX._ifft_ints(self.compute_F_evals(betas, delta))
+        bs = PGX.beta_stroke(betas[: self.t], alpha, delta)
+        poly_G = PGX._ifft_ints(self.compute_G_evals(bs))
+        poly_K = PGX.compute_K_from_G(self.ctx, poly_G, PGX.poly_eval(poly_F, alpha))
+        self.fold_witness(gamma)
+        return poly_F, poly_G, poly_K
+
+    def upload_incoming(self, host_W_pinned) -> int:
+        with self.torch.cuda.stream(self.stream):
+            self.W_in.copy_(host_W_pinned, non_blocking=True)
+        return host_W_pinned.numel() * 8
+
+    def commit_incoming(self) -> np.ndarray:
+        """generate_plonk_trace's commit of the new trace (src/plonk/mod.rs:441-445): the 12 * 2^k-point MSM."""
+        st = self.stream.cuda_stream
+        self.ck.commit_device(self.W_in.data_ptr(), self.A * self.n, self.commit_W.data_ptr(), 0, st)
+        with self.torch.cuda.stream(self.stream):
+            self.h_commit_W.copy_(self.commit_W, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_commit_W.numpy().view(np.uint64).copy()

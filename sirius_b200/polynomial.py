@@ -295,3 +295,13 @@ def main_gate_expression(T: int, fixed_base: int, advice_base: int, num_selector
     for s, q1, q5 in zip(state, q_1, q_5):
         acc = acc + (q1 * s + q5 * pow_5(s))
     return acc
+
+
+def tiny_gate_expression() -> Expression:
+    """The Cyclefold support circuit's gate `s * (s0*s1*mul + s0*sum0 + s1*sum1 + rc - output)` as
+    `Expression::from_halo2_expr` sees it (src/ivc/cyclefold/support_circuit/tiny_gate.rs:38-84): 1 selector, fixed
+    columns [mul, sum0, sum1, rc], advice columns [state0, state1, output]; folding degree 2."""
+    s = Expression.Polynomial(0, 0)
+    mul, sum0, sum1, rc = (Expression.Polynomial(1 + j, 0) for j in range(4))
+    state0, state1, output = (Expression.Polynomial(5 + j, 0) for j in range(3))
+    return s * ((state0 * state1 * mul) + (state0 * sum0) + (state1 * sum1) + rc - output)

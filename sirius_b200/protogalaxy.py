@@ -190,14 +190,41 @@ def compute_G(ctx: PolyContext, betas_stroke: Sequence[int], acc_W: np.ndarray, 
     return _ifft_ints(evals)
 
 
+def _batch_inverse(vals: List[int]) -> List[int]:
+    """Montgomery's trick over Python ints (all values non-zero): one modular inversion for the whole list."""
+    pref, acc = [], 1
+    for v in vals:
+        pref.append(acc)
+        acc = acc * v % M
+    inv = pow(acc, -1, M)
+    out = [0] * len(vals)
+    for i in range(len(vals) - 1, -1, -1):
+        out[i] = inv * pref[i] % M
+        inv = inv * vals[i] % M
+    return out
+
+
 def compute_K_from_G(ctx: PolyContext, poly_G: Sequence[int], poly_F_in_alpha: int, zeta: int = fft.FR_ZETA) -> List[int]:
-    vals = []
-    for w in iter_cyclic_subgroup(ctx.fft_log_domain_size_K()):
-        X = zeta * w % M
-        g = poly_eval(poly_G, X)
-        L0 = eval_lagrange_polys(X, ctx.lagrange_domain())[0]
-        Z = eval_vanish_polynomial(ctx.instances_to_fold, X)
-        vals.append((g - poly_F_in_alpha * L0) * pow(Z, -1, M) % M)
+    """poly/mod.rs:475-509: K on the coset zeta * H, K(X) = (G(X) - F(alpha) * L0(X)) / Z(X), then coset_ifft.  Same values as the
+    point-by-point form (L0 from iter_eval_lagrange_poly_for_cyclic_group incl. its 0/0 -> 1 case, lagrange.rs:50-74; Z from
+    eval_vanish_polynomial, :83-85); the 2 * #points inversions are shared (host glue, O(#points))."""
+    n = ctx.instances_to_fold
+    log_n = ctx.lagrange_domain()
+    ninv = pow(1 << log_n, -1, M)
+    Xs = [zeta * w % M for w in iter_cyclic_subgroup(ctx.fft_log_domain_size_K())]
+    xn1 = [(pow(X, 1 << log_n, M) - 1) % M for X in Xs]      # X^(2^log_n) - 1: numerator of every Lagrange value
+    Z = [(pow(X, n, M) - 1) % M for X in Xs]
+    den = [(X - 1) % M for X in Xs]                            # first subgroup element is 1
+    if any(d == 0 for d in den) or any(z == 0 for z in Z):
+        vals = []                                              # degenerate point: fall back to the literal form
+        for X in Xs:
+            g = poly_eval(poly_G, X)
+            L0 = eval_lagrange_polys(X, log_n)[0]
+            vals.append((g - poly_F_in_alpha * L0) * pow(eval_vanish_polynomial(n, X), -1, M) % M)
+    else:
+        inv = _batch_inverse(den + Z)
+        m = len(Xs)
+        vals = [(poly_eval(poly_G, X) - poly_F_in_alpha * (ninv * x1 % M * inv[i] % M)) * inv[m + i] % M for i, (X, x1) in enumerate(zip(Xs, xn1))]
     a = _to_mont(vals, M)
     fft.coset_ifft(a, zeta)
     return _from_mont(a)

@@ -31,19 +31,29 @@ from .commitment import CommitmentKey
 
 PRIMARY = dict(name="primary", curve=0, field=0, T_list=[5, 3])   # bn256 / Fr : MainGate<5> + Poseidon MainGate<3>
 SECONDARY = dict(name="secondary", curve=1, field=1, T_list=[5])  # grumpkin / Fq : MainGate<5> (trivial step circuit)
+# Cyclefold support circuit (src/ivc/cyclefold/support_circuit/tiny_gate.rs:38-84, k = 15): 1 selector, 4 fixed, 3 advice, d = 2
+SUPPORT = dict(name="support", curve=1, field=1, kind="tiny", T_list=[])
 SEED = 0x5349524955530000
 
 
 def shapes(side):
+    if side.get("kind") == "tiny":
+        return 4, 3
     nfix = sum(2 * T + 5 for T in side["T_list"])
     nadv = sum(T + 2 for T in side["T_list"])
     return nfix, nadv
 
 
+def num_selectors(side) -> int:
+    return 1 if side.get("kind") == "tiny" else 0
+
+
 def compressed_gates(side, mod=P):
-    """The compressed MainGate expressions of one side, built with `mod` = sirius_b200.polynomial (product) or the
-    oracle's expr_ref (same constructor names) -- the callers pass their own module so this file never imports oracle/."""
+    """The gate expressions of one side, built with `mod` = sirius_b200.polynomial (product) or the oracle's expr_ref
+    (same constructor names) -- the callers pass their own module so this file never imports oracle/."""
     nfix, nadv = shapes(side)
+    if side.get("kind") == "tiny":
+        return [mod.tiny_gate_expression()], nfix, nadv
     gates, fb, ab = [], 0, 0
     for T in side["T_list"]:
         gates.append(mod.main_gate_expression(T, fb, ab, 0, nfix))
@@ -60,6 +70,73 @@ def default_windows(k: int) -> List[int]:
     if k >= 19:
         return [17, 20]
     return [16, 13, 15, 17]
+
+
+def build_structure_key(side, k, rank, world, stream, windows, seed, key_cols=None):
+    """PlonkStructure + CommitmentKey of one side restricted to this rank's rows: synthetic uniform fixed columns and
+    selector bits generated in HBM; key = [i+1]G for the first key_cols (default: num_advice) * 2^k indices."""
+    import torch
+
+    lib = _lib.load()
+    gates, nfix, nadv = compressed_gates(side)
+    nsel = num_selectors(side)
+    cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_selectors=nsel, num_fixed=nfix, num_advice=nadv))
+    n = 1 << k
+    row0, n_loc = sharding.row_slice(rank, world, n)
+    k_loc = n_loc.bit_length() - 1
+    modulus = curves.SCALAR_FIELD[side["curve"]]
+    with torch.cuda.stream(stream):
+        d_fixed = [device.random_field_device(n_loc, seed + 1000 * side["curve"] + 10 * rank + j) for j in range(nfix)]
+        gsel = torch.Generator(device="cuda")
+        gsel.manual_seed(seed + 555 + rank)
+        d_sel = [torch.randint(0, 2, (n_loc,), dtype=torch.uint8, device="cuda", generator=gsel) for _ in range(nsel)]
+    stream.synchronize()   # .cpu() below runs on the default stream
+    fixed = [t.cpu().numpy().view(np.uint64) for t in d_fixed]
+    selectors = [t.cpu().numpy() for t in d_sel]
+    del d_fixed, d_sel
+    S = SG.PlonkStructure(side["field"], modulus, k_loc, selectors, fixed, nadv, 0, cg, gates=gates)
+    if world > 1:
+        sharding.check_rotations_row_local(P.GraphEvaluator.new(cg.homogeneous, modulus).rotations)
+    # commitment key restricted to this rank's rows: ck[col * n + row] for row in the slice, column-major
+    # (the benches' key has 2^(k+4) generators, benches/sangria_poseidon.rs:26-30; only the prefix W needs is materialised)
+    kc = key_cols or nadv
+    with torch.cuda.stream(stream):
+        d_bases = torch.empty((kc * n_loc, 8), dtype=torch.int64, device="cuda")
+    g = curves.generator_limbs(side["curve"])
+    for col, (first, count) in enumerate(sharding.key_segments(kc, n, rank, world)):
+        _lib.check(lib.sb_index_multiples_device(side["curve"], g.ctypes.data_as(_lib.u64p), first, count,
+                                                 ctypes.c_void_p(d_bases.data_ptr() + col * n_loc * 64), ctypes.c_void_p(stream.cuda_stream)))
+    stream.synchronize()
+    ck = CommitmentKey.from_device(side["curve"], d_bases.data_ptr(), kc * n_loc, window_bits=windows[0], stream=stream.cuda_stream)
+    for wb in windows[1:]:
+        ck.add_window(wb, stream.cuda_stream)
+    stream.synchronize()
+    del d_bases
+    return S, ck, cg, dict(side=side, nadv=nadv, nfix=nfix, n_loc=n_loc, fixed=fixed, selectors=selectors)
+
+
+def build_sangria_side(side, k, rank, world, stream, windows, seed, key_cols=None):
+    """Structure + key + device session (device.DeviceSangriaSide) for one curve, restricted to this rank's rows."""
+    import torch
+
+    S, ck, cg, info = build_structure_key(side, k, rank, world, stream, windows, seed, key_cols)
+    nadv, n_loc = info["nadv"], info["n_loc"]
+    sess = device.DeviceSangriaSide(S, ck, stream)
+    with torch.cuda.stream(stream):
+        sess.W_acc.copy_(device.random_field_device(nadv * n_loc, seed + 7 + side["curve"] + 100 * rank))
+        sess.E_acc.copy_(device.random_field_device(n_loc, seed + 8 + side["curve"] + 100 * rank))
+        sess.W_in.copy_(device.random_field_device(nadv * n_loc, seed + 9 + side["curve"] + 100 * rank))
+    stream.synchronize()
+    host_W = torch.empty(sess.W_in.shape, dtype=torch.int64).pin_memory()
+    host_W.copy_(sess.W_in)
+    torch.cuda.synchronize()
+    nch = cg.ctx.num_challenges - 1
+    with torch.cuda.stream(stream):
+        d_ch = device.random_field_device(2 * nch + 2, seed + 11 + side["curve"])   # identical on every rank
+    stream.synchronize()
+    ch = d_ch.cpu().numpy().view(np.uint64)
+    extra = dict(info, host_W=host_W, c1=ch[:nch], c2=ch[nch:2 * nch], u1=ch[2 * nch], r=ch[2 * nch + 1])
+    return sess, extra
 
 
 class Combiner:
@@ -118,55 +195,7 @@ class SangriaStepWorkload:
 
     # ------------------------------------------------------------------ construction
     def _build_side(self, side):
-        torch = self.torch
-        stream, rank, world, k = self.stream, self.rank, self.world, self.k
-        gates, nfix, nadv = compressed_gates(side)
-        cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_fixed=nfix, num_advice=nadv))
-        n = 1 << k
-        row0, n_loc = sharding.row_slice(rank, world, n)
-        k_loc = n_loc.bit_length() - 1
-        modulus = curves.SCALAR_FIELD[side["curve"]]
-        seed = self.seed
-        with torch.cuda.stream(stream):
-            d_fixed = [device.random_field_device(n_loc, seed + 1000 * side["curve"] + 10 * rank + j) for j in range(nfix)]
-        stream.synchronize()   # .cpu() below runs on the default stream
-        fixed = [t.cpu().numpy().view(np.uint64) for t in d_fixed]
-        del d_fixed
-        S = SG.PlonkStructure(side["field"], modulus, k_loc, [], fixed, nadv, 0, cg)
-        if world > 1:
-            sharding.check_rotations_row_local(P.GraphEvaluator.new(cg.homogeneous, modulus).rotations)
-        # commitment key restricted to this rank's rows: ck[col * n + row] for row in the slice, column-major
-        # (the benches' key has 2^(k+4) generators, benches/sangria_poseidon.rs:26-30; only the prefix W needs is materialised)
-        assert nadv * n <= (1 << (k + 4))
-        with torch.cuda.stream(stream):
-            d_bases = torch.empty((nadv * n_loc, 8), dtype=torch.int64, device="cuda")
-        g = curves.generator_limbs(side["curve"])
-        for col, (first, count) in enumerate(sharding.key_segments(nadv, n, rank, world)):
-            _lib.check(self.lib.sb_index_multiples_device(side["curve"], g.ctypes.data_as(_lib.u64p), first, count,
-                                                          ctypes.c_void_p(d_bases.data_ptr() + col * n_loc * 64), ctypes.c_void_p(stream.cuda_stream)))
-        stream.synchronize()
-        ck = CommitmentKey.from_device(side["curve"], d_bases.data_ptr(), nadv * n_loc, window_bits=self.windows[0], stream=stream.cuda_stream)
-        for wb in self.windows[1:]:
-            ck.add_window(wb, stream.cuda_stream)
-        stream.synchronize()
-        del d_bases
-        sess = device.DeviceSangriaSide(S, ck, stream)
-        with torch.cuda.stream(stream):
-            sess.W_acc.copy_(device.random_field_device(nadv * n_loc, seed + 7 + side["curve"] + 100 * rank))
-            sess.E_acc.copy_(device.random_field_device(n_loc, seed + 8 + side["curve"] + 100 * rank))
-            sess.W_in.copy_(device.random_field_device(nadv * n_loc, seed + 9 + side["curve"] + 100 * rank))
-        stream.synchronize()
-        host_W = torch.empty(sess.W_in.shape, dtype=torch.int64).pin_memory()
-        host_W.copy_(sess.W_in)
-        torch.cuda.synchronize()
-        nch = cg.ctx.num_challenges - 1
-        with torch.cuda.stream(stream):
-            d_ch = device.random_field_device(2 * nch + 2, seed + 11 + side["curve"])   # identical on every rank
-        stream.synchronize()
-        ch = d_ch.cpu().numpy().view(np.uint64)
-        extra = dict(side=side, host_W=host_W, c1=ch[:nch], c2=ch[nch:2 * nch], u1=ch[2 * nch], r=ch[2 * nch + 1], nadv=nadv, nfix=nfix,
-                     n_loc=n_loc, fixed=fixed)
-        return sess, extra
+        return build_sangria_side(side, self.k, self.rank, self.world, self.stream, self.windows, self.seed)
 
     # ------------------------------------------------------------------ the timed step
     def _prove(self, sess, ex):
@@ -281,7 +310,7 @@ class SangriaStepWorkload:
             fixed = self._gather_cm(fixed_loc, ex["nfix"])
             n = 1 << self.k
             snap[ex["side"]["name"]] = dict(
-                side=ex["side"], k=self.k, nadv=ex["nadv"], nfix=ex["nfix"],
+                side=ex["side"], k=self.k, nadv=ex["nadv"], nfix=ex["nfix"], selectors=[],
                 fixed=[fixed[j * n:(j + 1) * n] for j in range(ex["nfix"])],
                 W1=self._gather_cm(sess.W_acc, ex["nadv"]), E1=self._gather_cm(sess.E_acc, 1), W2=self._gather_cm(sess.W_in, ex["nadv"]),
                 c1=ex["c1"].copy(), c2=ex["c2"].copy(), u1=ex["u1"].copy(), r=ex["r"].copy(),
@@ -302,3 +331,89 @@ class SangriaStepWorkload:
         for sess in self.sides:
             sess.S.close()
             sess.ck.close()
+
+
+class CyclefoldStepWorkload:
+    """The prover hot path of `cyclefold::IVC::next` (reference src/ivc/cyclefold/incrementally_verifiable_computation/mod.rs:210-335,
+    SURVEY 3.2) at the shapes of benches/cyclefold_poseidon (primary: bn256, A=12, F=26, 2 gates; support circuit: grumpkin,
+    k=15, tiny gate), single GPU, device-resident:
+
+      1. ProtoGalaxy::prove(acc, [trace]) (src/nifs/protogalaxy/mod.rs:400-481): compute_F (2^(k+1) leaves, 32 points),
+         compute_G (8 Lagrange blends), K (host), fold_witness
+      2. fold_support_circuit (:404-473): commit of the support trace (3 * 2^15 scalars) + SangriaFS::prove (2 cross terms,
+         2 commits, W/E fold)
+      3. ProtoGalaxy::generate_plonk_trace of the next primary trace: the 12 * 2^k-point MSM
+
+    Challenges (betas, delta, alpha, gamma, r) come from the host random oracle in the reference; here they are seeded
+    values.  row_mode = ROW_CORRECT by default: in the reference-compatible mode every leaf evaluates row 0
+    and a timing would be meaningless."""
+
+    def __init__(self, k: int, stream=None, windows: Optional[List[int]] = None, seed: int = SEED, support_k: int = 15, row_mode: int = 1):
+        import random
+
+        import torch
+
+        self.torch = torch
+        self.k, self.seed, self.support_k = k, seed, support_k
+        self.stream = stream if stream is not None else torch.cuda.Stream()
+        st = self.stream
+        S, ck, cg, info = build_structure_key(PRIMARY, k, 0, 1, st, windows or ([20] if k >= 19 else [17]), seed)
+        self.pg = device.DeviceProtogalaxySide(S, ck, st, row_mode)
+        self.info = info
+        A, n = info["nadv"], 1 << k
+        with torch.cuda.stream(st):
+            self.pg.W_acc.copy_(device.random_field_device(A * n, seed + 21))
+            self.pg.W_in.copy_(device.random_field_device(A * n, seed + 22))
+        st.synchronize()
+        self.host_W = torch.empty(self.pg.W_in.shape, dtype=torch.int64).pin_memory()
+        self.host_W.copy_(self.pg.W_in)
+        torch.cuda.synchronize()
+        self.sup, self.sup_ex = build_sangria_side(SUPPORT, support_k, 0, 1, st, [13], seed + 3)
+        rng = random.Random(seed)
+        M = S.modulus
+        self.betas = [rng.randrange(M) for _ in range(self.pg.t)]
+        self.delta, self.alpha, self.gamma = rng.randrange(M), rng.randrange(M), rng.randrange(M)
+        self.last = None
+        st.synchronize()
+
+    def step(self, upload: bool = False) -> int:
+        h2d = 0
+        self.last = self.pg.prove(self.betas, self.delta, self.alpha, self.gamma)      # 1. ProtoGalaxy::prove
+        sup, ex = self.sup, self.sup_ex                                                  # 2. fold_support_circuit
+        if upload:
+            h2d += sup.upload_incoming(ex["host_W"])
+        sup.commit_incoming()
+        sup.commit_cross_terms(ex["c1"], ex["u1"], ex["c2"])
+        sup.fold(ex["r"])
+        if upload:                                                                       # 3. the next primary trace
+            h2d += self.pg.upload_incoming(self.host_W)
+        self.pg.commit_incoming()
+        return h2d
+
+    def snapshot_inputs(self) -> Dict:
+        torch = self.torch
+        self.stream.synchronize()
+        pg, ex = self.pg, self.sup_ex
+        cpu = lambda t: t.cpu().numpy().view(np.uint64).copy()  # noqa: E731
+        return dict(
+            k=self.k, row_mode=pg.row_mode, fixed=self.info["fixed"], nadv=self.info["nadv"], W_acc=cpu(pg.W_acc), W_in=cpu(pg.W_in),
+            betas=list(self.betas), delta=self.delta, alpha=self.alpha, gamma=self.gamma,
+            support=dict(side=SUPPORT, k=self.support_k, nadv=ex["nadv"], nfix=ex["nfix"], fixed=ex["fixed"], selectors=ex["selectors"],
+                         W1=cpu(self.sup.W_acc), E1=cpu(self.sup.E_acc), W2=cpu(self.sup.W_in), c1=ex["c1"].copy(), c2=ex["c2"].copy(),
+                         u1=ex["u1"].copy(), r=ex["r"].copy()),
+        )
+
+    def snapshot_results(self) -> Dict:
+        self.stream.synchronize()
+        pg, sup = self.pg, self.sup
+        cpu = lambda t: t.cpu().numpy().view(np.uint64).copy()  # noqa: E731
+        poly_F, poly_G, poly_K = self.last
+        return dict(poly_F=poly_F, poly_G=poly_G, poly_K=poly_K, W=cpu(pg.W_acc), commit_W=pg.h_commit_W.numpy().view(np.uint64).copy(),
+                    support=dict(commits_T=sup.h_commit_T.numpy().view(np.uint64).copy(), commit_W=sup.h_commit_W.numpy().view(np.uint64).copy(),
+                                 W=cpu(sup.W_acc), E=cpu(sup.E_acc)))
+
+    def close(self):
+        self.pg.S.close()
+        self.pg.ck.close()
+        self.sup.S.close()
+        self.sup.ck.close()

@@ -198,3 +198,27 @@ def test_two_threads_two_streams_reentrant(oracle):
     for ck, _ in keys.values():
         ck.close()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("k,row_mode", [(12, 0), (12, 1), (14, 1)])
+def test_cyclefold_next_step_vs_c_oracle(oracle, k, row_mode):
+    """Protogalaxy F / G / K / fold_witness + the support-circuit fold + the trace commitment of cyclefold::IVC::next at
+    k >= 12, device-resident, against the C-interpreter oracle (oracle/pg_fast.py pinned to the literal pg_ref.py on the CPU);
+    both leaf-row modes (reference-compatible `& 2^k` and corrected `% 2^k`)."""
+    import torch
+
+    from oracle import step_ref
+    from sirius_b200 import workload as WL
+
+    wl = WL.CyclefoldStepWorkload(k, torch.cuda.Stream(), windows=[13], support_k=11, row_mode=row_mode)
+    try:
+        for i in range(2):   # the second step folds into the first step's accumulator
+            snap = wl.snapshot_inputs()
+            wl.step(upload=(i == 0))
+            got = wl.snapshot_results()
+            exp = step_ref.cyclefold_step(snap)
+            rep = step_ref.compare_cyclefold(got, exp)
+            assert rep["ok"], rep["bad"]
+            assert len(got["poly_F"]) == 16 and len(got["poly_G"]) == 8 and len(got["poly_K"]) == 256
+    finally:
+        wl.close()

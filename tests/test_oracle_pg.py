@@ -104,3 +104,55 @@ def test_poly_context_quirk_F5():
     assert ctx.fft_points_count_G == 8 and ctx.fft_log_domain_size_K() == 8
     ctx3 = PG.PolyContext(S, 3)
     assert ctx3.fft_points_count_G == 16 and ctx3.fft_log_domain_size_K() == 16
+
+
+# ---- oracle/pg_fast.py (C interpreter + array tree, used at k >= 12) pinned to the literal pg_ref.py ----------------
+@pytest.mark.parametrize("mode", ["compat", "correct"])
+@pytest.mark.parametrize("k,T_list,L", [(3, [2], 1), (4, [2, 2], 1), (3, [2], 3)])
+def test_pg_fast_equals_literal_restatement(oracle, mode, k, T_list, L):
+    from oracle import pg_fast as PF
+
+    n = 1 << k
+    nfix = sum(2 * T + 5 for T in T_list)
+    nadv = sum(T + 2 for T in T_list)
+    gates, fb, ab = [], 0, 0
+    for T in T_list:
+        gates.append(E.main_gate_expression(T, fb, ab, 0, nfix))
+        fb, ab = fb + 2 * T + 5, ab + T + 2
+    gates.append(E.Sub(E.Mul(E.Poly(nfix + 0, 1), E.Chal(0)), E.Poly(nfix + 1, -1)))   # a challenge and rotated cells
+    fixed = [oracle.random_field(R.FIELD_FR, 100 * k + i, n) for i in range(nfix)]
+    So = PG.PGStructure(k, [], [R.from_mont_limbs(f, M) for f in fixed], nadv, 0, gates, num_challenges=1)
+    Sf = PF.Structure(k, [], fixed, nadv, gates)
+    ctx = PG.PolyContext(So, L)
+    assert Sf.betas_count() == ctx.betas_count() and Sf.count() == ctx.count
+    Ws = [oracle.random_field(R.FIELD_FR, 7 * k + j, nadv * n) for j in range(L + 1)]
+    Wi = [[R.from_mont_limbs(w, M)] for w in Ws]
+    rng = R.Xoshiro256ss(5 + k)
+    chs = [[rng.field(M)] for _ in range(L + 1)]
+    t = ctx.betas_count()
+    betas = [rng.field(M) for _ in range(t)]
+    delta, alpha, gamma = rng.field(M), rng.field(M), rng.field(M)
+    assert PF.compute_F(Sf, betas, delta, Ws[0], chs[0], mode) == PG.compute_F(ctx, betas, delta, Wi[0], chs[0], mode)
+    assert PF.evaluate_e(Sf, Ws[0], chs[0], betas, mode) == PG.evaluate_e(So, Wi[0], chs[0], betas, mode)
+    bs = PG.beta_stroke(betas, alpha, delta)
+    max_degree = max(PG.gate_degree(g, So.ctx) for g in gates)
+    assert PF.compute_G(Sf, max_degree, bs, Ws[0], chs[0], Ws[1:], chs[1:], mode) == PG.compute_G(ctx, bs, Wi[0], chs[0], Wi[1:], chs[1:], mode)
+    Lg = R.eval_lagrange_polys(ctx.lagrange_domain(), gamma)
+    assert R.from_mont_limbs(PF.fold_witness(Ws[0], Ws[1:], Lg), M) == PG.fold_witness(Wi[0], Wi[1:], Lg)[0]
+
+
+def test_c_tree_parallel_levels_equal_serial_subtrees(oracle):
+    """so_beta_tree runs the nodes of a level on all cores above 4096 nodes; the result must equal the composition of
+    2^12-leaf subtrees (computed on the serial path) with a top tree -- guards the ping-pong buffering."""
+    from oracle import pg_fast as PF
+
+    t, n = 16, 1 << 16
+    lv = oracle.random_field(R.FIELD_FR, 99, n)
+    rng = R.Xoshiro256ss(3)
+    c = [rng.field(M) for _ in range(t)]
+    sub = [PF.tree(lv[i * 4096:(i + 1) * 4096], c[:12]) for i in range(16)]
+    assert PF.tree(lv, c) == PF.tree(R.to_mont_limbs(sub, M), c[12:])
+    # and the weighted-sum identity on a small tree
+    small = oracle.random_field(R.FIELD_FR, 7, 8)
+    vals = R.from_mont_limbs(small, M)
+    assert PF.tree(small, c[:3]) == sum(w * v for w, v in zip(_pow_weights(8, c[:3]), vals)) % M
