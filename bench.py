@@ -57,7 +57,8 @@ def workload_config(n_gpus, k):
                     f"(MSM {12 << k} + 6x{1 << k} bn256, MSM {7 << k} + 5x{1 << k} grumpkin, 11 cross-term vectors, W/E folds)",
         "k": k,
         "ck_log2": k + 4,
-        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks, one exchange of 128-byte partial sums per commitment group",
+        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks; per commitment group ONE kernel exchanges the 128-byte partial sums over NVLink peer "
+                                                      f"memory and adds them ({os.environ.get('SB_BENCH_EXCHANGE', 'peer')} exchange)",
         "l2": "inputs larger than L2 (window tables of several GB gathered at random; 0.4 GB of per-step scratch at k=17)",
     }
 
@@ -607,7 +608,7 @@ def run_msm_sweep(args):
     from sirius_b200 import workload as WL
     import sirius_b200
 
-    combiner = WL.Combiner(world, stream) if world > 1 else None
+    combiner = WL.make_combiner(rank, world, stream)
     logs = [int(x) for x in (args.sizes or "16,18,20,22,24").split(",")]
     cells = []
     sampler = ClockSampler(arm.local_rank)

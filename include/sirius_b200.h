@@ -46,6 +46,7 @@ extern "C" {
 typedef struct sb_ck* sb_ck_t;           /* device-resident CommitmentKey (src/commitment.rs:29-32) */
 typedef struct sb_prog* sb_prog_t;       /* uploaded GraphEvaluator program (src/polynomial/graph_evaluator.rs:164-180) */
 typedef struct sb_sparse* sb_sparse_t;   /* device-resident SparseMatrix (src/polynomial/sparse.rs:5), rows in CSR order */
+typedef struct sb_comm* sb_comm_t;       /* peer-memory communicator of the multi-GPU commitment (one process per GPU) */
 typedef struct sb_columns* sb_columns_t; /* device-resident selectors + fixed columns of a PlonkStructure (src/plonk/mod.rs:132-133) */
 
 /* ValueSource (graph_evaluator.rs:57-68) and Calculation (graph_evaluator.rs:72-89) discriminants */
@@ -100,7 +101,8 @@ int sb_ck_window_bits(sb_ck_t ck);
  * key 0: batched-affine reduction rounds before the XYZZ bucket kernel (-1 = automatic, 0 = off, <= 8);
  * key 1: outputs per thread of one round (8 or 16);
  * key 2: sort of the digit entries (0 = automatic, 1 = counting sort with one atomic per entry, 2 = two-level
- *        partition sort through shared-memory histograms whenever the bucket count allows). */
+ *        partition sort through shared-memory histograms whenever the bucket count allows);
+ * key 3: commitment tail (1 = 4-warp cooperative group law, the default; 0 = the single-lane / quad-lane kernels). */
 int sb_msm_tune(int key, int value);
 
 /* CommitmentKey::commit (src/commitment.rs:81-90): out = sum_{i<n} scalars[i] * ck[i], affine.
@@ -120,6 +122,22 @@ int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, voi
 /* Batched form: out[b] = affine(sum_g partials[g * stride + b]), g < count ranks, b < batch commitments -- reads
  * the all-gather output [rank][batch] in place. */
 int sb_msm_combine_batch_device(int curve, const void* d_partials_xyzz, int count, size_t batch, size_t stride, void* d_out_xy, void* stream);
+
+/* ---- multi-GPU, one process per GPU: exchange over NVLink / NVSwitch peer memory (csrc/comm.cu) -----------------------
+ * sb_comm_create allocates this rank's mailbox and returns its 64-byte CUDA IPC handle; the caller all-gathers the handles
+ * (any transport: torch.distributed, MPI, a file) and passes the world * 64 bytes, rank-major, to sb_comm_connect on every
+ * rank, followed by a barrier of its own.  max_batch = the largest commitment group (<= 4096). */
+int sb_comm_create(int rank, int world, size_t max_batch, sb_comm_t* out, unsigned char ipc_handle_out[64]);
+int sb_comm_connect(sb_comm_t comm, const unsigned char* all_handles);
+void sb_comm_destroy(sb_comm_t comm);
+int sb_comm_status(sb_comm_t comm, void* stream); /* 0 = every exchange completed, 1 = a rank timed out (4 s), < 0 = error */
+/* out[b] = affine(sum over the ranks of partial[b]), the same on every rank: ONE kernel stores this rank's partials into the
+ * peers' mailboxes, waits for theirs and adds them (no host round trip, no NCCL).  Every rank must make the same calls. */
+int sb_comm_allsum_points_device(sb_comm_t comm, int curve, const void* d_partials_xyzz, size_t batch, void* d_out_xy, void* stream);
+/* CommitmentKey::commit of `batch` row-sharded vectors: this rank's rows of the scalars against this rank's slice of the key
+ * (`ck` holds ck[col * n + row] for the rank's rows); the exchange is fused into the last kernel of the pipeline. */
+int sb_msm_batch_sharded_device(sb_ck_t ck, sb_comm_t comm, const void* d_scalars_mont, size_t n, size_t stride, size_t batch, void* d_out_xy,
+                                void* stream);
 
 /* Validation of a key read from the reference's cache file (raw memory dump of [C], src/commitment.rs:99-128): counts
  * the points that are neither the identity (0,0) nor on y^2 = x^3 + b, as load_or_setup_cache does (:148-157). */
@@ -287,6 +305,10 @@ int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n,
 /* lazy-domain twins (operands anywhere in [0, 2p), raw results; out_canon = a mod p with bit 255 set where a = 0 mod p) */
 int sb_selftest_lazy(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul, uint64_t* out_sub,
                      uint64_t* out_dbl, uint64_t* out_canon);
+
+/* group law: the 4-warp cooperative addition / doubling of the commitment tail (csrc/coop.cuh) against the single-lane forms,
+ * on a chain that visits every exceptional case; 3 affine points per input pair in each output */
+int sb_selftest_coop(int curve, const uint64_t* a_xy, const uint64_t* b_xy, size_t n, uint64_t* out_coop_xy, uint64_t* out_plain_xy);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,12 @@ SIGNATURES = {
     "sb_msm_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, vp, vp, vp]),
     "sb_msm_batch": (ctypes.c_int, [vp, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p]),
     "sb_msm_batch_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp]),
+    "sb_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.c_char_p]),
+    "sb_comm_connect": (ctypes.c_int, [vp, ctypes.c_char_p]),
+    "sb_comm_destroy": (None, [vp]),
+    "sb_comm_status": (ctypes.c_int, [vp, vp]),
+    "sb_comm_allsum_points_device": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_size_t, vp, vp]),
+    "sb_msm_batch_sharded_device": (ctypes.c_int, [vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
     "sb_points_on_curve": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_size_t, u64p]),
     "sb_points_on_curve_device": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, vp, vp]),
     "sb_index_multiples_device": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.c_uint64, ctypes.c_size_t, vp, vp]),
@@ -92,6 +98,7 @@ SIGNATURES = {
     "sb_profile_enable": (None, [ctypes.c_int]),
     "sb_profile_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "sb_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "sb_selftest_coop": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p]),
     "sb_selftest_lazy": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]),
     "sb_selftest_field": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p, u64p]),
 }

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "curve.cuh"
 #include "quad.cuh"
+#include "coop.cuh"
 
 namespace sb {
 
@@ -72,6 +73,23 @@ __global__ void k_mb_madd_lazy(XYZZ<F>* io, int iters) {  // the bucket kernel's
     q.y = io[2 * i + 1].y;
     for (int k = 0; k < iters; k++) xyzz_madd_lazy(a, q, (k & 1) != 0);
     io[2 * i] = canon_point(a);
+}
+// serial additions / doublings by the 4 warps of a block (coop.cuh): block = 128 threads = 32 logical lanes
+template <class F>
+__global__ void __launch_bounds__(COOP_THREADS) k_mb_coop_add(XYZZ<F>* io, int iters) {
+    __shared__ CoopBuf sh;
+    const size_t i = (size_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    XYZZ<F> a = io[2 * i], b = io[2 * i + 1];
+    for (int k = 0; k < iters; k++) coop4_add(a, b, sh);
+    if (threadIdx.x < 32) io[2 * i] = a;
+}
+template <class F>
+__global__ void __launch_bounds__(COOP_THREADS) k_mb_coop_double(XYZZ<F>* io, int iters) {
+    __shared__ CoopBuf sh;
+    const size_t i = (size_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    XYZZ<F> a = io[2 * i];
+    for (int k = 0; k < iters; k++) coop4_double(a, sh);
+    if (threadIdx.x < 32) io[2 * i] = a;
 }
 // Timing experiment only (wrong results): the product with 16 of its 128 IMAD.WIDE removed and ~100 extra
 // carry-chain additions, to price a Karatsuba product (48 + 64 wide multiplies + more additions) before writing it.
@@ -309,6 +327,8 @@ extern "C" int sb_microbench(int which, int iters, int blocks, int threads, doub
             case 11: k_mb_inv<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
             case 12: k_mb_inv_safegcd<Fq><<<blocks, threads, 0, rt.stream>>>((Fq*)d, iters); break;
             case 13: k_mb_madd_lazy<Fq><<<blocks, threads, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
+            case 14: k_mb_coop_add<Fq><<<blocks, COOP_THREADS, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
+            case 15: k_mb_coop_double<Fq><<<blocks, COOP_THREADS, 0, rt.stream>>>((XYZZ<Fq>*)d, iters); break;
             case 20: k_mb_pipe<20><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
             case 21: k_mb_pipe<21><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;
             case 22: k_mb_pipe<22><<<blocks, threads, 0, rt.stream>>>((uint32_t*)d, iters); break;

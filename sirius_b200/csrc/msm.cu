@@ -29,6 +29,7 @@
 #include "curve.cuh"
 #include "affine.cuh"
 #include "quad.cuh"
+#include "coop.cuh"
 
 namespace sb {
 
@@ -848,6 +849,125 @@ k_weighted_finish(const XYZZ<F>* __restrict__ D_all, int log_k, int lc, int max_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// the same tail on the 4-warp cooperative group law (coop.cuh): a block of 128 threads = 32 logical lanes, each
+// addition ~4 dependent products instead of 14.  These kernels replace k_fixup / k_rowcol_sums / k_digit_sums /
+// k_weighted_finish (kept above for A/B measurements, sb_msm_tune key 3).
+// ------------------------------------------------------------------------------------------------
+// fix-up: logical lane = bucket.  Pieces of a bucket are summed serially, but every addition is cooperative; lanes whose
+// bucket has fewer pieces idle (identity operand) until the block's longest bucket is done.
+template <class F>
+__global__ void __launch_bounds__(COOP_THREADS)
+k_fixup_coop(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>* __restrict__ buckets,
+             const XYZZ<F>* __restrict__ PH, const XYZZ<F>* __restrict__ PT, uint32_t* __restrict__ heavy_count,
+             uint32_t* __restrict__ heavy_list) {
+    __shared__ CoopBuf sh;
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * 32u + (uint32_t)lane;
+    uint32_t np = 0, t0 = 0;
+    bool head_tail = false;
+    if (b < KB) {
+        const uint32_t o = offsets[b], o2 = offsets[b + 1];
+        if (o2 == o) {
+            if (role == 0) store_vec(buckets + b, XYZZ<F>::identity());
+        } else {
+            t0 = o / LS;
+            np = (o2 - 1) / LS - t0 + 1;
+            head_tail = (o - t0 * LS) != 0;
+            if (np == 1) np = 0;   // written by k_accumulate
+            else if (np > (uint32_t)FIX_SEQ) {
+                if (role == 0) heavy_list[atomicAdd(heavy_count, 1u)] = b;
+                np = 0;
+            }
+        }
+    }
+    const uint32_t np_max = __reduce_max_sync(0xffffffffu, np);   // identical in the 4 warps (replicated data)
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (np) acc = head_tail ? load_vec(PT + t0) : load_vec(PH + t0);
+#pragma unroll 1
+    for (uint32_t p = 1; p < np_max; p++) {
+        XYZZ<F> q = XYZZ<F>::identity();
+        if (p < np) q = load_vec(PH + t0 + p);
+        coop4_add(acc, q, sh);
+    }
+    if (np && role == 0) store_vec(buckets + b, acc);
+}
+
+// row / column sums: one block per row or column, grid (R + C, batch)
+template <class F>
+__global__ void __launch_bounds__(COOP_THREADS)
+k_rowcol_coop(const XYZZ<F>* __restrict__ buckets_all, int log_k, int lc, XYZZ<F>* __restrict__ vec_all) {
+    __shared__ CoopBuf sh;
+    const uint32_t K = 1u << log_k, C = 1u << lc, R = K >> lc;
+    const uint32_t w = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const XYZZ<F>* buckets = buckets_all + (size_t)blockIdx.y * K;
+    const bool row = w < R;
+    const uint32_t cnt = row ? C : R, per = (cnt + 31u) >> 5;
+    XYZZ<F> acc = XYZZ<F>::identity();
+#pragma unroll 1
+    for (uint32_t t = 0; t < per; t++) {
+        const uint32_t j = t * 32u + (uint32_t)lane;
+        XYZZ<F> x = XYZZ<F>::identity();
+        if (j < cnt) x = row ? load_vec(buckets + (size_t)w * C + j) : load_vec(buckets + (size_t)j * C + (w - R));
+        if (t == 0) acc = x;
+        else coop4_add(acc, x, sh);
+    }
+    acc = coop_lane_sum(acc, sh);
+    if (threadIdx.x == 0) store_vec(vec_all + (size_t)blockIdx.y * (R + C) + w, acc);
+}
+
+// grid (2, batch): blockIdx.x = 0 -> X = C * sum_r r * Row_r, 1 -> Y = sum_q (q + 1) * Col_q.
+// Logical lane l holds the m = n / 32 consecutive entries E[l*m .. l*m+m): a running sum gives S_l = sum E and
+// T_l = sum_i (i + 1) E[l*m + i]; then sum_j (j + w0) E_j = m * sum_{l >= 1} suffix_l(S) + sum_l (T_l - (1 - w0) S_l):
+// one suffix scan and one sum over the lanes (shuffles), log2(m) doublings -- no scalar multiplication, no digit sums.
+template <class F>
+__global__ void __launch_bounds__(COOP_THREADS)
+k_weighted_coop(const XYZZ<F>* __restrict__ vec_all, int log_k, int lc, XYZZ<F>* __restrict__ xy_all) {
+    __shared__ CoopBuf sh;
+    const uint32_t K = 1u << log_k, C = 1u << lc, R = K >> lc;
+    const int which = blockIdx.x;
+    const uint32_t n = which == 0 ? R : C;
+    const XYZZ<F>* E = vec_all + (size_t)blockIdx.y * (R + C) + (which == 0 ? 0 : R);
+    const int lane = threadIdx.x & 31;
+    const uint32_t m = n >= 32u ? (n >> 5) : 1u;
+    int log_m = 0;
+    while ((1u << log_m) < m) log_m++;
+    XYZZ<F> S = XYZZ<F>::identity(), T = XYZZ<F>::identity();
+#pragma unroll 1
+    for (int i = (int)m - 1; i >= 0; i--) {
+        const uint32_t j = (uint32_t)lane * m + (uint32_t)i;
+        XYZZ<F> x = XYZZ<F>::identity();
+        if (j < n) x = load_vec(E + j);
+        if (i == (int)m - 1) {
+            S = x;
+            T = x;
+        } else {
+            coop4_add(S, x, sh);
+            coop4_add(T, S, sh);
+        }
+    }
+    XYZZ<F> V = T;
+    if (which == 0) {   // weights start at 0: T - S
+        XYZZ<F> ns = S;
+        ns.y = neg(ns.y);
+        coop4_add(V, ns, sh);
+    }
+    XYZZ<F> suf = S;    // inclusive suffix sums over the lanes
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        XYZZ<F> t = coop_shfl_down(suf, d);
+        coop4_add(suf, t, sh);
+    }
+    XYZZ<F> A = lane >= 1 ? suf : XYZZ<F>::identity();
+    for (int k = 0; k < log_m; k++) coop4_double(A, sh);
+    coop4_add(V, A, sh);
+    V = coop_lane_sum(V, sh);
+    if (which == 0)
+        for (int k = 0; k < lc; k++) coop4_double(V, sh);   // the row part carries the factor C = 2^lc
+    if (threadIdx.x == 0) store_vec(xy_all + (size_t)blockIdx.y * 2 + which, V);
+}
+
 // root = C*X + Y (both already weighted) ; out = affine(root)
 template <class F>
 __global__ void k_reduce_final(const XYZZ<F>* __restrict__ xy_all, uint32_t batch, Affine<F>* out_xy, XYZZ<F>* out_xyzz) {
@@ -951,6 +1071,10 @@ static int g_sort_mode = []() {   // 0 = automatic, 1 = always the per-entry ato
 static int g_pair_b = []() {
     const char* e = getenv("SB_MSM_PAIR_B");
     return e ? atoi(e) : 16;
+}();
+static int g_tail_mode = []() {   // 1 = 4-warp cooperative tail kernels (coop.cuh), 0 = the round-1 single-lane / quad-lane tail
+    const char* e = getenv("SB_MSM_TAIL");
+    return e ? atoi(e) : 1;
 }();
 constexpr int MAX_AFFINE_ROUNDS = 8;
 
@@ -1058,11 +1182,13 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     return SB_OK;
 }
 
+int comm_exchange_enqueue(::sb_comm* c, int curve, const void* d_in, int pairs, size_t batch, void* d_out_xy, cudaStream_t st);   // comm.cu
+
 static size_t g_part_smem_set = 0;   // largest dynamic shared-memory size k_partition has been opted into (under rt.mu)
 
 template <class F, class S>
 static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, size_t stride, void* d_out_xy,
-                       void* d_out_xyzz, cudaStream_t st) {
+                       void* d_out_xyzz, cudaStream_t st, ::sb_comm* comm = nullptr) {
     const uint32_t n = (uint32_t)p.n, total = (uint32_t)p.total;
     auto* dig = (uint2*)(ws + p.off_dig);
     auto* counts = (uint32_t*)(ws + p.off_counts);
@@ -1178,7 +1304,8 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     }
     {
         ProfScope ps(st, PROF_FIXUP, KB);
-        k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
+        if (g_tail_mode) k_fixup_coop<F><<<(KB + 31) / 32, COOP_THREADS, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
+        else k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
         k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(off_final, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
@@ -1191,6 +1318,12 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         auto* xy = (XYZZ<F>*)(ws + p.off_nodes_b);    // [batch][2]
         {
             ProfScope ps(st, PROF_REDUCE, KB);
+            if (g_tail_mode) {
+                k_rowcol_coop<F><<<dim3(R + C, p.batch), COOP_THREADS, 0, st>>>(buckets, log_k, lc, vec);
+                SB_KERNEL_CHECK();
+                k_weighted_coop<F><<<dim3(2, p.batch), COOP_THREADS, 0, st>>>(vec, log_k, lc, xy);
+                SB_KERNEL_CHECK();
+            } else {
             dim3 g1((R + C + 3) / 4, p.batch);
             k_rowcol_sums<F><<<g1, 128, 0, st>>>(buckets, log_k, lc, vec);
             SB_KERNEL_CHECK();
@@ -1203,27 +1336,39 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
             dim3 g2(2, p.batch);
             k_weighted_finish<F><<<g2, 32 * (max_pos + 1), 0, st>>>(dsum, log_k, lc, max_pos, xy);
             SB_KERNEL_CHECK();
+            }
         }
         {
             ProfScope pf(st, PROF_FINALIZE, p.batch);
-            k_reduce_final<F><<<p.batch, 4, 0, st>>>(xy, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
-            SB_KERNEL_CHECK();
+            if (comm) {   // multi-GPU: X + Y, the exchange over peer memory, the sum of the ranks' partials and the normalisation in ONE kernel
+                SB_TRY(comm_exchange_enqueue(comm, ck->curve, xy, 1, p.batch, d_out_xy, st));
+            } else {
+                k_reduce_final<F><<<p.batch, 4, 0, st>>>(xy, p.batch, (Affine<F>*)d_out_xy, (XYZZ<F>*)d_out_xyzz);
+                SB_KERNEL_CHECK();
+            }
         }
     }
     return SB_OK;
 }
 
 static int msm_dispatch(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, size_t stride, void* d_out_xy,
-                        void* d_out_xyzz, cudaStream_t st) {
+                        void* d_out_xyzz, cudaStream_t st, ::sb_comm* comm = nullptr) {
     if (p.batch == 0) return SB_OK;
+    if (p.n == 0 && comm) {   // this rank owns no rows of the vector: its partial is the identity, the peers still wait for it
+        void* xy = ws + p.off_nodes_b;
+        if (ck->curve == CURVE_BN256) k_identity_out<Fq><<<p.batch * 2, 32, 0, st>>>(p.batch * 2, nullptr, (XYZZ<Fq>*)xy);
+        else k_identity_out<Fr><<<p.batch * 2, 32, 0, st>>>(p.batch * 2, nullptr, (XYZZ<Fr>*)xy);
+        SB_KERNEL_CHECK();
+        return comm_exchange_enqueue(comm, ck->curve, xy, 1, p.batch, d_out_xy, st);
+    }
     if (p.n == 0) {
         if (ck->curve == CURVE_BN256) k_identity_out<Fq><<<p.batch, 32, 0, st>>>(p.batch, (Affine<Fq>*)d_out_xy, (XYZZ<Fq>*)d_out_xyzz);
         else k_identity_out<Fr><<<p.batch, 32, 0, st>>>(p.batch, (Affine<Fr>*)d_out_xy, (XYZZ<Fr>*)d_out_xyzz);
         SB_KERNEL_CHECK();
         return SB_OK;
     }
-    if (ck->curve == CURVE_BN256) return msm_enqueue<Fq, Fr>(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st);
-    return msm_enqueue<Fr, Fq>(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st);
+    if (ck->curve == CURVE_BN256) return msm_enqueue<Fq, Fr>(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
+    return msm_enqueue<Fr, Fq>(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
 }
 
 static int ck_add_table(sb_ck* ck, const void* d_bases, int c, cudaStream_t st) {
@@ -1357,6 +1502,7 @@ int sb_msm_tune(int key, int value) {
     if (key == 0 && value >= -1 && value <= MAX_AFFINE_ROUNDS) g_affine_rounds = value;
     else if (key == 1 && (value == 8 || value == 16)) g_pair_b = value;
     else if (key == 2 && value >= 0 && value <= 2) g_sort_mode = value;
+    else if (key == 3 && (value == 0 || value == 1)) g_tail_mode = value;
     else {
         set_error("sb_msm_tune: bad key/value %d/%d", key, value);
         return SB_ERR_ARG;
@@ -1389,6 +1535,26 @@ int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t
     Scratch& ws = ws_slot(st, WS_MSM);
     SB_TRY(ws.reserve(p.total_bytes));
     return msm_dispatch(ck, p, (char*)ws.ptr, d_scalars_mont, stride, d_out_xy, d_out_xyzz, st);
+}
+
+/* Row-sharded commitment group: this rank's scalars against this rank's slice of the key; the partial sums are
+ * exchanged over peer memory inside the pipeline's last kernel (comm.cu) and every rank receives the affine totals. */
+int sb_msm_batch_sharded_device(sb_ck_t ck, sb_comm_t comm, const void* d_scalars_mont, size_t n, size_t stride, size_t batch, void* d_out_xy,
+                                void* stream) {
+    if (!ck || !comm || (!d_scalars_mont && n && batch) || !d_out_xy || stride < n) {
+        set_error("sb_msm_batch_sharded_device: bad argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(check_len(ck, n));
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    RtLock lk(rt.mu);
+    MsmPlan p;
+    SB_TRY(make_plan(ck, n, batch, false, p));
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    Scratch& ws = ws_slot(st, WS_MSM);
+    SB_TRY(ws.reserve(p.total_bytes));
+    return msm_dispatch(ck, p, (char*)ws.ptr, d_scalars_mont, stride, d_out_xy, nullptr, st, comm);
 }
 
 int sb_msm_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, void* d_out_xy, void* d_out_xyzz, void* stream) {

@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "curve.cuh"
+#include "coop.cuh"
 
 namespace sb {
 
@@ -182,11 +183,92 @@ __global__ void k_selftest_lazy(const F* a, const F* b, size_t n, F* o_mul, F* o
     o_canon[i] = c;
 }
 
+// the same chain of group operations through the 4-warp cooperative forms (coop.cuh) and the single-lane forms; it
+// visits every exceptional case: generic add, P + P through add, doubling, P + (-P), identity on either side
+template <class F, bool COOP>
+SB_D void selftest_chain(const Affine<F>& pa, const Affine<F>& pb, CoopBuf* sh, Affine<F>& out_t, Affine<F>& out_u, Affine<F>& out_v) {
+    auto addp = [&](XYZZ<F>& x, const XYZZ<F>& y) {
+        if constexpr (COOP) coop4_add(x, y, *sh);
+        else xyzz_add<true>(x, y);
+    };
+    auto dblp = [&](XYZZ<F>& x) {
+        if constexpr (COOP) coop4_double(x, *sh);
+        else x = xyzz_double<true>(x);
+    };
+    XYZZ<F> a = XYZZ<F>::from_affine(pa), b = XYZZ<F>::from_affine(pb);
+    XYZZ<F> t = a;
+    addp(t, b);                 // generic (or an exceptional case when the inputs say so)
+    XYZZ<F> t2 = t;
+    addp(t, t2);                // P + P through the addition
+    dblp(t);                    // doubling
+    addp(t, b);                 // generic with non-trivial ZZ
+    XYZZ<F> u = t;
+    XYZZ<F> nt = t;
+    nt.y = neg(nt.y);
+    addp(u, nt);                // P + (-P) -> identity
+    XYZZ<F> v = t;
+    addp(v, u);                 // + identity
+    addp(u, t);                 // identity + P
+    dblp(u);
+    out_t = xyzz_to_affine<true>(t);
+    out_u = xyzz_to_affine<true>(u);
+    out_v = xyzz_to_affine<true>(v);
+}
+template <class F>
+__global__ void __launch_bounds__(COOP_THREADS) k_selftest_coop(const Affine<F>* pa, const Affine<F>* pb, size_t n, Affine<F>* out_coop, Affine<F>* out_plain) {
+    __shared__ CoopBuf sh;
+    const size_t i = (size_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    Affine<F> za, zb;
+    za.x = F::zero(); za.y = F::zero(); zb = za;
+    const Affine<F> a = i < n ? pa[i] : za, b = i < n ? pb[i] : zb;   // lanes past the end run the chain on identities (block-uniform trip counts)
+    Affine<F> t, u, v;
+    selftest_chain<F, true>(a, b, &sh, t, u, v);
+    if (i < n && threadIdx.x < 32) { out_coop[3 * i] = t; out_coop[3 * i + 1] = u; out_coop[3 * i + 2] = v; }
+    if (threadIdx.x < 32) {
+        selftest_chain<F, false>(a, b, nullptr, t, u, v);
+        if (i < n) { out_plain[3 * i] = t; out_plain[3 * i + 1] = u; out_plain[3 * i + 2] = v; }
+    }
+}
+
 }  // namespace sb
 
 using namespace sb;
 
 extern "C" {
+
+/* Group-law self test: for every pair (a[i], b[i]) of affine points the chain ((a+b)+(a+b)) doubled, + b, then P + (-P), + identity,
+ * identity + P, through the 4-warp cooperative operations (out_coop) and the single-lane ones (out_plain); 3 affine points per pair. */
+int sb_selftest_coop(int curve, const uint64_t* a_xy, const uint64_t* b_xy, size_t n, uint64_t* out_coop_xy, uint64_t* out_plain_xy) {
+    if (!a_xy || !b_xy || !out_coop_xy || !out_plain_xy || !n) {
+        set_error("sb_selftest_coop: bad argument");
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    RtLock lk(rt.mu);
+    char* d = nullptr;
+    SB_CUDA_TRY(cudaMalloc(&d, n * 64 * 8));
+    int rc = SB_OK;
+    cudaError_t e = cudaMemcpyAsync(d, a_xy, n * 64, cudaMemcpyHostToDevice, rt.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n * 64, b_xy, n * 64, cudaMemcpyHostToDevice, rt.stream);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)((n + 31) / 32);
+        if (curve == CURVE_BN256)
+            k_selftest_coop<Fq><<<blocks, COOP_THREADS, 0, rt.stream>>>((const Affine<Fq>*)d, (const Affine<Fq>*)(d + n * 64), n, (Affine<Fq>*)(d + n * 128), (Affine<Fq>*)(d + n * 320));
+        else
+            k_selftest_coop<Fr><<<blocks, COOP_THREADS, 0, rt.stream>>>((const Affine<Fr>*)d, (const Affine<Fr>*)(d + n * 64), n, (Affine<Fr>*)(d + n * 128), (Affine<Fr>*)(d + n * 320));
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_coop_xy, d + n * 128, n * 192, cudaMemcpyDeviceToHost, rt.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_plain_xy, d + n * 320, n * 192, cudaMemcpyDeviceToHost, rt.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rt.stream);
+    if (e != cudaSuccess) {
+        set_error("sb_selftest_coop: %s", cudaGetErrorString(e));
+        rc = SB_ERR_CUDA;
+    }
+    cudaFree(d);
+    return rc;
+}
 
 const char* sb_last_error(void) { return g_err; }
 int sb_version(void) { return 1; }

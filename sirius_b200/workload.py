@@ -173,10 +173,73 @@ class Combiner:
         self.stream.synchronize()
 
 
+class PeerCombiner:
+    """N > 1, the default: the exchange is fused into the last kernel of the commitment pipeline (csrc/comm.cu): every rank
+    stores its 128-byte partial sums into the peers' mailboxes over NVLink (CUDA IPC peer memory), waits for theirs, adds
+    them and normalises -- no NCCL launch and no extra kernels on the critical path of a commitment group.
+    torch.distributed is used once, to all-gather the 64-byte IPC handles."""
+
+    MAX_BATCH = 64
+
+    def __init__(self, rank, world, stream, alone: bool = False):
+        """alone = True: a one-rank communicator (the rank exchanges with itself) -- tools/shard_profile.py uses it to time one
+        rank's share of an N-GPU step, exchange kernel included, on a single GPU."""
+        import torch
+
+        self.rank, self.world, self.stream, self.torch = rank, world, stream, torch
+        self.lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        if alone:
+            _lib.check(self.lib.sb_comm_create(0, 1, self.MAX_BATCH, ctypes.byref(self._h), handle))
+            _lib.check(self.lib.sb_comm_connect(self._h, handle.raw))
+        else:
+            import torch.distributed as dist
+
+            _lib.check(self.lib.sb_comm_create(rank, world, self.MAX_BATCH, ctypes.byref(self._h), handle))
+            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
+            gathered = torch.empty((world, 64), dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(gathered, mine)
+            torch.cuda.synchronize()
+            _lib.check(self.lib.sb_comm_connect(self._h, gathered.cpu().numpy().tobytes()))
+            dist.barrier()   # every mailbox exists and is zeroed before the first store into it
+        torch.cuda.synchronize()
+        self.out = {}
+
+    def commit(self, ck: CommitmentKey, d_scalars: int, n: int, batch: int, h_out) -> None:
+        torch = self.torch
+        if batch not in self.out:
+            with torch.cuda.stream(self.stream):
+                self.out[batch] = torch.zeros((batch, 8), dtype=torch.int64, device="cuda")
+        out = self.out[batch]
+        _lib.check(self.lib.sb_msm_batch_sharded_device(ck._h, self._h, ctypes.c_void_p(d_scalars), n, n, batch, ctypes.c_void_p(out.data_ptr()),
+                                                        ctypes.c_void_p(self.stream.cuda_stream)))
+        with torch.cuda.stream(self.stream):
+            h_out.copy_(out.view(h_out.shape), non_blocking=True)
+        self.stream.synchronize()
+
+    def status(self) -> int:
+        return int(self.lib.sb_comm_status(self._h, ctypes.c_void_p(self.stream.cuda_stream)))
+
+    def close(self):
+        if self._h.value:
+            self.lib.sb_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+
+def make_combiner(rank, world, stream):
+    """SB_BENCH_EXCHANGE=nccl selects the library path (NCCL all-gather + combine kernel) for A/B measurements."""
+    if world <= 1:
+        return None
+    if os.environ.get("SB_BENCH_EXCHANGE", "peer") == "nccl":
+        return Combiner(world, stream)
+    return PeerCombiner(rank, world, stream)
+
+
 class SangriaStepWorkload:
     """Both sides of the cycle, device-resident, restricted to this rank's rows."""
 
-    def __init__(self, k: int, rank: int = 0, world: int = 1, stream=None, windows: Optional[List[int]] = None, seed: int = SEED):
+    def __init__(self, k: int, rank: int = 0, world: int = 1, stream=None, windows: Optional[List[int]] = None, seed: int = SEED, combiner="auto"):
         import torch
 
         self.torch = torch
@@ -190,7 +253,7 @@ class SangriaStepWorkload:
             sess, ex = self._build_side(side)
             self.sides.append(sess)
             self.extras.append(ex)
-        self.combiner = Combiner(world, self.stream) if world > 1 else None
+        self.combiner = make_combiner(rank, world, self.stream) if combiner == "auto" else combiner
         self.stream.synchronize()
 
     # ------------------------------------------------------------------ construction
@@ -328,6 +391,8 @@ class SangriaStepWorkload:
         return res
 
     def close(self):
+        if self.combiner is not None and hasattr(self.combiner, "close"):
+            self.combiner.close()
         for sess in self.sides:
             sess.S.close()
             sess.ck.close()
