@@ -78,6 +78,13 @@ int sb_version(void);
 
 /* Select / initialise the CUDA device this process uses (one process per GPU).  device < 0: keep current. */
 int sb_init(int device);
+/* One process, several GPUs: devices[0] is the primary device (all _device entry points, cross terms, folds, NTT run there);
+ * CommitmentKeys registered from host memory afterwards are split block-cyclically over the n devices, and the plain
+ * `sb_msm(ck, host scalars, n, out)` / `sb_msm_batch` -- i.e. the unchanged Rust `CommitmentKey::commit` body of INTEGRATION.md --
+ * shard every commit over them inside the library: per-device upload of the rank's share of the scalars, the Pippenger
+ * pipeline on every device, peer copies of the 128-byte partial sums, one combine kernel.  n = 1 is sb_init(devices[0]). */
+int sb_init_devices(const int* devices, int n);
+int sb_num_devices(void);
 void sb_shutdown(void);
 int sb_device_count(void);
 /* Frees the device scratch kept for `stream` (synchronises it first). */

@@ -28,6 +28,8 @@ SIGNATURES = {
     "sb_last_error": (ctypes.c_char_p, []),
     "sb_version": (ctypes.c_int, []),
     "sb_init": (ctypes.c_int, [ctypes.c_int]),
+    "sb_init_devices": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "sb_num_devices": (ctypes.c_int, []),
     "sb_shutdown": (None, []),
     "sb_device_count": (ctypes.c_int, []),
     "sb_stream_release": (None, [vp]),

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/sirius_b200.h"
 
@@ -65,6 +66,10 @@ struct Runtime {
     int sm_count = 0;
     cudaStream_t stream = nullptr;   // the library's own stream: host-memory entry points run here
     std::atomic<bool> ready{false};
+    // sb_init_devices: the devices a single process drives (devs[0] = the primary above).  Host-memory commits against a
+    // key registered while several devices are active are sharded over them inside the library (msm.cu).
+    struct Dev { int device; cudaStream_t stream; int sm_count; };
+    std::vector<Dev> devs;
 };
 Runtime& runtime();
 int ensure_runtime();

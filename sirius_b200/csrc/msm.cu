@@ -22,6 +22,8 @@
 #include <string.h>
 #include <algorithm>
 #include <memory>
+#include <string>
+#include <thread>
 #include <vector>
 #include <new>
 
@@ -1024,6 +1026,10 @@ struct sb_ck {
     uint32_t K;
     void* table;
     std::vector<sb_ck_table> tables;  // every registered window width; the commit picks the cheapest per call
+    // single process, several GPUs (sb_init_devices): the key is split block-cyclically (SHARD_BLOCK points per block) over
+    // the devices; shards[g] is an ordinary key on device g holding blocks g, g + G, g + 2G, ...  (empty = not sharded)
+    std::vector<sb_ck*> shards;
+    int dev_index = 0;   // index into Runtime::devs of the device holding `tables`
 };
 
 namespace sb {
@@ -1184,7 +1190,7 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
 
 int comm_exchange_enqueue(::sb_comm* c, int curve, const void* d_in, int pairs, size_t batch, void* d_out_xy, cudaStream_t st);   // comm.cu
 
-static size_t g_part_smem_set = 0;   // largest dynamic shared-memory size k_partition has been opted into (under rt.mu)
+static size_t g_part_smem_set[64] = {0};   // per device: largest dynamic shared-memory size k_partition has been opted into
 
 template <class F, class S>
 static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, size_t stride, void* d_out_xy,
@@ -1229,9 +1235,12 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         k_scan_small<<<1, 1024, 0, st>>>(part_count, P, part_off);
         SB_KERNEL_CHECK();
         const size_t part_smem = ((size_t)3 * P + 256 + 2) * 4 + (size_t)256 * p.W * 8;
-        if (part_smem > g_part_smem_set) {   // ONE tracker for the one (non-template) kernel: the attribute only ever grows
+        int cur_dev = 0;
+        cudaGetDevice(&cur_dev);
+        size_t& smem_set = g_part_smem_set[cur_dev & 63];
+        if (part_smem > smem_set) {   // ONE tracker per device for the one (non-template) kernel: the attribute only ever grows
             SB_CUDA_TRY(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
-            g_part_smem_set = part_smem;
+            smem_set = part_smem;
         }
         k_partition<<<(total + 255) / 256, 256, part_smem, st>>>((const uint32_t*)dig, n, total, K, (uint32_t)ck->n, p.W, P, part_off, part_cursor, out1);
         SB_KERNEL_CHECK();
@@ -1433,6 +1442,156 @@ static int ck_build(int curve, const void* d_bases, size_t n, int window_bits, c
     return SB_OK;
 }
 
+// ---- single process, several GPUs ------------------------------------------------------------------------------------
+constexpr size_t SHARD_BLOCK = 4096;   // points per block of the block-cyclic split: any prefix of the key is balanced to within a block
+
+// number of the first n global indices that land on device g of G
+static size_t shard_count(size_t n, int g, int G) {
+    const size_t cycle = SHARD_BLOCK * (size_t)G;
+    const size_t q = n / cycle, rem = n - q * cycle;
+    const size_t lo = (size_t)g * SHARD_BLOCK;
+    const size_t extra = rem > lo ? std::min(rem - lo, SHARD_BLOCK) : 0;
+    return q * SHARD_BLOCK + extra;
+}
+
+// device g's elements (elem_bytes each) of the first n of a host array -> contiguous device memory, on `st`
+static cudaError_t shard_upload(void* d_dst, const void* h_src, size_t n, size_t elem_bytes, int g, int G, cudaStream_t st) {
+    const size_t cycle = SHARD_BLOCK * (size_t)G;
+    const size_t q = n / cycle, rem = n - q * cycle;
+    const size_t lo = (size_t)g * SHARD_BLOCK;
+    const char* src = (const char*)h_src + lo * elem_bytes;
+    cudaError_t e = cudaSuccess;
+    if (q) e = cudaMemcpy2DAsync(d_dst, SHARD_BLOCK * elem_bytes, src, cycle * elem_bytes, SHARD_BLOCK * elem_bytes, q, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && rem > lo) {
+        const size_t extra = std::min(rem - lo, SHARD_BLOCK);
+        e = cudaMemcpyAsync((char*)d_dst + q * SHARD_BLOCK * elem_bytes, src + q * cycle * elem_bytes, extra * elem_bytes, cudaMemcpyHostToDevice, st);
+    }
+    return e;
+}
+
+static int ck_register_sharded(int curve, const uint64_t* bases_xy, size_t n, int window_bits, sb_ck_t* out) {
+    Runtime& rt = runtime();
+    const int G = (int)rt.devs.size();
+    sb_ck* parent = new (std::nothrow) sb_ck();
+    if (!parent) return SB_ERR_OOM;
+    parent->curve = curve;
+    parent->n = n;
+    int rc = SB_OK;
+    for (int g = 0; g < G && rc == SB_OK; g++) {
+        const size_t ng = shard_count(n, g, G);
+        cudaSetDevice(rt.devs[g].device);
+        void* d_bases = nullptr;
+        cudaError_t e = cudaMalloc(&d_bases, ng * 64 + 64);
+        if (e == cudaSuccess) e = shard_upload(d_bases, bases_xy, n, 64, g, G, rt.devs[g].stream);
+        if (e != cudaSuccess) {
+            set_error("sb_ck_register (device %d): %s", rt.devs[g].device, cudaGetErrorString(e));
+            rc = SB_ERR_CUDA;
+        }
+        sb_ck* sh = nullptr;
+        if (rc == SB_OK) rc = ck_build(curve, d_bases, ng, window_bits, rt.devs[g].stream, &sh);
+        if (d_bases) cudaFree(d_bases);
+        if (rc == SB_OK) {
+            sh->dev_index = g;
+            parent->shards.push_back(sh);
+        }
+    }
+    cudaSetDevice(rt.device);
+    if (rc != SB_OK) {
+        sb_ck_release(parent);
+        return rc;
+    }
+    parent->c = parent->shards[0]->c;
+    parent->W = parent->shards[0]->W;
+    parent->K = parent->shards[0]->K;
+    parent->table = nullptr;
+    *out = parent;
+    return SB_OK;
+}
+
+static Scratch g_gather;   // device 0: [G][batch] XYZZ partials + batch affine results (sharded host commits; under rt.mu)
+
+// sb_msm_batch on a sharded key: every device commits its block-cyclic share of the scalars (uploaded straight from the
+// caller's arrays by one host thread per device), the 128-byte partial sums travel to the primary device by peer copies,
+// one combine kernel adds them.  Bit-identical to the single-device result (exact arithmetic).
+static int msm_batch_sharded(sb_ck* ck, const uint64_t* const* scalars_mont, size_t n, size_t batch, uint64_t* out_xy) {
+    Runtime& rt = runtime();
+    const int G = (int)ck->shards.size();
+    if (G != (int)rt.devs.size()) {
+        set_error("sb_msm: the key was registered for %d devices, the runtime now drives %zu", G, rt.devs.size());
+        return SB_ERR_ARG;
+    }
+    std::vector<MsmPlan> plans(G);
+    std::vector<char*> wss(G);
+    std::vector<size_t> counts(G);
+    for (int g = 0; g < G; g++) {   // workspaces are reserved by the calling thread (the per-stream slot map is not thread-safe)
+        counts[g] = shard_count(n, g, G);
+        SB_TRY(make_plan(ck->shards[g], counts[g], batch, true, plans[g]));
+        cudaSetDevice(rt.devs[g].device);
+        Scratch& ws = ws_slot(rt.devs[g].stream, WS_MSM);
+        int rc = ws.reserve(plans[g].total_bytes);
+        if (rc != SB_OK) {
+            cudaSetDevice(rt.device);
+            return rc;
+        }
+        wss[g] = (char*)ws.ptr;
+    }
+    cudaSetDevice(rt.device);
+    SB_TRY(g_gather.reserve((size_t)G * batch * 128 + batch * 64 + 256));
+    char* gather = (char*)g_gather.ptr;
+    std::vector<cudaEvent_t> done(G);
+    std::vector<int> rcs(G, SB_OK);
+    std::vector<std::string> errs(G);
+    auto worker = [&](int g) {
+        const Runtime::Dev& dv = rt.devs[g];
+        cudaSetDevice(dv.device);
+        const MsmPlan& p = plans[g];
+        char* ws = wss[g];
+        cudaError_t e = cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming);
+        for (size_t b = 0; b < batch && e == cudaSuccess; b++)
+            e = shard_upload(ws + p.off_scalars + b * counts[g] * 32, scalars_mont[b], n, 32, g, G, dv.stream);
+        int rc = SB_OK;
+        if (e == cudaSuccess) rc = msm_dispatch(ck->shards[g], p, ws, ws + p.off_scalars, counts[g], nullptr, ws + p.off_out_xyzz, dv.stream);
+        if (rc != SB_OK) errs[g] = sb_last_error();
+        if (e == cudaSuccess && rc == SB_OK)
+            e = cudaMemcpyPeerAsync(gather + (size_t)g * batch * 128, rt.device, ws + p.off_out_xyzz, dv.device, batch * 128, dv.stream);
+        if (e == cudaSuccess && rc == SB_OK) e = cudaEventRecord(done[g], dv.stream);
+        if (e != cudaSuccess) {
+            errs[g] = std::string("device ") + std::to_string(dv.device) + ": " + cudaGetErrorString(e);
+            rc = SB_ERR_CUDA;
+        }
+        rcs[g] = rc;
+    };
+    {
+        std::vector<std::thread> threads;
+        for (int g = 1; g < G; g++) threads.emplace_back(worker, g);
+        worker(0);
+        for (auto& t : threads) t.join();
+    }
+    cudaSetDevice(rt.device);
+    int rc = SB_OK;
+    for (int g = 0; g < G; g++)
+        if (rcs[g] != SB_OK && rc == SB_OK) {
+            set_error("sb_msm (sharded): %s", errs[g].c_str());
+            rc = rcs[g];
+        }
+    if (rc == SB_OK) {
+        for (int g = 0; g < G; g++) SB_CUDA_TRY(cudaStreamWaitEvent(rt.stream, done[g], 0));
+        char* d_out = gather + (size_t)G * batch * 128;
+        rc = sb_msm_combine_batch_device(ck->curve, gather, G, batch, batch, d_out, rt.stream);
+        if (rc == SB_OK) {
+            SB_CUDA_TRY(cudaMemcpyAsync(out_xy, d_out, 64 * batch, cudaMemcpyDeviceToHost, rt.stream));
+            SB_CUDA_TRY(cudaStreamSynchronize(rt.stream));
+        }
+    }
+    for (int g = 0; g < G; g++) {   // the partial-sum buffers are reused by the next call: every device must be done with them
+        cudaSetDevice(rt.devs[g].device);
+        if (rcs[g] == SB_OK) cudaStreamSynchronize(rt.devs[g].stream);
+        if (done[g]) cudaEventDestroy(done[g]);
+    }
+    cudaSetDevice(rt.device);
+    return rc;
+}
+
 }  // namespace sb
 
 using namespace sb;
@@ -1447,6 +1606,7 @@ int sb_ck_register(int curve, const uint64_t* bases_xy, size_t n, int window_bit
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
     RtLock lk(rt.mu);
+    if (rt.devs.size() > 1 && (curve == CURVE_BN256 || curve == CURVE_GRUMPKIN)) return ck_register_sharded(curve, bases_xy, n, window_bits, out);
     void* d_bases = nullptr;
     if (n) {
         SB_CUDA_TRY(cudaMalloc(&d_bases, n * 64));
@@ -1475,14 +1635,33 @@ int sb_ck_register_device(int curve, const void* d_bases_xy, size_t n, int windo
 
 void sb_ck_release(sb_ck_t ck) {
     if (!ck) return;
-    for (sb_ck_table& t : ck->tables)
-        if (t.table) cudaFree(t.table);
+    for (sb_ck* sh : ck->shards) sb_ck_release(sh);
+    if (!ck->tables.empty()) {
+        Runtime& rt = runtime();
+        const bool other = ck->dev_index > 0 && ck->dev_index < (int)rt.devs.size();
+        if (other) cudaSetDevice(rt.devs[ck->dev_index].device);
+        for (sb_ck_table& t : ck->tables)
+            if (t.table) cudaFree(t.table);
+        if (other) cudaSetDevice(rt.device);
+    }
     delete ck;
 }
 
 /* A further window width for the same key: table 0 holds the generators themselves (window 0 of any table), so
  * additional tables are derived on the device.  Commits then use whichever registered width is cheapest. */
 int sb_ck_add_window(sb_ck_t ck, int window_bits, void* stream) {
+    if (ck && !ck->shards.empty()) {   // sharded key: the width is added on every device (its own stream)
+        SB_TRY(ensure_runtime());
+        Runtime& rt = runtime();
+        RtLock lk(rt.mu);
+        int rc = SB_OK;
+        for (size_t g = 0; g < ck->shards.size() && rc == SB_OK; g++) {
+            cudaSetDevice(rt.devs[g].device);
+            rc = ck_add_table(ck->shards[g], ck->shards[g]->tables[0].table, window_bits, rt.devs[g].stream);
+        }
+        cudaSetDevice(rt.device);
+        return rc;
+    }
     if (!ck || ck->tables.empty()) {
         set_error("sb_ck_add_window: bad key");
         return SB_ERR_ARG;
@@ -1525,6 +1704,10 @@ int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t
         set_error("sb_msm_batch_device: bad argument");
         return SB_ERR_ARG;
     }
+    if (!ck->shards.empty()) {
+        set_error("sb_msm_batch_device: this key is sharded over %zu devices (sb_init_devices); use the host entry points sb_msm / sb_msm_batch", ck->shards.size());
+        return SB_ERR_ARG;
+    }
     SB_TRY(check_len(ck, n));
     SB_TRY(ensure_runtime());
     Runtime& rt = runtime();
@@ -1541,7 +1724,7 @@ int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t
  * exchanged over peer memory inside the pipeline's last kernel (comm.cu) and every rank receives the affine totals. */
 int sb_msm_batch_sharded_device(sb_ck_t ck, sb_comm_t comm, const void* d_scalars_mont, size_t n, size_t stride, size_t batch, void* d_out_xy,
                                 void* stream) {
-    if (!ck || !comm || (!d_scalars_mont && n && batch) || !d_out_xy || stride < n) {
+    if (!ck || !comm || (!d_scalars_mont && n && batch) || !d_out_xy || stride < n || !ck->shards.empty()) {
         set_error("sb_msm_batch_sharded_device: bad argument");
         return SB_ERR_ARG;
     }
@@ -1571,6 +1754,12 @@ int sb_msm_batch(sb_ck_t ck, const uint64_t* const* scalars_mont, size_t n, size
     Runtime& rt = runtime();
     RtLock lk(rt.mu);
     if (batch == 0) return SB_OK;
+    for (size_t b = 0; b < batch && n; b++)
+        if (!scalars_mont[b]) {
+            set_error("sb_msm_batch: null scalar vector %zu", b);
+            return SB_ERR_ARG;
+        }
+    if (!ck->shards.empty()) return msm_batch_sharded(ck, scalars_mont, n, batch, out_xy);
     MsmPlan p;
     SB_TRY(make_plan(ck, n, batch, true, p));
     Scratch& wss = ws_slot(rt.stream, WS_MSM);

@@ -86,6 +86,13 @@ static int init_locked(Runtime& rt, int device) {
     SB_CUDA_TRY(cudaStreamCreateWithFlags(&rt.stream, cudaStreamNonBlocking));
     rt.device = cur;
     rt.sm_count = prop.multiProcessorCount;
+    for (size_t i = 1; i < rt.devs.size(); i++)
+        if (rt.devs[i].stream) {
+            cudaSetDevice(rt.devs[i].device);
+            cudaStreamDestroy(rt.devs[i].stream);
+        }
+    cudaSetDevice(cur);
+    rt.devs.assign(1, Runtime::Dev{cur, rt.stream, rt.sm_count});
     rt.ready.store(true, std::memory_order_release);
     return SB_OK;
 }
@@ -314,6 +321,58 @@ int sb_init(int device) {
     RtLock lk(rt.mu);
     return init_locked(rt, device);
 }
+
+/* One process, several GPUs (`sb_init(devs, n)`): devices[0] becomes the primary device (every _device entry point and
+ * every non-commit kernel runs there); keys registered from host memory afterwards are split block-cyclically over all n devices and
+ * sb_msm / sb_msm_batch shard each commit over them, exchanging the 128-byte partial sums by peer copies.  n = 1 is sb_init. */
+int sb_init_devices(const int* devices, int n) {
+    if (!devices || n < 1 || n > 16) {
+        set_error("sb_init_devices: bad argument");
+        return SB_ERR_ARG;
+    }
+    Runtime& rt = runtime();
+    RtLock lk(rt.mu);
+    rt.ready.store(false);   // force re-initialisation of the primary even when the device is unchanged
+    SB_TRY(init_locked(rt, devices[0]));
+    for (int i = 1; i < n; i++) {
+        for (int j = 0; j < i; j++)
+            if (devices[j] == devices[i]) {
+                set_error("sb_init_devices: device %d listed twice", devices[i]);
+                return SB_ERR_ARG;
+            }
+        cudaDeviceProp prop;
+        SB_CUDA_TRY(cudaGetDeviceProperties(&prop, devices[i]));
+        if (prop.major < 10) {
+            set_error("device %d is sm_%d%d; this library is built for sm_100a only", devices[i], prop.major, prop.minor);
+            return SB_ERR_CUDA;
+        }
+        SB_CUDA_TRY(cudaSetDevice(devices[i]));
+        Runtime::Dev d{devices[i], nullptr, prop.multiProcessorCount};
+        SB_CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        rt.devs.push_back(d);
+    }
+    // peer access in both directions (partial sums travel by cudaMemcpyPeerAsync; NVLink when the GPUs share an NVSwitch)
+    for (size_t i = 0; i < rt.devs.size(); i++) {
+        SB_CUDA_TRY(cudaSetDevice(rt.devs[i].device));
+        for (size_t j = 0; j < rt.devs.size(); j++) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, rt.devs[i].device, rt.devs[j].device);
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(rt.devs[j].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", rt.devs[i].device, rt.devs[j].device, cudaGetErrorString(e));
+                    return SB_ERR_CUDA;
+                }
+                cudaGetLastError();
+            }
+        }
+    }
+    SB_CUDA_TRY(cudaSetDevice(rt.device));
+    return SB_OK;
+}
+
+int sb_num_devices(void) { return (int)runtime().devs.size(); }
 
 void sb_shutdown(void) {
     Runtime& rt = runtime();

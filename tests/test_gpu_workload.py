@@ -222,3 +222,50 @@ def test_cyclefold_next_step_vs_c_oracle(oracle, k, row_mode):
             assert len(got["poly_F"]) == 16 and len(got["poly_G"]) == 8 and len(got["poly_K"]) == 256
     finally:
         wl.close()
+
+
+def test_in_library_multi_gpu_commit(oracle):
+    """Multi-GPU behind the ABI (SURVEY 8b `sb_init(devs, n)`): one process, `sb_init_devices`, then the PLAIN host entry points
+    `sb_msm` / `sb_msm_batch` -- what the unchanged Rust `CommitmentKey::commit` binds -- shard every commit over the devices.
+    Lengths around the block-cyclic boundaries, prefixes of the key, batches, both curves; then back to one device."""
+    import ctypes
+
+    import torch
+
+    import oracle as O
+    import sirius_b200
+    from sirius_b200 import _lib
+
+    G = torch.cuda.device_count()
+    if G < 2:
+        pytest.skip("needs >= 2 GPUs on the box (run with gpurun --gpus 2)")
+    lib = _lib.load()
+    devs = (ctypes.c_int * G)(*range(G))
+    _lib.check(lib.sb_init_devices(devs, G))
+    try:
+        assert lib.sb_num_devices() == G
+        for curve in (0, 1):
+            n = 3 * 4096 * G + 4096 + 77          # several full cycles + a partial one
+            bases = O.running_bases(curve, n)
+            ck = sirius_b200.CommitmentKey(curve, bases)
+            for m in (n, n - 1, 4096 * G, 4096 * G + 1, 4095, 1, 0, 2 * 4096 * G - 5):
+                s = O.random_field(curve, 31 + m, m)
+                assert np.array_equal(ck.commit(s), O.msm(curve, s, bases)), (curve, m)
+            vs = [O.random_field(curve, 900 + j, 4096 * G + 9) for j in range(3)]
+            got = ck.commit_batch(vs)
+            for j, v in enumerate(vs):
+                assert np.array_equal(got[j], O.msm(curve, v, bases)), (curve, "batch", j)
+            with pytest.raises(sirius_b200.TooLongInput):
+                ck.commit(O.random_field(curve, 1, n + 1))
+            ck.add_window(9)
+            s = O.random_field(curve, 5, 5000)
+            assert np.array_equal(ck.commit(s), O.msm(curve, s, bases))
+            ck.close()
+    finally:
+        one = (ctypes.c_int * 1)(0)
+        _lib.check(lib.sb_init_devices(one, 1))
+    bases = O.running_bases(0, 1000)
+    ck = sirius_b200.CommitmentKey(0, bases)
+    s = O.random_field(0, 3, 1000)
+    assert np.array_equal(ck.commit(s), O.msm(0, s, bases))
+    ck.close()
