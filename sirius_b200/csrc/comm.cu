@@ -6,11 +6,11 @@
 // launches and NCCL's protocol latency on the critical path of EVERY commitment group, four times per fold step.
 // Here the last kernel of the pipeline does the exchange itself:
 //
-//   1. adds the two halves of the weighted bucket sum (X + Y) -> this rank's partial,
+//   1. adds the two halves of the weighted bucket sum (X + Y) -> this rank's partial (4-warp cooperative addition, coop.cuh),
 //   2. stores it into the mailbox of every peer (plain 16-byte stores to peer memory mapped through CUDA IPC: NVLink
 //      P2P writes), fences system-wide, then raises a per-(rank, commitment) sequence flag in each peer's mailbox,
 //   3. spins on the flags in its OWN mailbox (local HBM polls) until every rank's partial has arrived,
-//   4. adds the partials in rank order and normalises to affine.
+//   4. adds the partials by a log2(world)-step butterfly over the block's logical lanes and normalises to affine.
 //
 // No host round trip, no NCCL launch; every rank ends with the same affine commitments.  Mailboxes are double-buffered
 // by the parity of the call sequence number: a rank can be at most one call ahead of a peer (it needs the peer's flag
@@ -22,7 +22,7 @@
 
 #include "common.cuh"
 #include "curve.cuh"
-#include "quad.cuh"
+#include "coop.cuh"
 
 namespace sb {
 
@@ -61,24 +61,25 @@ SB_D uint4 ld_volatile_v4(const uint4* p) {
     return v;
 }
 
-// grid = batch blocks of 128 threads.  in: pairs ? xy[b][2] (the two halves of the weighted bucket sum) : partial[b].
+// grid = batch blocks of 128 threads = 32 logical lanes of the 4-warp cooperative group law (coop.cuh).
+// in: pairs ? xy[b][2] (the two halves of the weighted bucket sum) : partial[b].
 template <class F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(COOP_THREADS)
 k_exchange_combine(CommView c, uint32_t seq, const XYZZ<F>* __restrict__ in, int pairs, Affine<F>* __restrict__ out_xy,
                    unsigned int* __restrict__ status) {
+    __shared__ CoopBuf sh;
     __shared__ XYZZ<F> mine;
     __shared__ int failed;
     const uint32_t b = blockIdx.x, parity = seq & 1u;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) failed = 0;
-    if (tid < 4) {   // one 4-lane group forms this rank's partial
-        XYZZ<F> acc = in[pairs ? 2 * b : b];
-        if (pairs) {
-            XYZZ<F> y = in[2 * b + 1];
-            quad_add(acc, y);
-        }
-        if (tid == 0) mine = acc;
+    // 1. this rank's partial: X + Y (every logical lane computes the same sum; one addition of latency)
+    XYZZ<F> acc = in[pairs ? 2 * b : b];
+    if (pairs) {
+        const XYZZ<F> y = in[2 * b + 1];
+        coop4_add(acc, y, sh);
     }
+    if (tid == 0) mine = acc;
     __syncthreads();
     // 2. the partial goes to every rank's mailbox: 8 x 16-byte stores per peer
     if (tid < c.world * 8) {
@@ -104,23 +105,26 @@ k_exchange_combine(CommView c, uint32_t seq, const XYZZ<F>* __restrict__ in, int
     }
     __syncthreads();
     if (failed) return;
-    // 4. sum in rank order, normalise
-    if (tid < 4) {
-        XYZZ<F> acc = XYZZ<F>::identity();
-        for (int r = 0; r < c.world; r++) {
-            XYZZ<F> q;
-            const uint4* src = reinterpret_cast<const uint4*>(c.peers[c.rank] + mailbox_slot_off(c, parity, (uint32_t)r, b));
+    // 4. logical lane r takes rank r's partial; a log2(world)-step butterfly adds them (same order on every rank)
+    XYZZ<F> q = XYZZ<F>::identity();
+    if (lane < c.world) {
+        const uint4* src = reinterpret_cast<const uint4*>(c.peers[c.rank] + mailbox_slot_off(c, parity, (uint32_t)lane, b));
 #pragma unroll
-            for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(&q)[k] = ld_volatile_v4(src + k);
-            quad_add(acc, q);
-        }
-        if (tid == 0) {
-            Affine<F> a = xyzz_to_affine<false>(acc);
-            uint4* d = reinterpret_cast<uint4*>(out_xy + b);
-            const uint4* s = reinterpret_cast<const uint4*>(&a);
+        for (int k = 0; k < 8; k++) reinterpret_cast<uint4*>(&q)[k] = ld_volatile_v4(src + k);
+    }
+    int span = 1;
+    while (span < c.world) span <<= 1;
+#pragma unroll 1
+    for (int d = span >> 1; d >= 1; d >>= 1) {
+        XYZZ<F> t = coop_shfl_xor(q, d);
+        coop4_add(q, t, sh);
+    }
+    if (tid == 0) {
+        Affine<F> a = xyzz_to_affine<false>(q);
+        uint4* d = reinterpret_cast<uint4*>(out_xy + b);
+        const uint4* s = reinterpret_cast<const uint4*>(&a);
 #pragma unroll
-            for (int k = 0; k < 4; k++) d[k] = s[k];
-        }
+        for (int k = 0; k < 4; k++) d[k] = s[k];
     }
 }
 
@@ -158,9 +162,9 @@ int comm_exchange_enqueue(sb_comm* c, int curve, const void* d_in, int pairs, si
     v.max_batch = (uint32_t)c->max_batch;
     const uint32_t seq = ++c->seq;
     if (curve == CURVE_BN256)
-        k_exchange_combine<Fq><<<(unsigned)batch, 128, 0, st>>>(v, seq, (const XYZZ<Fq>*)d_in, pairs, (Affine<Fq>*)d_out_xy, c->d_status);
+        k_exchange_combine<Fq><<<(unsigned)batch, COOP_THREADS, 0, st>>>(v, seq, (const XYZZ<Fq>*)d_in, pairs, (Affine<Fq>*)d_out_xy, c->d_status);
     else if (curve == CURVE_GRUMPKIN)
-        k_exchange_combine<Fr><<<(unsigned)batch, 128, 0, st>>>(v, seq, (const XYZZ<Fr>*)d_in, pairs, (Affine<Fr>*)d_out_xy, c->d_status);
+        k_exchange_combine<Fr><<<(unsigned)batch, COOP_THREADS, 0, st>>>(v, seq, (const XYZZ<Fr>*)d_in, pairs, (Affine<Fr>*)d_out_xy, c->d_status);
     else {
         set_error("sb_comm: unknown curve %d", curve);
         return SB_ERR_ARG;

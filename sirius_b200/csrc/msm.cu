@@ -886,11 +886,14 @@ k_fixup_coop(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZ
     const uint32_t np_max = __reduce_max_sync(0xffffffffu, np);   // identical in the 4 warps (replicated data)
     XYZZ<F> acc = XYZZ<F>::identity();
     if (np) acc = head_tail ? load_vec(PT + t0) : load_vec(PH + t0);
+    XYZZ<F> q = XYZZ<F>::identity();
+    if (1 < np) q = load_vec(PH + t0 + 1);
 #pragma unroll 1
     for (uint32_t p = 1; p < np_max; p++) {
-        XYZZ<F> q = XYZZ<F>::identity();
-        if (p < np) q = load_vec(PH + t0 + p);
+        XYZZ<F> q_next = XYZZ<F>::identity();   // the next piece is in flight while this one is added
+        if (p + 1 < np) q_next = load_vec(PH + t0 + p + 1);
         coop4_add(acc, q, sh);
+        q = q_next;
     }
     if (np && role == 0) store_vec(buckets + b, acc);
 }
@@ -1136,11 +1139,29 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     // >= 4 resident warps per scheduler (148 SMs x 4 SMSPs x 4 warps x 32 lanes = 75 776 threads) in k_accumulate
     // and no longer than ~1/4 of the average bucket (measured: chunks spanning several buckets run ~30 % slower)
     {
-        const size_t wave_threads = (size_t)(runtime().sm_count > 0 ? runtime().sm_count : 148) * 4 * 128;  // one full wave of k_accumulate
+        // Small commits (the row shards of a multi-GPU step, KB <= 32768 buckets) are bound by the LATENCY of the per-commitment
+        // tail, not by throughput: two resident blocks per SM already keep the integer pipe ~full (a lone warp reaches 70 % of the
+        // mixed-addition peak), and chunks twice as long halve the pieces the fix-up has to add serially -- measured on one rank's
+        // share of the 8-GPU step: 3.74 -> 3.56 ms (fix-up 0.50 -> 0.34 ms).  Large commits keep four blocks per SM and chunks
+        // of at most a quarter bucket (longer chunks cost the accumulate kernel what the fix-up gains, profiles/r2_chunk_policy.txt).
+        static const int wave_blocks_env = []() {
+            const char* e = getenv("SB_MSM_WAVE_BLOCKS");
+            const int v = e ? atoi(e) : 0;
+            return v >= 1 && v <= 4 ? v : 0;
+        }();
+        static const int bucket_div_env = []() {
+            const char* e = getenv("SB_MSM_BUCKET_DIV");
+            const int v = e ? atoi(e) : 0;
+            return v >= 1 && v <= 8 ? v : 0;
+        }();
+        const bool small = p.KB <= 32768u;
+        const int wave_blocks = wave_blocks_env ? wave_blocks_env : (small ? 2 : 4);
+        const int bucket_div = bucket_div_env ? bucket_div_env : (small ? 2 : 4);
+        const size_t wave_threads = (size_t)(runtime().sm_count > 0 ? runtime().sm_count : 148) * wave_blocks * 128;  // one full wave of k_accumulate
         const size_t m = p.rounds ? (p.nW >> p.rounds) : p.nW;
         const size_t per_bucket = m / (p.KB ? p.KB : 1);
         int l = LS_MIN_LOG;
-        while (l < LS_MAX_LOG && (m >> (l + 1)) >= wave_threads && ((size_t)4 << l) < per_bucket) l++;
+        while (l < LS_MAX_LOG && (m >> (l + 1)) >= wave_threads && ((size_t)bucket_div << l) < per_bucket) l++;
         size_t len = (size_t)1 << l;
         // shorten the chunks so that the threads fill a whole number of waves (every thread does the same work: a
         // partly filled last wave costs a full wave's latency on the SMs it touches)
@@ -1313,7 +1334,9 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     }
     {
         ProfScope ps(st, PROF_FIXUP, KB);
-        if (g_tail_mode) k_fixup_coop<F><<<(KB + 31) / 32, COOP_THREADS, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
+        // cooperative fix-up for few buckets (latency-bound, skewed top-window buckets); with many buckets the fix-up is
+        // throughput-bound and one plain lane per bucket wastes nothing (0.44 vs 0.63 ms per step at k = 17 on one GPU)
+        if (g_tail_mode && KB <= 32768u) k_fixup_coop<F><<<(KB + 31) / 32, COOP_THREADS, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
         else k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
         k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(off_final, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);

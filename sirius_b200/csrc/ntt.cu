@@ -13,6 +13,7 @@
 //
 // Roofline: algorithmic traffic 64 B/element; arithmetic (log2 N)/2 + O(1) Montgomery products
 // per element.
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <vector>
