@@ -728,6 +728,8 @@ def main():
     ap.add_argument("--verify-max-log", type=int, default=24, help="msm_sweep: check cells up to this log2 size against the CPU oracle")
     ap.add_argument("--k", type=int, default=K_TABLE, help="table size 2^k rows of the main line (default 17 = BASELINE configs[1])")
     args = ap.parse_args()
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # before torch / NCCL load: keep stdout to the one JSON line (NCCL prints its banner there)
     if args.workload == "cyclefold_poseidon":
         return run_cyclefold(args)
     if args.workload == "msm_sweep":

@@ -186,10 +186,15 @@ int sb_cross_terms(sb_prog_t prog, uint32_t degree, sb_columns_t cols, uint32_t 
                    const uint64_t* const* W1, const size_t* W1_lens, size_t W1_rounds, const uint64_t* const* W2,
                    const size_t* W2_lens, size_t W2_rounds, const uint64_t* challenges1, const uint64_t* challenges2,
                    size_t num_challenges, uint64_t* const* out_T);
-/* d_adv*_cols: HOST arrays of num_fold_vars DEVICE column pointers; d_out: degree * 2^log_rows elements. */
+/* d_adv*_cols: HOST arrays of num_fold_vars DEVICE column pointers; d_out: degree * 2^log_rows elements.
+ * The evaluation runs on a straight-line kernel generated from the calculation list and compiled with NVRTC on first use
+ * per (program, degree, column layout) -- a few seconds once; sb_expr_jit_enable(0) (or SB_EXPR_JIT=0) keeps the
+ * interpreter kernel.  Both give the same bits. */
 int sb_cross_terms_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, const void* const* d_adv1_cols,
                           const void* const* d_adv2_cols, size_t num_fold_vars, const uint64_t* challenges1,
                           const uint64_t* challenges2, size_t num_challenges, void* d_out, void* stream);
+
+void sb_expr_jit_enable(int on);
 
 /* RelaxedPlonkWitness::fold (src/nifs/sangria/accumulator.rs:363-404):
  *   axpy : out[i] = w1[i] + r * w2[i]                        (:366-378)
@@ -313,6 +318,11 @@ int sb_selftest_field(int field, const uint64_t* a, const uint64_t* b, size_t n,
 int sb_selftest_lazy(int field, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_mul, uint64_t* out_sub,
                      uint64_t* out_dbl, uint64_t* out_canon);
 
+/* run-time compiled cross-term kernels (csrc/expr.cu): generate + NVRTC-compile the straight-line kernel of a calculation list for
+ * (degree, column layout) without a device; log receives the compiler output (ptxas resource usage) */
+int sb_expr_jit_selftest(int field, const sb_calc* calcs, size_t n_calcs, size_t n_constants, const int32_t* rotations, size_t n_rotations, uint32_t degree,
+                         uint32_t num_selectors, uint32_t num_fixed, uint32_t num_fold_vars, uint32_t num_challenges, char* log, size_t log_cap,
+                         size_t* cubin_bytes);
 /* group law: the 4-warp cooperative addition / doubling of the commitment tail (csrc/coop.cuh) against the single-lane forms,
  * on a chain that visits every exceptional case; 3 affine points per input pair in each output */
 int sb_selftest_coop(int curve, const uint64_t* a_xy, const uint64_t* b_xy, size_t n, uint64_t* out_coop_xy, uint64_t* out_plain_xy);

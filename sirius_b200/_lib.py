@@ -100,6 +100,9 @@ SIGNATURES = {
     "sb_profile_enable": (None, [ctypes.c_int]),
     "sb_profile_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "sb_microbench": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "sb_expr_jit_enable": (None, [ctypes.c_int]),
+    "sb_expr_jit_selftest": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int32), ctypes.c_size_t, ctypes.c_uint32,
+                                            ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "sb_selftest_coop": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p]),
     "sb_selftest_lazy": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p]),
     "sb_selftest_field": (ctypes.c_int, [ctypes.c_int, u64p, u64p, ctypes.c_size_t, u64p, u64p, u64p, u64p, u64p]),

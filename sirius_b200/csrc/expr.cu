@@ -17,8 +17,12 @@
 // coalesced (consecutive rows -> consecutive 32-byte elements).
 #include <string.h>
 
+#include <nvrtc.h>
+#include <stdlib.h>
+
 #include <algorithm>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -249,6 +253,9 @@ struct sb_prog {
     void* d_vinv;
     std::vector<uint32_t> poly_indices;  // distinct column indices the program reads (for validation)
     std::vector<uint32_t> fixed_indices; // ValueSource::Fixed column indices (checked against the registered columns)
+    std::vector<sb::DevOp> h_ops;        // host copy of the lowered program: input of the straight-line code generator (expr_jit)
+    std::vector<int32_t> h_rotations;
+    std::vector<struct sb_jit_entry*> jit;   // compiled cross-term kernels, one per (degree, column layout)
     uint32_t max_challenge;
     bool uses_challenge;
 };
@@ -444,6 +451,213 @@ static int pg_leaves_enqueue(sb_prog* const* gates, size_t num_gates, sb_columns
     return SB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// straight-line cross-term kernels, compiled at run time (NVRTC)
+// ------------------------------------------------------------------------------------------------
+// The interpreter above pays, per calculation, a 16-byte op fetch, the decode, two operand-kind switches and a
+// shared-memory round trip of every intermediate (ncu: issue-active 25-31 %, i.e. latency-bound, not pipe-bound).
+// A compiled GraphEvaluator program is a fixed straight-line sequence, so for the cross terms (the hot use) the
+// library generates CUDA source for the program -- every calculation one statement on register-resident values,
+// every distinct leaf (column, rotation) loaded and blended ONCE -- compiles it with NVRTC for sm_100a and keeps
+// the kernel per (program, degree, column layout).  Same lazy-domain field operations (field.cuh is compiled in
+// verbatim), same evaluation points 0..d, same inverse Vandermonde: bit-identical outputs.  SB_EXPR_JIT=0 keeps
+// the interpreter (also the fallback if the run-time compiler is unavailable).
+struct JitArgs {
+    const void* const* fixed;
+    const uint8_t* const* selectors;
+    const void* const* adv1;
+    const void* const* adv2;
+    const void* constants;
+    const void* challenges;   // [(d+1)][num_challenges]
+    const void* vinv;         // [(d+1)][(d+1)]
+    void* out;                // [d][n]
+    uint32_t n, rows_per_block;
+};
+
+}  // namespace sb
+
+struct sb_jit_entry {
+    uint32_t degree, num_selectors, num_fixed, nfv, nch;
+    cudaLibrary_t lib;
+    cudaKernel_t fn;
+    bool ok;
+};
+
+namespace sb {
+
+static const char FIELD_SRC[] =
+#include "field_src.inc"
+    ;
+
+static std::string jit_source(int field, const std::vector<DevOp>& ops, const std::vector<int32_t>& rots, uint32_t degree, uint32_t num_sel,
+                              uint32_t num_fixed, uint32_t nfv, uint32_t nch) {
+    std::string s;
+    s.reserve(1 << 16);
+    s += "typedef unsigned char uint8_t;\ntypedef unsigned short uint16_t;\ntypedef unsigned int uint32_t;\ntypedef unsigned long long uint64_t;\n"
+         "typedef signed char int8_t;\ntypedef short int16_t;\ntypedef int int32_t;\ntypedef long long int64_t;\n";
+    s += FIELD_SRC;
+    s += "\nusing namespace sb;\ntypedef ";
+    s += field == FIELD_FR ? "Fr" : "Fq";
+    s += " F;\n";
+    s += "struct JitArgs { const void* const* fixed; const uint8_t* const* selectors; const void* const* adv1; const void* const* adv2; const void* constants;\n"
+         "  const void* challenges; const void* vinv; void* out; uint32_t n, rows_per_block; };\n"
+         "__device__ __forceinline__ F ld(const void* p, uint32_t i) { F r; const uint4* s = reinterpret_cast<const uint4*>(p) + 2 * (size_t)i; uint4* d = reinterpret_cast<uint4*>(&r);\n"
+         "  d[0] = __ldg(s); d[1] = __ldg(s + 1); return r; }\n"
+         "__device__ __forceinline__ void st(void* p, size_t i, const F& v) { uint4* d = reinterpret_cast<uint4*>(p) + 2 * i; const uint4* s = reinterpret_cast<const uint4*>(&v); d[0] = s[0]; d[1] = s[1]; }\n";
+    const uint32_t m = degree + 1;
+    char buf[512];
+    snprintf(buf, sizeof(buf),
+             "extern \"C\" __global__ void __launch_bounds__(128) sb_ct(JitArgs A) {\n"
+             "  extern __shared__ uint4 sm_[];\n  F* exch = reinterpret_cast<F*>(sm_);\n"
+             "  const uint32_t m = %uu, r_in = threadIdx.x / m, t = threadIdx.x - r_in * m;\n"
+             "  const uint32_t row = blockIdx.x * A.rows_per_block + r_in, mask = A.n - 1u;\n  (void)mask;\n"
+             "  const bool live = r_in < A.rows_per_block && row < A.n;\n  if (live) {\n", m);
+    s += buf;
+    // leaves are materialised at their first use
+    std::vector<std::string> leaf_keys, leaf_names;
+    auto leaf = [&](uint32_t kind, uint32_t v) -> std::string {
+        snprintf(buf, sizeof(buf), "%u:%u", kind, v);
+        const std::string key = buf;
+        for (size_t i = 0; i < leaf_keys.size(); i++)
+            if (leaf_keys[i] == key) return leaf_names[i];
+        snprintf(buf, sizeof(buf), "l%zu", leaf_keys.size());
+        const std::string name = buf;
+        std::string def;
+        if (kind == VS_CONSTANT) {
+            snprintf(buf, sizeof(buf), "    const F %s = ld(A.constants, %uu);\n", name.c_str(), v);
+            def = buf;
+        } else if (kind == VS_CHALLENGE) {
+            snprintf(buf, sizeof(buf), "    const F %s = ld(A.challenges, t * %uu + %uu);\n", name.c_str(), nch, v);
+            def = buf;
+        } else {
+            const uint32_t index = v & 0xffffffu;
+            const int32_t rot = rots.empty() ? 0 : rots[v >> 24];
+            char rexpr[64];
+            if (rot == 0) snprintf(rexpr, sizeof(rexpr), "row");
+            else snprintf(rexpr, sizeof(rexpr), "((uint32_t)((int32_t)row + (%d)) & mask)", rot);   // get_rotation_idx, graph_evaluator.rs:51-53
+            if (kind == VS_FIXED) {
+                snprintf(buf, sizeof(buf), "    const F %s = ld(A.fixed[%u], %s);\n", name.c_str(), index, rexpr);
+                def = buf;
+            } else if (index < num_sel) {
+                snprintf(buf, sizeof(buf), "    const F %s = A.selectors[%u][%s] ? F::one() : F::zero();\n", name.c_str(), index, rexpr);
+                def = buf;
+            } else if (index < num_sel + num_fixed) {
+                snprintf(buf, sizeof(buf), "    const F %s = ld(A.fixed[%u], %s);\n", name.c_str(), index - num_sel, rexpr);
+                def = buf;
+            } else {
+                const uint32_t a = index - num_sel - num_fixed;
+                if (a >= nfv) {   // explicit second-instance variable
+                    snprintf(buf, sizeof(buf), "    const F %s = ld(A.adv2[%u], %s);\n", name.c_str(), a - nfv, rexpr);
+                    def = buf;
+                } else {          // w1 + t * w2 at this thread's evaluation point (PlonkEvalDomain::eval_advice_var with the folded instance)
+                    snprintf(buf, sizeof(buf), "    F %s = ld(A.adv1[%u], %s);\n    { const F w = ld(A.adv2[%u], %s); for (uint32_t k = 0; k < t; k++) %s = add(%s, w); }\n",
+                             name.c_str(), a, rexpr, a, rexpr, name.c_str(), name.c_str());
+                    def = buf;
+                }
+            }
+        }
+        s += def;
+        leaf_keys.push_back(key);
+        leaf_names.push_back(name);
+        return name;
+    };
+    std::vector<std::string> slot_name;   // current SSA name held by each slot
+    std::string last = "F::zero()";
+    for (size_t i = 0; i < ops.size(); i++) {
+        const DevOp& o = ops[i];
+        const uint32_t op = o.code & 0xff, ak = (o.code >> 8) & 0xff, bk = (o.code >> 16) & 0xff;
+        auto operand = [&](uint32_t kind, uint32_t v) -> std::string {
+            if (kind == VS_INTERMEDIATE) return v < slot_name.size() ? slot_name[v] : std::string("F::zero()");
+            return leaf(kind, v);
+        };
+        const std::string a = operand(ak, o.a);
+        std::string expr;
+        switch (op) {
+            case OP_ADD: expr = "add_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
+            case OP_SUB: expr = "sub_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
+            case OP_MUL: expr = "mul_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
+            case OP_SQUARE: expr = "mul_lazy(" + a + ", " + a + ")"; break;
+            case OP_DOUBLE: expr = "dbl_lazy(" + a + ")"; break;
+            case OP_NEGATE: expr = "neg_lazy(" + a + ")"; break;
+            default: expr = a; break;  // OP_STORE
+        }
+        snprintf(buf, sizeof(buf), "v%zu", i);
+        const std::string name = buf;
+        s += "    const F " + name + " = " + expr + ";\n";
+        if (o.dst >= slot_name.size()) slot_name.resize(o.dst + 1);
+        slot_name[o.dst] = name;
+        last = name;
+    }
+    s += "    exch[r_in * m + t] = " + last + ";\n  }\n  __syncthreads();\n";
+    snprintf(buf, sizeof(buf),
+             "  if (live && t + 1u <= %uu) {\n    const uint32_t j = t + 1u;\n    F acc = F::zero();\n"
+             "    for (uint32_t q = 0; q < m; q++) acc = add_lazy(acc, mul_lazy(ld(A.vinv, j * m + q), exch[r_in * m + q]));\n"
+             "    st(A.out, (size_t)(j - 1u) * A.n + row, canon(acc));\n  }\n}\n", degree);
+    s += buf;
+    return s;
+}
+
+// source -> CUBIN for sm_100a; `log` receives the compiler's messages
+static int jit_compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& log) {
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, src.c_str(), "sb_ct.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+        log = "nvrtcCreateProgram failed";
+        return SB_ERR_CUDA;
+    }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v"};
+    const nvrtcResult r = nvrtcCompileProgram(prog, 4, opts);
+    size_t ls = 0;
+    nvrtcGetProgramLogSize(prog, &ls);
+    if (ls > 1) {
+        log.resize(ls);
+        nvrtcGetProgramLog(prog, &log[0]);
+    }
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return SB_ERR_CUDA;
+    }
+    size_t cs = 0;
+    nvrtcGetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    return SB_OK;
+}
+
+static int g_jit_on = []() {
+    const char* e = getenv("SB_EXPR_JIT");
+    return (!e || atoi(e) != 0) ? 1 : 0;
+}();
+static bool jit_enabled() { return g_jit_on != 0; }
+
+// the compiled kernel for (prog, degree, layout), built on first use; nullptr -> use the interpreter
+static sb_jit_entry* jit_lookup(sb_prog* prog, uint32_t degree, const sb_columns* cols, uint32_t nfv, uint32_t nch) {
+    if (!jit_enabled()) return nullptr;
+    for (sb_jit_entry* e : prog->jit)
+        if (e->degree == degree && e->num_selectors == cols->num_selectors && e->num_fixed == cols->num_fixed && e->nfv == nfv && e->nch == nch)
+            return e->ok ? e : nullptr;
+    sb_jit_entry* e = new (std::nothrow) sb_jit_entry();
+    if (!e) return nullptr;
+    *e = sb_jit_entry{degree, cols->num_selectors, cols->num_fixed, nfv, nch, nullptr, nullptr, false};
+    prog->jit.push_back(e);
+    std::vector<char> cubin;
+    std::string log;
+    const std::string src = jit_source(prog->field, prog->h_ops, prog->h_rotations, degree, cols->num_selectors, cols->num_fixed, nfv, nch);
+    if (jit_compile_cubin(src, cubin, log) != SB_OK) {
+        fprintf(stderr, "libsirius_b200: run-time compilation of the cross-term kernel failed, using the interpreter:\n%.2000s\n", log.c_str());
+        return nullptr;
+    }
+    if (cudaLibraryLoadData(&e->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+        cudaLibraryGetKernel(&e->fn, e->lib, "sb_ct") != cudaSuccess) {
+        cudaGetLastError();
+        fprintf(stderr, "libsirius_b200: loading the compiled cross-term kernel failed, using the interpreter\n");
+        return nullptr;
+    }
+    cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    e->ok = true;
+    return e;
+}
+
 template <class F>
 static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols, const void* const* h_adv1,
                                const void* const* h_adv2, size_t nfv, const uint64_t* ch1, const uint64_t* ch2,
@@ -505,6 +719,26 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
         set_error("expression needs %u live intermediates: too many for shared memory", prog->num_slots);
         return SB_ERR_ARG;
     }
+    if (sb_jit_entry* je = jit_lookup(prog, degree, cols, (uint32_t)nfv, (uint32_t)num_challenges)) {
+        JitArgs ja;
+        ja.fixed = A.cols.fixed;
+        ja.selectors = A.cols.selectors;
+        ja.adv1 = (const void* const*)A.adv1;
+        ja.adv2 = (const void* const*)A.adv2;
+        ja.constants = A.constants;
+        ja.challenges = A.challenges;
+        ja.vinv = prog->d_vinv;
+        ja.out = d_out;
+        ja.n = n;
+        ja.rows_per_block = 128u / m;
+        if (ja.rows_per_block > n) ja.rows_per_block = n;
+        void* kargs[1] = {&ja};
+        const unsigned jblocks = (n + ja.rows_per_block - 1) / ja.rows_per_block;
+        ProfScope ps(st, PROF_CROSS_TERMS, n);
+        SB_CUDA_TRY(cudaLaunchKernel((const void*)je->fn, dim3(jblocks), dim3(128), kargs, (size_t)ja.rows_per_block * m * 32, st));
+        count_launch();
+        return SB_OK;
+    }
     SB_CUDA_TRY(cudaFuncSetAttribute(k_cross_terms<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
         ProfScope ps(st, PROF_CROSS_TERMS, n);
@@ -543,17 +777,23 @@ static int fold_var_location(size_t index, size_t num_advice, size_t num_lookup,
 
 extern "C" {
 
-int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint64_t* constants_mont, size_t n_constants,
-                    const int32_t* rotations, size_t n_rotations, sb_prog_t* out) {
-    if (!out || (!calcs && n_calcs) || (!constants_mont && n_constants) || (!rotations && n_rotations)) {
-        set_error("sb_expr_compile: null argument");
-        return SB_ERR_ARG;
-    }
+}  // extern "C"
+
+namespace sb {
+
+// host-only half of sb_expr_compile: validation, aliasing of leaf `Store`s, liveness-based slot assignment
+struct Lowered {
+    std::vector<DevOp> ops;
+    uint32_t num_slots = 0, result_slot = 0, max_challenge = 0;
+    bool uses_challenge = false;
+    std::vector<uint32_t> poly_indices, fixed_indices;
+};
+
+static int lower_program(int field, const sb_calc* calcs, size_t n_calcs, size_t n_constants, size_t n_rotations, Lowered& L) {
     if (field != FIELD_FR && field != FIELD_FQ) {
         set_error("sb_expr_compile: unknown field %d", field);
         return SB_ERR_ARG;
     }
-    SB_TRY(ensure_runtime());
     // liveness: last reader of every intermediate
     std::vector<long> last_use(n_calcs, -1);
     std::vector<long> def_of(n_calcs, -1);  // target -> defining calc
@@ -626,22 +866,17 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
     std::vector<uint32_t> slot_of(n_calcs, 0);
     std::vector<uint32_t> free_slots;
     uint32_t num_slots = 0;
-    std::vector<DevOp> ops;
-    ops.reserve(n_calcs);
-    sb_prog* p = new (std::nothrow) sb_prog();
-    if (!p) return SB_ERR_OOM;
-    p->max_challenge = 0;
-    p->uses_challenge = false;
+    L.ops.reserve(n_calcs);
     auto enc = [&](const Src& v) -> uint32_t {
         if (v.kind == VS_INTERMEDIATE) return slot_of[v.index];
         if (v.kind == VS_POLY || v.kind == VS_FIXED) {
-            if (v.kind == VS_POLY) p->poly_indices.push_back(v.index);
-            else p->fixed_indices.push_back(v.index);
+            if (v.kind == VS_POLY) L.poly_indices.push_back(v.index);
+            else L.fixed_indices.push_back(v.index);
             return v.index | (v.rot << 24);
         }
         if (v.kind == VS_CHALLENGE) {
-            p->uses_challenge = true;
-            if (v.index > p->max_challenge) p->max_challenge = v.index;
+            L.uses_challenge = true;
+            if (v.index > L.max_challenge) L.max_challenge = v.index;
         }
         return v.index;
     };
@@ -668,19 +903,46 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
         }
         slot_of[c.target] = sl;
         o.dst = sl;
-        ops.push_back(o);
+        L.ops.push_back(o);
         if (last_use[c.target] < 0) free_slots.push_back(sl);  // never read (dead value)
     }
-    const size_t n_ops = ops.size();
+    L.num_slots = num_slots;
+    L.result_slot = n_calcs ? slot_of[calcs[n_calcs - 1].target] : 0;
+    return SB_OK;
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint64_t* constants_mont, size_t n_constants,
+                    const int32_t* rotations, size_t n_rotations, sb_prog_t* out) {
+    if (!out || (!calcs && n_calcs) || (!constants_mont && n_constants) || (!rotations && n_rotations)) {
+        set_error("sb_expr_compile: null argument");
+        return SB_ERR_ARG;
+    }
+    Lowered L;
+    SB_TRY(lower_program(field, calcs, n_calcs, n_constants, n_rotations, L));
+    SB_TRY(ensure_runtime());
+    sb_prog* p = new (std::nothrow) sb_prog();
+    if (!p) return SB_ERR_OOM;
+    const size_t n_ops = L.ops.size();
     p->field = field;
     p->num_ops = (uint32_t)n_ops;
-    p->num_slots = num_slots;
-    p->result_slot = n_calcs ? slot_of[calcs[n_calcs - 1].target] : 0;
+    p->num_slots = L.num_slots;
+    p->result_slot = L.result_slot;
     p->num_constants = (uint32_t)n_constants;
     p->num_rotations = (uint32_t)n_rotations;
+    p->max_challenge = L.max_challenge;
+    p->uses_challenge = L.uses_challenge;
+    p->poly_indices = L.poly_indices;
+    p->fixed_indices = L.fixed_indices;
+    p->h_ops = L.ops;
+    p->h_rotations.assign(rotations, rotations + n_rotations);
     p->d_ops = p->d_constants = p->d_rotations = nullptr;
     p->vinv_degree = 0;
     p->d_vinv = nullptr;
+    const std::vector<DevOp>& ops = L.ops;
     Runtime& rt = runtime();
     RtLock lk(rt.mu);
     cudaError_t e = cudaMalloc(&p->d_ops, sizeof(DevOp) * (n_ops ? n_ops : 1));
@@ -699,12 +961,44 @@ int sb_expr_compile(int field, const sb_calc* calcs, size_t n_calcs, const uint6
     return SB_OK;
 }
 
+/* 1 (default): cross terms run on straight-line kernels compiled at run time; 0: on the interpreter.  Same results. */
+void sb_expr_jit_enable(int on) { g_jit_on = on ? 1 : 0; }
+
+/* Code generator + run-time compiler check that needs no device (NVRTC cross-compiles for sm_100a): lowers the calculation list,
+ * generates the straight-line cross-term kernel for (degree, column layout) and compiles it.  log (may be NULL) receives the
+ * compiler output incl. the ptxas resource line; *cubin_bytes the size of the image.  Used by the CPU tests. */
+int sb_expr_jit_selftest(int field, const sb_calc* calcs, size_t n_calcs, size_t n_constants, const int32_t* rotations, size_t n_rotations, uint32_t degree,
+                         uint32_t num_selectors, uint32_t num_fixed, uint32_t num_fold_vars, uint32_t num_challenges, char* log, size_t log_cap,
+                         size_t* cubin_bytes) {
+    if ((!calcs && n_calcs) || (!rotations && n_rotations) || degree < 1 || degree > (uint32_t)EXPR_MAX_DEGREE) {
+        set_error("sb_expr_jit_selftest: bad argument");
+        return SB_ERR_ARG;
+    }
+    Lowered L;
+    SB_TRY(lower_program(field, calcs, n_calcs, n_constants, n_rotations, L));
+    std::vector<int32_t> rots(rotations, rotations + n_rotations);
+    const std::string src = jit_source(field, L.ops, rots, degree, num_selectors, num_fixed, num_fold_vars, num_challenges);
+    std::vector<char> cubin;
+    std::string out;
+    const int rc = jit_compile_cubin(src, cubin, out);
+    if (log && log_cap) {
+        snprintf(log, log_cap, "%s", out.c_str());
+    }
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (rc != SB_OK) set_error("sb_expr_jit_selftest: NVRTC failed: %.400s", out.c_str());
+    return rc;
+}
+
 void sb_expr_free(sb_prog_t p) {
     if (!p) return;
     if (p->d_ops) cudaFree(p->d_ops);
     if (p->d_constants) cudaFree(p->d_constants);
     if (p->d_rotations) cudaFree(p->d_rotations);
     if (p->d_vinv) cudaFree(p->d_vinv);
+    for (sb_jit_entry* e : p->jit) {
+        if (e->lib) cudaLibraryUnload(e->lib);
+        delete e;
+    }
     delete p;
 }
 
