@@ -319,7 +319,8 @@ int sb_selftest_lazy(int field, const uint64_t* a, const uint64_t* b, size_t n, 
                      uint64_t* out_dbl, uint64_t* out_canon);
 
 /* run-time compiled cross-term kernels (csrc/expr.cu): generate + NVRTC-compile the straight-line kernel of a calculation list for
- * (degree, column layout) without a device; log receives the compiler output (ptxas resource usage) */
+ * (degree, column layout) without a device; log receives the compiler output (ptxas resource usage).  degree = 0 generates
+ * the plain per-row evaluation kernel (sb_expr_eval), degree = num_traces << 8 the Protogalaxy leaf kernel on a blend of traces */
 int sb_expr_jit_selftest(int field, const sb_calc* calcs, size_t n_calcs, size_t n_constants, const int32_t* rotations, size_t n_rotations, uint32_t degree,
                          uint32_t num_selectors, uint32_t num_fixed, uint32_t num_fold_vars, uint32_t num_challenges, char* log, size_t log_cap,
                          size_t* cubin_bytes);

@@ -365,6 +365,253 @@ static int validate_program(const sb_prog* prog, const sb_columns* cols, size_t 
     return SB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// straight-line cross-term kernels, compiled at run time (NVRTC)
+// ------------------------------------------------------------------------------------------------
+// The interpreter above pays, per calculation, a 16-byte op fetch, the decode, two operand-kind switches and a
+// shared-memory round trip of every intermediate (ncu: issue-active 25-31 %, i.e. latency-bound, not pipe-bound).
+// A compiled GraphEvaluator program is a fixed straight-line sequence, so for the cross terms (the hot use) the
+// library generates CUDA source for the program -- every calculation one statement on register-resident values,
+// every distinct leaf (column, rotation) loaded and blended ONCE -- compiles it with NVRTC for sm_100a and keeps
+// the kernel per (program, degree, column layout).  Same lazy-domain field operations (field.cuh is compiled in
+// verbatim), same evaluation points 0..d, same inverse Vandermonde: bit-identical outputs.  SB_EXPR_JIT=0 keeps
+// the interpreter (also the fallback if the run-time compiler is unavailable).
+struct JitArgs {
+    const void* const* fixed;
+    const uint8_t* const* selectors;
+    const void* const* adv1;
+    const void* const* adv2;
+    const void* constants;
+    const void* challenges;   // [(d+1)][num_challenges]
+    const void* vinv;         // [(d+1)][(d+1)]
+    void* out;                // [d][n]
+    uint32_t n, rows_per_block;
+};
+struct JitEvalArgs {          // plain evaluation (GraphEvaluator::evaluate per row), optionally on a Lagrange blend of traces
+    const void* const* fixed;
+    const uint8_t* const* selectors;
+    const void* const* adv1;
+    const void* const* adv2;
+    const void* constants;
+    const void* challenges;        // [evaluations][num_challenges]
+    const void* const* blend_cols; // [num_blend][num_fold_vars]
+    const void* blend_coef;        // [evaluations][num_blend]
+    void* out;                     // [n]
+    uint32_t n, t, row0_only;
+};
+
+}  // namespace sb
+
+struct sb_jit_entry {
+    uint32_t degree;        // cross terms: folding degree d (d + 1 evaluation points per row); 0: plain evaluation kernel
+    uint32_t num_blend;     // plain evaluation: traces blended per fold variable (Protogalaxy), 0 = none
+    uint32_t num_selectors, num_fixed, nfv, nch;
+    cudaLibrary_t lib;
+    cudaKernel_t fn;
+    bool ok;
+};
+
+namespace sb {
+
+static const char FIELD_SRC[] =
+#include "field_src.inc"
+    ;
+
+static std::string jit_source(int field, const std::vector<DevOp>& ops, const std::vector<int32_t>& rots, uint32_t degree, uint32_t num_sel,
+                              uint32_t num_fixed, uint32_t nfv, uint32_t nch, uint32_t num_blend = 0) {
+    const bool eval_mode = degree == 0;
+    std::string s;
+    s.reserve(1 << 16);
+    s += "typedef unsigned char uint8_t;\ntypedef unsigned short uint16_t;\ntypedef unsigned int uint32_t;\ntypedef unsigned long long uint64_t;\n"
+         "typedef signed char int8_t;\ntypedef short int16_t;\ntypedef int int32_t;\ntypedef long long int64_t;\n";
+    s += FIELD_SRC;
+    s += "\nusing namespace sb;\ntypedef ";
+    s += field == FIELD_FR ? "Fr" : "Fq";
+    s += " F;\n";
+    s += "struct JitArgs { const void* const* fixed; const uint8_t* const* selectors; const void* const* adv1; const void* const* adv2; const void* constants;\n"
+         "  const void* challenges; const void* vinv; void* out; uint32_t n, rows_per_block; };\n"
+         "__device__ __forceinline__ F ld(const void* p, uint32_t i) { F r; const uint4* s = reinterpret_cast<const uint4*>(p) + 2 * (size_t)i; uint4* d = reinterpret_cast<uint4*>(&r);\n"
+         "  d[0] = __ldg(s); d[1] = __ldg(s + 1); return r; }\n"
+         "__device__ __forceinline__ void st(void* p, size_t i, const F& v) { uint4* d = reinterpret_cast<uint4*>(p) + 2 * i; const uint4* s = reinterpret_cast<const uint4*>(&v); d[0] = s[0]; d[1] = s[1]; }\n";
+    s += "struct JitEvalArgs { const void* const* fixed; const uint8_t* const* selectors; const void* const* adv1; const void* const* adv2; const void* constants;\n"
+         "  const void* challenges; const void* const* blend_cols; const void* blend_coef; void* out; uint32_t n, t, row0_only; };\n";
+    const uint32_t m = degree + 1;
+    char buf[768];
+    if (eval_mode)
+        s += "extern \"C\" __global__ void __launch_bounds__(128) sb_ct(JitEvalArgs A) {\n"
+             "  const uint32_t out_row = blockIdx.x * blockDim.x + threadIdx.x, mask = A.n - 1u, t = A.t;\n  (void)mask; (void)t;\n"
+             "  if (out_row >= A.n) return;\n"
+             "  const uint32_t row = A.row0_only ? 0u : out_row;   // `index & 2^k` leaf addressing (src/plonk/mod.rs:714, SURVEY F4)\n  {\n";
+    else {
+    snprintf(buf, sizeof(buf),
+             "extern \"C\" __global__ void __launch_bounds__(128) sb_ct(JitArgs A) {\n"
+             "  extern __shared__ uint4 sm_[];\n  F* exch = reinterpret_cast<F*>(sm_);\n"
+             "  const uint32_t m = %uu, r_in = threadIdx.x / m, t = threadIdx.x - r_in * m;\n"
+             "  const uint32_t row = blockIdx.x * A.rows_per_block + r_in, mask = A.n - 1u;\n  (void)mask;\n"
+             "  const bool live = r_in < A.rows_per_block && row < A.n;\n  if (live) {\n", m);
+    s += buf;
+    }
+    // leaves are materialised at their first use
+    std::vector<std::string> leaf_keys, leaf_names;
+    auto leaf = [&](uint32_t kind, uint32_t v) -> std::string {
+        snprintf(buf, sizeof(buf), "%u:%u", kind, v);
+        const std::string key = buf;
+        for (size_t i = 0; i < leaf_keys.size(); i++)
+            if (leaf_keys[i] == key) return leaf_names[i];
+        snprintf(buf, sizeof(buf), "l%zu", leaf_keys.size());
+        const std::string name = buf;
+        std::string def;
+        if (kind == VS_CONSTANT) {
+            snprintf(buf, sizeof(buf), "    const F %s = ld(A.constants, %uu);\n", name.c_str(), v);
+            def = buf;
+        } else if (kind == VS_CHALLENGE) {
+            snprintf(buf, sizeof(buf), "    const F %s = ld(A.challenges, t * %uu + %uu);\n", name.c_str(), nch, v);
+            def = buf;
+        } else {
+            const uint32_t index = v & 0xffffffu;
+            const int32_t rot = rots.empty() ? 0 : rots[v >> 24];
+            char rexpr[64];
+            if (rot == 0) snprintf(rexpr, sizeof(rexpr), "row");
+            else snprintf(rexpr, sizeof(rexpr), "((uint32_t)((int32_t)row + (%d)) & mask)", rot);   // get_rotation_idx, graph_evaluator.rs:51-53
+            if (kind == VS_FIXED) {
+                snprintf(buf, sizeof(buf), "    const F %s = ld(A.fixed[%u], %s);\n", name.c_str(), index, rexpr);
+                def = buf;
+            } else if (index < num_sel) {
+                snprintf(buf, sizeof(buf), "    const F %s = A.selectors[%u][%s] ? F::one() : F::zero();\n", name.c_str(), index, rexpr);
+                def = buf;
+            } else if (index < num_sel + num_fixed) {
+                snprintf(buf, sizeof(buf), "    const F %s = ld(A.fixed[%u], %s);\n", name.c_str(), index - num_sel, rexpr);
+                def = buf;
+            } else {
+                const uint32_t a = index - num_sel - num_fixed;
+                if (eval_mode && num_blend) {   // Lagrange blend of the traces (FoldedWitness::new, poly/folded_witness.rs:66-143), ONCE per leaf
+                    snprintf(buf, sizeof(buf), "    F %s = mul(ld(A.blend_coef, t * %uu), ld(A.blend_cols[%u], %s));\n", name.c_str(), num_blend, a, rexpr);
+                    def = buf;
+                    for (uint32_t j = 1; j < num_blend; j++) {
+                        snprintf(buf, sizeof(buf), "    %s = add(%s, mul(ld(A.blend_coef, t * %uu + %uu), ld(A.blend_cols[%u], %s)));\n", name.c_str(), name.c_str(), num_blend, j,
+                                 j * nfv + a, rexpr);
+                        def += buf;
+                    }
+                } else if (eval_mode && a < nfv) {
+                    snprintf(buf, sizeof(buf), "    const F %s = ld(A.adv1[%u], %s);\n", name.c_str(), a, rexpr);
+                    def = buf;
+                } else if (a >= nfv) {   // explicit second-instance variable
+                    snprintf(buf, sizeof(buf), "    const F %s = ld(A.adv2[%u], %s);\n", name.c_str(), a - nfv, rexpr);
+                    def = buf;
+                } else {          // w1 + t * w2 at this thread's evaluation point (PlonkEvalDomain::eval_advice_var with the folded instance)
+                    snprintf(buf, sizeof(buf), "    F %s = ld(A.adv1[%u], %s);\n    { const F w = ld(A.adv2[%u], %s); for (uint32_t k = 0; k < t; k++) %s = add(%s, w); }\n",
+                             name.c_str(), a, rexpr, a, rexpr, name.c_str(), name.c_str());
+                    def = buf;
+                }
+            }
+        }
+        s += def;
+        leaf_keys.push_back(key);
+        leaf_names.push_back(name);
+        return name;
+    };
+    std::vector<std::string> slot_name;   // current SSA name held by each slot
+    std::string last = "F::zero()";
+    for (size_t i = 0; i < ops.size(); i++) {
+        const DevOp& o = ops[i];
+        const uint32_t op = o.code & 0xff, ak = (o.code >> 8) & 0xff, bk = (o.code >> 16) & 0xff;
+        auto operand = [&](uint32_t kind, uint32_t v) -> std::string {
+            if (kind == VS_INTERMEDIATE) return v < slot_name.size() ? slot_name[v] : std::string("F::zero()");
+            return leaf(kind, v);
+        };
+        const std::string a = operand(ak, o.a);
+        std::string expr;
+        switch (op) {
+            case OP_ADD: expr = "add_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
+            case OP_SUB: expr = "sub_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
+            case OP_MUL: expr = "mul_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
+            case OP_SQUARE: expr = "mul_lazy(" + a + ", " + a + ")"; break;
+            case OP_DOUBLE: expr = "dbl_lazy(" + a + ")"; break;
+            case OP_NEGATE: expr = "neg_lazy(" + a + ")"; break;
+            default: expr = a; break;  // OP_STORE
+        }
+        snprintf(buf, sizeof(buf), "v%zu", i);
+        const std::string name = buf;
+        s += "    const F " + name + " = " + expr + ";\n";
+        if (o.dst >= slot_name.size()) slot_name.resize(o.dst + 1);
+        slot_name[o.dst] = name;
+        last = name;
+    }
+    if (eval_mode) {
+        s += "    st(A.out, out_row, canon(" + last + "));\n  }\n}\n";
+        return s;
+    }
+    s += "    exch[r_in * m + t] = " + last + ";\n  }\n  __syncthreads();\n";
+    snprintf(buf, sizeof(buf),
+             "  if (live && t + 1u <= %uu) {\n    const uint32_t j = t + 1u;\n    F acc = F::zero();\n"
+             "    for (uint32_t q = 0; q < m; q++) acc = add_lazy(acc, mul_lazy(ld(A.vinv, j * m + q), exch[r_in * m + q]));\n"
+             "    st(A.out, (size_t)(j - 1u) * A.n + row, canon(acc));\n  }\n}\n", degree);
+    s += buf;
+    return s;
+}
+
+// source -> CUBIN for sm_100a; `log` receives the compiler's messages
+static int jit_compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& log) {
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, src.c_str(), "sb_ct.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+        log = "nvrtcCreateProgram failed";
+        return SB_ERR_CUDA;
+    }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v"};
+    const nvrtcResult r = nvrtcCompileProgram(prog, 4, opts);
+    size_t ls = 0;
+    nvrtcGetProgramLogSize(prog, &ls);
+    if (ls > 1) {
+        log.resize(ls);
+        nvrtcGetProgramLog(prog, &log[0]);
+    }
+    if (r != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        return SB_ERR_CUDA;
+    }
+    size_t cs = 0;
+    nvrtcGetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    return SB_OK;
+}
+
+static int g_jit_on = []() {
+    const char* e = getenv("SB_EXPR_JIT");
+    return (!e || atoi(e) != 0) ? 1 : 0;
+}();
+static bool jit_enabled() { return g_jit_on != 0; }
+
+// the compiled kernel for (prog, degree, layout), built on first use; nullptr -> use the interpreter
+static sb_jit_entry* jit_lookup(sb_prog* prog, uint32_t degree, const sb_columns* cols, uint32_t nfv, uint32_t nch, uint32_t num_blend = 0) {
+    if (!jit_enabled()) return nullptr;
+    for (sb_jit_entry* e : prog->jit)
+        if (e->degree == degree && e->num_blend == num_blend && e->num_selectors == cols->num_selectors && e->num_fixed == cols->num_fixed && e->nfv == nfv &&
+            e->nch == nch)
+            return e->ok ? e : nullptr;
+    sb_jit_entry* e = new (std::nothrow) sb_jit_entry();
+    if (!e) return nullptr;
+    *e = sb_jit_entry{degree, num_blend, cols->num_selectors, cols->num_fixed, nfv, nch, nullptr, nullptr, false};
+    prog->jit.push_back(e);
+    std::vector<char> cubin;
+    std::string log;
+    const std::string src = jit_source(prog->field, prog->h_ops, prog->h_rotations, degree, cols->num_selectors, cols->num_fixed, nfv, nch, num_blend);
+    if (jit_compile_cubin(src, cubin, log) != SB_OK) {
+        fprintf(stderr, "libsirius_b200: run-time compilation of the cross-term kernel failed, using the interpreter:\n%.2000s\n", log.c_str());
+        return nullptr;
+    }
+    if (cudaLibraryLoadData(&e->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+        cudaLibraryGetKernel(&e->fn, e->lib, "sb_ct") != cudaSuccess) {
+        cudaGetLastError();
+        fprintf(stderr, "libsirius_b200: loading the compiled cross-term kernel failed, using the interpreter\n");
+        return nullptr;
+    }
+    cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    e->ok = true;
+    return e;
+}
+
 template <class F>
 static int eval_enqueue(sb_prog* prog, sb_columns* cols, const void* const* h_adv1, const void* const* h_adv2, size_t nfv,
                         const uint64_t* challenges, size_t num_challenges, void* d_out, cudaStream_t st) {
@@ -386,6 +633,25 @@ static int eval_enqueue(sb_prog* prog, sb_columns* cols, const void* const* h_ad
     A.num_challenges = (uint32_t)num_challenges;
     const uint32_t n = 1u << cols->log_rows;
     const uint32_t threads = n < (uint32_t)EXPR_THREADS ? n : EXPR_THREADS;
+    if (sb_jit_entry* je = jit_lookup(prog, 0, cols, (uint32_t)nfv, (uint32_t)num_challenges, 0)) {
+        JitEvalArgs ja;
+        ja.fixed = A.cols.fixed;
+        ja.selectors = A.cols.selectors;
+        ja.adv1 = (const void* const*)A.adv1;
+        ja.adv2 = (const void* const*)A.adv2;
+        ja.constants = A.constants;
+        ja.challenges = A.challenges;
+        ja.blend_cols = nullptr;
+        ja.blend_coef = nullptr;
+        ja.out = d_out;
+        ja.n = n;
+        ja.t = 0;
+        ja.row0_only = 0;
+        void* kargs[1] = {&ja};
+        SB_CUDA_TRY(cudaLaunchKernel((const void*)je->fn, dim3((n + threads - 1) / threads), dim3(threads), kargs, 0, st));
+        count_launch();
+        return SB_OK;
+    }
     const size_t smem = (size_t)(prog->num_slots ? prog->num_slots : 1) * 32 * threads;
     if (smem > 200 * 1024) {
         set_error("expression needs %u live intermediates: too many for shared memory", prog->num_slots);
@@ -436,6 +702,27 @@ static int pg_leaves_enqueue(sb_prog* const* gates, size_t num_gates, sb_columns
         A.blend_cols = (const F* const*)d;
         A.blend_coef = (const F*)(d + ptr_bytes);
         const uint32_t threads = n < (uint32_t)EXPR_THREADS ? n : EXPR_THREADS;
+        if (sb_jit_entry* je = jit_lookup(prog, 0, cols, (uint32_t)nfv, (uint32_t)num_challenges, (uint32_t)num_traces)) {
+            for (size_t b = 0; b < num_blends; b++) {
+                JitEvalArgs ja;
+                ja.fixed = A.cols.fixed;
+                ja.selectors = A.cols.selectors;
+                ja.adv1 = nullptr;
+                ja.adv2 = nullptr;
+                ja.constants = A.constants;
+                ja.challenges = A.challenges;
+                ja.blend_cols = (const void* const*)A.blend_cols;
+                ja.blend_coef = A.blend_coef;
+                ja.out = (F*)d_leaves + b * leaves + g * (size_t)n;
+                ja.n = n;
+                ja.t = (uint32_t)b;
+                ja.row0_only = row_mode_compat ? 1u : 0u;
+                void* kargs[1] = {&ja};
+                SB_CUDA_TRY(cudaLaunchKernel((const void*)je->fn, dim3((n + threads - 1) / threads), dim3(threads), kargs, 0, st));
+                count_launch();
+            }
+            continue;
+        }
         const size_t smem = (size_t)(prog->num_slots ? prog->num_slots : 1) * 32 * threads;
         if (smem > 200 * 1024) {
             set_error("expression needs %u live intermediates: too many for shared memory", prog->num_slots);
@@ -449,213 +736,6 @@ static int pg_leaves_enqueue(sb_prog* const* gates, size_t num_gates, sb_columns
         }
     }
     return SB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// straight-line cross-term kernels, compiled at run time (NVRTC)
-// ------------------------------------------------------------------------------------------------
-// The interpreter above pays, per calculation, a 16-byte op fetch, the decode, two operand-kind switches and a
-// shared-memory round trip of every intermediate (ncu: issue-active 25-31 %, i.e. latency-bound, not pipe-bound).
-// A compiled GraphEvaluator program is a fixed straight-line sequence, so for the cross terms (the hot use) the
-// library generates CUDA source for the program -- every calculation one statement on register-resident values,
-// every distinct leaf (column, rotation) loaded and blended ONCE -- compiles it with NVRTC for sm_100a and keeps
-// the kernel per (program, degree, column layout).  Same lazy-domain field operations (field.cuh is compiled in
-// verbatim), same evaluation points 0..d, same inverse Vandermonde: bit-identical outputs.  SB_EXPR_JIT=0 keeps
-// the interpreter (also the fallback if the run-time compiler is unavailable).
-struct JitArgs {
-    const void* const* fixed;
-    const uint8_t* const* selectors;
-    const void* const* adv1;
-    const void* const* adv2;
-    const void* constants;
-    const void* challenges;   // [(d+1)][num_challenges]
-    const void* vinv;         // [(d+1)][(d+1)]
-    void* out;                // [d][n]
-    uint32_t n, rows_per_block;
-};
-
-}  // namespace sb
-
-struct sb_jit_entry {
-    uint32_t degree, num_selectors, num_fixed, nfv, nch;
-    cudaLibrary_t lib;
-    cudaKernel_t fn;
-    bool ok;
-};
-
-namespace sb {
-
-static const char FIELD_SRC[] =
-#include "field_src.inc"
-    ;
-
-static std::string jit_source(int field, const std::vector<DevOp>& ops, const std::vector<int32_t>& rots, uint32_t degree, uint32_t num_sel,
-                              uint32_t num_fixed, uint32_t nfv, uint32_t nch) {
-    std::string s;
-    s.reserve(1 << 16);
-    s += "typedef unsigned char uint8_t;\ntypedef unsigned short uint16_t;\ntypedef unsigned int uint32_t;\ntypedef unsigned long long uint64_t;\n"
-         "typedef signed char int8_t;\ntypedef short int16_t;\ntypedef int int32_t;\ntypedef long long int64_t;\n";
-    s += FIELD_SRC;
-    s += "\nusing namespace sb;\ntypedef ";
-    s += field == FIELD_FR ? "Fr" : "Fq";
-    s += " F;\n";
-    s += "struct JitArgs { const void* const* fixed; const uint8_t* const* selectors; const void* const* adv1; const void* const* adv2; const void* constants;\n"
-         "  const void* challenges; const void* vinv; void* out; uint32_t n, rows_per_block; };\n"
-         "__device__ __forceinline__ F ld(const void* p, uint32_t i) { F r; const uint4* s = reinterpret_cast<const uint4*>(p) + 2 * (size_t)i; uint4* d = reinterpret_cast<uint4*>(&r);\n"
-         "  d[0] = __ldg(s); d[1] = __ldg(s + 1); return r; }\n"
-         "__device__ __forceinline__ void st(void* p, size_t i, const F& v) { uint4* d = reinterpret_cast<uint4*>(p) + 2 * i; const uint4* s = reinterpret_cast<const uint4*>(&v); d[0] = s[0]; d[1] = s[1]; }\n";
-    const uint32_t m = degree + 1;
-    char buf[512];
-    snprintf(buf, sizeof(buf),
-             "extern \"C\" __global__ void __launch_bounds__(128) sb_ct(JitArgs A) {\n"
-             "  extern __shared__ uint4 sm_[];\n  F* exch = reinterpret_cast<F*>(sm_);\n"
-             "  const uint32_t m = %uu, r_in = threadIdx.x / m, t = threadIdx.x - r_in * m;\n"
-             "  const uint32_t row = blockIdx.x * A.rows_per_block + r_in, mask = A.n - 1u;\n  (void)mask;\n"
-             "  const bool live = r_in < A.rows_per_block && row < A.n;\n  if (live) {\n", m);
-    s += buf;
-    // leaves are materialised at their first use
-    std::vector<std::string> leaf_keys, leaf_names;
-    auto leaf = [&](uint32_t kind, uint32_t v) -> std::string {
-        snprintf(buf, sizeof(buf), "%u:%u", kind, v);
-        const std::string key = buf;
-        for (size_t i = 0; i < leaf_keys.size(); i++)
-            if (leaf_keys[i] == key) return leaf_names[i];
-        snprintf(buf, sizeof(buf), "l%zu", leaf_keys.size());
-        const std::string name = buf;
-        std::string def;
-        if (kind == VS_CONSTANT) {
-            snprintf(buf, sizeof(buf), "    const F %s = ld(A.constants, %uu);\n", name.c_str(), v);
-            def = buf;
-        } else if (kind == VS_CHALLENGE) {
-            snprintf(buf, sizeof(buf), "    const F %s = ld(A.challenges, t * %uu + %uu);\n", name.c_str(), nch, v);
-            def = buf;
-        } else {
-            const uint32_t index = v & 0xffffffu;
-            const int32_t rot = rots.empty() ? 0 : rots[v >> 24];
-            char rexpr[64];
-            if (rot == 0) snprintf(rexpr, sizeof(rexpr), "row");
-            else snprintf(rexpr, sizeof(rexpr), "((uint32_t)((int32_t)row + (%d)) & mask)", rot);   // get_rotation_idx, graph_evaluator.rs:51-53
-            if (kind == VS_FIXED) {
-                snprintf(buf, sizeof(buf), "    const F %s = ld(A.fixed[%u], %s);\n", name.c_str(), index, rexpr);
-                def = buf;
-            } else if (index < num_sel) {
-                snprintf(buf, sizeof(buf), "    const F %s = A.selectors[%u][%s] ? F::one() : F::zero();\n", name.c_str(), index, rexpr);
-                def = buf;
-            } else if (index < num_sel + num_fixed) {
-                snprintf(buf, sizeof(buf), "    const F %s = ld(A.fixed[%u], %s);\n", name.c_str(), index - num_sel, rexpr);
-                def = buf;
-            } else {
-                const uint32_t a = index - num_sel - num_fixed;
-                if (a >= nfv) {   // explicit second-instance variable
-                    snprintf(buf, sizeof(buf), "    const F %s = ld(A.adv2[%u], %s);\n", name.c_str(), a - nfv, rexpr);
-                    def = buf;
-                } else {          // w1 + t * w2 at this thread's evaluation point (PlonkEvalDomain::eval_advice_var with the folded instance)
-                    snprintf(buf, sizeof(buf), "    F %s = ld(A.adv1[%u], %s);\n    { const F w = ld(A.adv2[%u], %s); for (uint32_t k = 0; k < t; k++) %s = add(%s, w); }\n",
-                             name.c_str(), a, rexpr, a, rexpr, name.c_str(), name.c_str());
-                    def = buf;
-                }
-            }
-        }
-        s += def;
-        leaf_keys.push_back(key);
-        leaf_names.push_back(name);
-        return name;
-    };
-    std::vector<std::string> slot_name;   // current SSA name held by each slot
-    std::string last = "F::zero()";
-    for (size_t i = 0; i < ops.size(); i++) {
-        const DevOp& o = ops[i];
-        const uint32_t op = o.code & 0xff, ak = (o.code >> 8) & 0xff, bk = (o.code >> 16) & 0xff;
-        auto operand = [&](uint32_t kind, uint32_t v) -> std::string {
-            if (kind == VS_INTERMEDIATE) return v < slot_name.size() ? slot_name[v] : std::string("F::zero()");
-            return leaf(kind, v);
-        };
-        const std::string a = operand(ak, o.a);
-        std::string expr;
-        switch (op) {
-            case OP_ADD: expr = "add_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
-            case OP_SUB: expr = "sub_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
-            case OP_MUL: expr = "mul_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
-            case OP_SQUARE: expr = "mul_lazy(" + a + ", " + a + ")"; break;
-            case OP_DOUBLE: expr = "dbl_lazy(" + a + ")"; break;
-            case OP_NEGATE: expr = "neg_lazy(" + a + ")"; break;
-            default: expr = a; break;  // OP_STORE
-        }
-        snprintf(buf, sizeof(buf), "v%zu", i);
-        const std::string name = buf;
-        s += "    const F " + name + " = " + expr + ";\n";
-        if (o.dst >= slot_name.size()) slot_name.resize(o.dst + 1);
-        slot_name[o.dst] = name;
-        last = name;
-    }
-    s += "    exch[r_in * m + t] = " + last + ";\n  }\n  __syncthreads();\n";
-    snprintf(buf, sizeof(buf),
-             "  if (live && t + 1u <= %uu) {\n    const uint32_t j = t + 1u;\n    F acc = F::zero();\n"
-             "    for (uint32_t q = 0; q < m; q++) acc = add_lazy(acc, mul_lazy(ld(A.vinv, j * m + q), exch[r_in * m + q]));\n"
-             "    st(A.out, (size_t)(j - 1u) * A.n + row, canon(acc));\n  }\n}\n", degree);
-    s += buf;
-    return s;
-}
-
-// source -> CUBIN for sm_100a; `log` receives the compiler's messages
-static int jit_compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& log) {
-    nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, src.c_str(), "sb_ct.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
-        log = "nvrtcCreateProgram failed";
-        return SB_ERR_CUDA;
-    }
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v"};
-    const nvrtcResult r = nvrtcCompileProgram(prog, 4, opts);
-    size_t ls = 0;
-    nvrtcGetProgramLogSize(prog, &ls);
-    if (ls > 1) {
-        log.resize(ls);
-        nvrtcGetProgramLog(prog, &log[0]);
-    }
-    if (r != NVRTC_SUCCESS) {
-        nvrtcDestroyProgram(&prog);
-        return SB_ERR_CUDA;
-    }
-    size_t cs = 0;
-    nvrtcGetCUBINSize(prog, &cs);
-    cubin.resize(cs);
-    nvrtcGetCUBIN(prog, cubin.data());
-    nvrtcDestroyProgram(&prog);
-    return SB_OK;
-}
-
-static int g_jit_on = []() {
-    const char* e = getenv("SB_EXPR_JIT");
-    return (!e || atoi(e) != 0) ? 1 : 0;
-}();
-static bool jit_enabled() { return g_jit_on != 0; }
-
-// the compiled kernel for (prog, degree, layout), built on first use; nullptr -> use the interpreter
-static sb_jit_entry* jit_lookup(sb_prog* prog, uint32_t degree, const sb_columns* cols, uint32_t nfv, uint32_t nch) {
-    if (!jit_enabled()) return nullptr;
-    for (sb_jit_entry* e : prog->jit)
-        if (e->degree == degree && e->num_selectors == cols->num_selectors && e->num_fixed == cols->num_fixed && e->nfv == nfv && e->nch == nch)
-            return e->ok ? e : nullptr;
-    sb_jit_entry* e = new (std::nothrow) sb_jit_entry();
-    if (!e) return nullptr;
-    *e = sb_jit_entry{degree, cols->num_selectors, cols->num_fixed, nfv, nch, nullptr, nullptr, false};
-    prog->jit.push_back(e);
-    std::vector<char> cubin;
-    std::string log;
-    const std::string src = jit_source(prog->field, prog->h_ops, prog->h_rotations, degree, cols->num_selectors, cols->num_fixed, nfv, nch);
-    if (jit_compile_cubin(src, cubin, log) != SB_OK) {
-        fprintf(stderr, "libsirius_b200: run-time compilation of the cross-term kernel failed, using the interpreter:\n%.2000s\n", log.c_str());
-        return nullptr;
-    }
-    if (cudaLibraryLoadData(&e->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
-        cudaLibraryGetKernel(&e->fn, e->lib, "sb_ct") != cudaSuccess) {
-        cudaGetLastError();
-        fprintf(stderr, "libsirius_b200: loading the compiled cross-term kernel failed, using the interpreter\n");
-        return nullptr;
-    }
-    cudaFuncSetAttribute((const void*)e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    e->ok = true;
-    return e;
 }
 
 template <class F>
@@ -970,14 +1050,19 @@ void sb_expr_jit_enable(int on) { g_jit_on = on ? 1 : 0; }
 int sb_expr_jit_selftest(int field, const sb_calc* calcs, size_t n_calcs, size_t n_constants, const int32_t* rotations, size_t n_rotations, uint32_t degree,
                          uint32_t num_selectors, uint32_t num_fixed, uint32_t num_fold_vars, uint32_t num_challenges, char* log, size_t log_cap,
                          size_t* cubin_bytes) {
-    if ((!calcs && n_calcs) || (!rotations && n_rotations) || degree < 1 || degree > (uint32_t)EXPR_MAX_DEGREE) {
+    uint32_t num_blend = 0;
+    if (degree >= 0x100u) {   // plain-evaluation kernel on a blend of (degree >> 8) traces; degree & 0xff must be 0
+        num_blend = degree >> 8;
+        degree &= 0xffu;
+    }
+    if ((!calcs && n_calcs) || (!rotations && n_rotations) || degree > (uint32_t)EXPR_MAX_DEGREE) {
         set_error("sb_expr_jit_selftest: bad argument");
         return SB_ERR_ARG;
     }
     Lowered L;
     SB_TRY(lower_program(field, calcs, n_calcs, n_constants, n_rotations, L));
     std::vector<int32_t> rots(rotations, rotations + n_rotations);
-    const std::string src = jit_source(field, L.ops, rots, degree, num_selectors, num_fixed, num_fold_vars, num_challenges);
+    const std::string src = jit_source(field, L.ops, rots, degree, num_selectors, num_fixed, num_fold_vars, num_challenges, num_blend);
     std::vector<char> cubin;
     std::string out;
     const int rc = jit_compile_cubin(src, cubin, out);

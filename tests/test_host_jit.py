@@ -76,3 +76,17 @@ def test_bad_program_is_rejected_before_code_generation():
     rc = lib.sb_expr_jit_selftest(0, ctypes.cast(calcs, ctypes.c_void_p), 1, 3, rots.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 1, 2, 0, 1, 1, 0, None, 0, None)
     assert rc == _lib.SB_ERR_ARG
     assert b"Horner" in lib.sb_last_error()
+
+
+@pytest.mark.parametrize("num_blend", [0, 2, 4])
+def test_plain_and_blended_evaluation_kernels_compile(num_blend):
+    """degree 0: the per-row evaluation kernel of sb_expr_eval (deciders); num_blend traces: the Protogalaxy leaf kernel that
+    evaluates a gate on the Lagrange blend of the traces (each leaf blended once)."""
+    from sirius_b200 import fft
+    from sirius_b200 import polynomial as P
+
+    gate = P.main_gate_expression(5, 0, 0, 0, 15)
+    ev = P.GraphEvaluator.new(gate, fft.FR_MODULUS)
+    rc, nbytes, log = _compile(0, ev, num_blend << 8, 0, 15, 7, 0)
+    assert rc == 0, log
+    assert nbytes > 1000 and "0 bytes spill stores" in log
