@@ -60,6 +60,10 @@ def workload_config(n_gpus, k):
         "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks; per commitment group ONE kernel exchanges the 128-byte partial sums over NVLink peer "
                                                       f"memory and adds them ({os.environ.get('SB_BENCH_EXCHANGE', 'peer')} exchange)",
         "l2": "inputs larger than L2 (window tables of several GB gathered at random; 0.4 GB of per-step scratch at k=17)",
+        "phases": ("sequential: one host synchronisation per commitment group (reference call order)" if os.environ.get("SB_BENCH_OVERLAP", "1") == "0"
+                   or os.environ.get("SB_BENCH_EXCHANGE", "peer") == "nccl" and n_gpus > 1 else
+                   "two per step (secondary trace, primary trace): the trace's W commitment on a second stream beside its cross terms + T commitments, "
+                   "one host synchronisation per phase (sirius_b200/workload.py step())"),
     }
 
 

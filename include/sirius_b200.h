@@ -193,6 +193,15 @@ int sb_cross_terms(sb_prog_t prog, uint32_t degree, sb_columns_t cols, uint32_t 
 int sb_cross_terms_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, const void* const* d_adv1_cols,
                           const void* const* d_adv2_cols, size_t num_fold_vars, const uint64_t* challenges1,
                           const uint64_t* challenges2, size_t num_challenges, void* d_out, void* stream);
+/* The same evaluation restricted to rows [row_begin, row_begin + row_count) of the table (output positions
+ * d_out[(j-1) * 2^log_rows + row] as in the full call; the other rows of d_out are not touched).  For callers that
+ * stream the fresh witness columns to the device in row blocks and evaluate a block while the next one is in flight
+ * (the rows of a fused cross-term sweep are independent: src/nifs/sangria/mod.rs:126-147 iterates row by row).
+ * Fails with SB_ERR_ARG if the expression queries a rotated row. */
+int sb_cross_terms_rows_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, const void* const* d_adv1_cols,
+                               const void* const* d_adv2_cols, size_t num_fold_vars, const uint64_t* challenges1,
+                               const uint64_t* challenges2, size_t num_challenges, size_t row_begin, size_t row_count,
+                               void* d_out, void* stream);
 
 void sb_expr_jit_enable(int on);
 
@@ -287,6 +296,13 @@ int sb_sparse_mismatch_device(sb_sparse_t m, const uint64_t* head, size_t head_l
  * be NULL) receives the total; SB_ERR_ARG if it exceeds out_capacity (cells). */
 int sb_concat_pad_device(const uint64_t* const* columns, const size_t* lens, size_t num_columns, size_t pad_size, void* d_out,
                          size_t out_capacity, size_t* out_len, void* stream);
+
+/* Rows [row_begin, row_begin + row_count) of every column of a column-major witness round ([num_columns][column_len]
+ * cells, the layout concatenate_with_padding produces) host -> device, as ONE strided asynchronous copy into the same
+ * positions of the device round vector.  With page-locked host memory a caller streams the fresh witness in row blocks
+ * and starts sb_cross_terms_rows_device on a block while the next one is in flight. */
+int sb_upload_rows_device(const uint64_t* columns, size_t num_columns, size_t column_len, size_t row_begin, size_t row_count,
+                          void* d_out, void* stream);
 
 /* ---- fft (src/fft.rs) ------------------------------------------------------------------------------ */
 

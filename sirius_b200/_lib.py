@@ -64,6 +64,8 @@ SIGNATURES = {
     "sb_expr_eval_device": (ctypes.c_int, [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.c_size_t, u64p, ctypes.c_size_t, vp, vp]),
     "sb_cross_terms": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(u64p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, ctypes.POINTER(u64p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.POINTER(u64p)]),
     "sb_cross_terms_device": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, vp, vp]),
+    "sb_upload_rows_device": (ctypes.c_int, [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
+    "sb_cross_terms_rows_device": (ctypes.c_int, [vp, ctypes.c_uint32, vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
     "sb_axpy_fold": (ctypes.c_int, [ctypes.c_int, u64p, u64p, u64p, u64p, ctypes.c_size_t]),
     "sb_axpy_fold_device": (ctypes.c_int, [ctypes.c_int, vp, vp, u64p, vp, ctypes.c_size_t, vp]),
     "sb_error_fold": (ctypes.c_int, [ctypes.c_int, u64p, ctypes.POINTER(u64p), ctypes.c_uint32, u64p, u64p, ctypes.c_size_t]),

@@ -194,13 +194,14 @@ k_expr_eval(EvalArgs<F> A, uint32_t t, int row0_only, F* __restrict__ out) {
 // read the same address).
 template <class F>
 __global__ void __launch_bounds__(EXPR_THREADS)
-k_cross_terms(EvalArgs<F> A, uint32_t degree, uint32_t rows_per_block, const F* __restrict__ vinv, F* __restrict__ out) {
+k_cross_terms(EvalArgs<F> A, uint32_t degree, uint32_t rows_per_block, uint32_t row0, uint32_t row_end, const F* __restrict__ vinv,
+              F* __restrict__ out) {
     extern __shared__ uint4 sm[];
     const uint32_t n = 1u << A.cols.log_rows;
     const uint32_t m = degree + 1;
     const uint32_t r_in = threadIdx.x / m, t = threadIdx.x - r_in * m;
-    const uint32_t row = blockIdx.x * rows_per_block + r_in;
-    const bool live = r_in < rows_per_block && row < n;
+    const uint32_t row = row0 + blockIdx.x * rows_per_block + r_in;   // rows [row0, row_end) of the table
+    const bool live = r_in < rows_per_block && row < row_end;
     // exchange area behind the slot file: [rows_per_block][m] evaluations
     F* exch = reinterpret_cast<F*>(sm + (size_t)(A.num_slots ? A.num_slots : 1) * 2 * blockDim.x);
     if (live) {
@@ -385,7 +386,7 @@ struct JitArgs {
     const void* challenges;   // [(d+1)][num_challenges]
     const void* vinv;         // [(d+1)][(d+1)]
     void* out;                // [d][n]
-    uint32_t n, rows_per_block;
+    uint32_t n, rows_per_block, row0, row_end;   // this launch covers rows [row0, row_end)
 };
 struct JitEvalArgs {          // plain evaluation (GraphEvaluator::evaluate per row), optionally on a Lagrange blend of traces
     const void* const* fixed;
@@ -429,7 +430,7 @@ static std::string jit_source(int field, const std::vector<DevOp>& ops, const st
     s += field == FIELD_FR ? "Fr" : "Fq";
     s += " F;\n";
     s += "struct JitArgs { const void* const* fixed; const uint8_t* const* selectors; const void* const* adv1; const void* const* adv2; const void* constants;\n"
-         "  const void* challenges; const void* vinv; void* out; uint32_t n, rows_per_block; };\n"
+         "  const void* challenges; const void* vinv; void* out; uint32_t n, rows_per_block, row0, row_end; };\n"
          "__device__ __forceinline__ F ld(const void* p, uint32_t i) { F r; const uint4* s = reinterpret_cast<const uint4*>(p) + 2 * (size_t)i; uint4* d = reinterpret_cast<uint4*>(&r);\n"
          "  d[0] = __ldg(s); d[1] = __ldg(s + 1); return r; }\n"
          "__device__ __forceinline__ void st(void* p, size_t i, const F& v) { uint4* d = reinterpret_cast<uint4*>(p) + 2 * i; const uint4* s = reinterpret_cast<const uint4*>(&v); d[0] = s[0]; d[1] = s[1]; }\n";
@@ -447,8 +448,8 @@ static std::string jit_source(int field, const std::vector<DevOp>& ops, const st
              "extern \"C\" __global__ void __launch_bounds__(128) sb_ct(JitArgs A) {\n"
              "  extern __shared__ uint4 sm_[];\n  F* exch = reinterpret_cast<F*>(sm_);\n"
              "  const uint32_t m = %uu, r_in = threadIdx.x / m, t = threadIdx.x - r_in * m;\n"
-             "  const uint32_t row = blockIdx.x * A.rows_per_block + r_in, mask = A.n - 1u;\n  (void)mask;\n"
-             "  const bool live = r_in < A.rows_per_block && row < A.n;\n  if (live) {\n", m);
+             "  const uint32_t row = A.row0 + blockIdx.x * A.rows_per_block + r_in, mask = A.n - 1u;\n  (void)mask;\n"
+             "  const bool live = r_in < A.rows_per_block && row < A.row_end;\n  if (live) {\n", m);
     s += buf;
     }
     // leaves are materialised at their first use
@@ -741,7 +742,7 @@ static int pg_leaves_enqueue(sb_prog* const* gates, size_t num_gates, sb_columns
 template <class F>
 static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols, const void* const* h_adv1,
                                const void* const* h_adv2, size_t nfv, const uint64_t* ch1, const uint64_t* ch2,
-                               size_t num_challenges, void* d_out, cudaStream_t st) {
+                               size_t num_challenges, void* d_out, cudaStream_t st, size_t row_begin = 0, size_t row_count = ~(size_t)0) {
     if (degree < 1 || degree > (uint32_t)EXPR_MAX_DEGREE) {
         set_error("sb_cross_terms: degree %u out of range [1,%d]", degree, EXPR_MAX_DEGREE);
         return SB_ERR_ARG;
@@ -791,8 +792,15 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
     A.blend_cols = nullptr;
     A.blend_coef = nullptr;
     const uint32_t n = 1u << cols->log_rows;
+    if (row_count == ~(size_t)0) row_count = n - (row_begin < n ? row_begin : n);
+    if (row_begin > n || row_count > n - row_begin) {
+        set_error("sb_cross_terms: rows [%zu, %zu) outside the table of %u rows", row_begin, row_begin + row_count, n);
+        return SB_ERR_ARG;
+    }
+    if (!row_count) return SB_OK;
+    const uint32_t row0 = (uint32_t)row_begin, row_end = (uint32_t)(row_begin + row_count), nr = (uint32_t)row_count;
     uint32_t rows_per_block = (uint32_t)EXPR_THREADS / m;
-    if (rows_per_block > n) rows_per_block = n;
+    if (rows_per_block > nr) rows_per_block = nr;
     const uint32_t threads = (rows_per_block * m + 31) / 32 * 32;
     const size_t smem = (size_t)(prog->num_slots ? prog->num_slots : 1) * 32 * threads + (size_t)rows_per_block * m * 32;
     if (smem > 200 * 1024) {
@@ -811,18 +819,20 @@ static int cross_terms_enqueue(sb_prog* prog, uint32_t degree, sb_columns* cols,
         ja.out = d_out;
         ja.n = n;
         ja.rows_per_block = 128u / m;
-        if (ja.rows_per_block > n) ja.rows_per_block = n;
+        if (ja.rows_per_block > nr) ja.rows_per_block = nr;
+        ja.row0 = row0;
+        ja.row_end = row_end;
         void* kargs[1] = {&ja};
-        const unsigned jblocks = (n + ja.rows_per_block - 1) / ja.rows_per_block;
-        ProfScope ps(st, PROF_CROSS_TERMS, n);
+        const unsigned jblocks = (nr + ja.rows_per_block - 1) / ja.rows_per_block;
+        ProfScope ps(st, PROF_CROSS_TERMS, nr);
         SB_CUDA_TRY(cudaLaunchKernel((const void*)je->fn, dim3(jblocks), dim3(128), kargs, (size_t)ja.rows_per_block * m * 32, st));
         count_launch();
         return SB_OK;
     }
     SB_CUDA_TRY(cudaFuncSetAttribute(k_cross_terms<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     {
-        ProfScope ps(st, PROF_CROSS_TERMS, n);
-        k_cross_terms<F><<<(n + rows_per_block - 1) / rows_per_block, threads, smem, st>>>(A, degree, rows_per_block, (const F*)prog->d_vinv, (F*)d_out);
+        ProfScope ps(st, PROF_CROSS_TERMS, nr);
+        k_cross_terms<F><<<(nr + rows_per_block - 1) / rows_per_block, threads, smem, st>>>(A, degree, rows_per_block, row0, row_end, (const F*)prog->d_vinv, (F*)d_out);
         SB_KERNEL_CHECK();
     }
     return SB_OK;
@@ -1169,6 +1179,29 @@ int sb_cross_terms_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, co
     if (prog->field == FIELD_FR)
         return cross_terms_enqueue<Fr>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st);
     return cross_terms_enqueue<Fq>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st);
+}
+
+int sb_cross_terms_rows_device(sb_prog_t prog, uint32_t degree, sb_columns_t cols, const void* const* d_adv1_cols,
+                               const void* const* d_adv2_cols, size_t num_fold_vars, const uint64_t* challenges1,
+                               const uint64_t* challenges2, size_t num_challenges, size_t row_begin, size_t row_count, void* d_out, void* stream) {
+    if (!prog || !cols || !d_out || ((!d_adv1_cols || !d_adv2_cols) && num_fold_vars) || ((!challenges1 || !challenges2) && num_challenges)) {
+        set_error("sb_cross_terms_rows_device: null argument");
+        return SB_ERR_ARG;
+    }
+    for (int32_t r : prog->h_rotations)
+        if (r != 0) {   // a rotated query reads rows outside the range: the caller could not know which rows must be resident
+            set_error("sb_cross_terms_rows_device: the expression queries rotation %d; row ranges need row-local expressions", (int)r);
+            return SB_ERR_ARG;
+        }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    RtLock lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    if (prog->field == FIELD_FR)
+        return cross_terms_enqueue<Fr>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st, row_begin,
+                                       row_count);
+    return cross_terms_enqueue<Fq>(prog, degree, cols, d_adv1_cols, d_adv2_cols, num_fold_vars, challenges1, challenges2, num_challenges, d_out, st, row_begin,
+                                   row_count);
 }
 
 int sb_pg_leaves_device(sb_prog_t const* gates, size_t num_gates, sb_columns_t cols, const void* const* d_cols_tables,

@@ -578,6 +578,23 @@ int sb_concat_pad_device(const uint64_t* const* columns, const size_t* lens, siz
     return SB_OK;
 }
 
+int sb_upload_rows_device(const uint64_t* columns, size_t num_columns, size_t column_len, size_t row_begin, size_t row_count, void* d_out,
+                          void* stream) {
+    if (!num_columns || !row_count) return SB_OK;
+    if (!columns || !d_out || row_begin > column_len || row_count > column_len - row_begin) {
+        set_error("sb_upload_rows_device: bad argument (rows [%zu, %zu) of %zu)", row_begin, row_begin + row_count, column_len);
+        return SB_ERR_ARG;
+    }
+    SB_TRY(ensure_runtime());
+    Runtime& rt = runtime();
+    RtLock lk(rt.mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
+    // one strided copy: num_columns pieces of row_count cells, the same pitch (one column) on both sides
+    SB_CUDA_TRY(cudaMemcpy2DAsync((char*)d_out + row_begin * 32, column_len * 32, (const char*)columns + row_begin * 32, column_len * 32, row_count * 32,
+                                  num_columns, cudaMemcpyHostToDevice, st));
+    return SB_OK;
+}
+
 /* ---- host front ends: stage through the library workspace, block until the result is back ---------------- */
 
 int sb_lookup_multiplicity(int field, const uint64_t* l, size_t n_l, const uint64_t* t, size_t n_t, uint64_t* m) {

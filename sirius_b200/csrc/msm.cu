@@ -37,7 +37,9 @@ namespace sb {
 
 constexpr int LS_MIN_LOG = 4;   // sorted entries per accumulate chunk (one thread each): 2^4 .. 2^8, chosen per call
 constexpr int LS_MAX_LOG = 8;
-constexpr int FIX_SEQ = 32;     // buckets split in <= FIX_SEQ pieces are summed by one thread, larger ones by a block
+constexpr int FIX_SEQ = 6;      // buckets split in <= FIX_SEQ pieces are summed serially by their own lane in k_fixup[_coop] ..
+constexpr int FIX_TREE = 1024;  // .. up to FIX_TREE pieces by a cooperative block (k_fixup_tree: lane-strided runs + a 5-step lane tree) ..
+                                // .. and beyond that (all-equal scalars) by the 256-thread k_fixup_heavy
 constexpr int HEAVY_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;  // items per thread in the scan kernels
 constexpr int SCAN_THREADS = 256;
@@ -651,7 +653,7 @@ template <class F>
 __global__ void __launch_bounds__(128)
 k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>* __restrict__ buckets,
         const XYZZ<F>* __restrict__ PH, const XYZZ<F>* __restrict__ PT, uint32_t* __restrict__ heavy_count,
-        uint32_t* __restrict__ heavy_list) {
+        uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ tree_list) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= KB) return;
     const uint32_t o = offsets[b], o2 = offsets[b + 1];
@@ -662,8 +664,9 @@ k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>*
     const uint32_t t0 = o / LS;
     const uint32_t np = (o2 - 1) / LS - t0 + 1;
     if (np == 1) return;  // written by k_accumulate
-    if (np > (uint32_t)FIX_SEQ) {
-        heavy_list[atomicAdd(heavy_count, 1u)] = b;
+    if (np > (uint32_t)FIX_SEQ) {   // heavy_count[0]: buckets for k_fixup_heavy, heavy_count[1]: buckets for k_fixup_tree
+        if (np > (uint32_t)FIX_TREE) heavy_list[atomicAdd(heavy_count, 1u)] = b;
+        else tree_list[atomicAdd(heavy_count + 1, 1u)] = b;
         return;
     }
     XYZZ<F> acc = (o - t0 * LS) ? load_vec(PT + t0) : load_vec(PH + t0);
@@ -862,7 +865,7 @@ template <class F>
 __global__ void __launch_bounds__(COOP_THREADS)
 k_fixup_coop(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>* __restrict__ buckets,
              const XYZZ<F>* __restrict__ PH, const XYZZ<F>* __restrict__ PT, uint32_t* __restrict__ heavy_count,
-             uint32_t* __restrict__ heavy_list) {
+             uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ tree_list) {
     __shared__ CoopBuf sh;
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * 32u + (uint32_t)lane;
@@ -878,7 +881,10 @@ k_fixup_coop(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZ
             head_tail = (o - t0 * LS) != 0;
             if (np == 1) np = 0;   // written by k_accumulate
             else if (np > (uint32_t)FIX_SEQ) {
-                if (role == 0) heavy_list[atomicAdd(heavy_count, 1u)] = b;
+                if (role == 0) {
+                    if (np > (uint32_t)FIX_TREE) heavy_list[atomicAdd(heavy_count, 1u)] = b;
+                    else tree_list[atomicAdd(heavy_count + 1, 1u)] = b;
+                }
                 np = 0;
             }
         }
@@ -898,28 +904,89 @@ k_fixup_coop(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZ
     if (np && role == 0) store_vec(buckets + b, acc);
 }
 
-// row / column sums: one block per row or column, grid (R + C, batch)
+// Buckets split over FIX_SEQ < np <= FIX_TREE chunks (uniform scalars: the few buckets of the short top window, which
+// take n / 2^(top bits) entries each; witness-like scalars: the small-value buckets of window 0).  A cooperative block
+// takes TWO queued buckets, 16 logical lanes each: lane l adds pieces l, l + 16, .. (block-uniform trip count), then a
+// 4-step xor tree -- 4 + np / 16 dependent additions where the lane-per-bucket loop of k_fixup would need np - 1.
+// (A cooperative addition costs an SM ~2.7 us whatever the number of busy lanes -- a lone block already keeps the four
+// integer pipes issuing -- so the kernel's time is blocks / 148 x additions x 2.7 us: two buckets per block halve it.)
 template <class F>
 __global__ void __launch_bounds__(COOP_THREADS)
-k_rowcol_coop(const XYZZ<F>* __restrict__ buckets_all, int log_k, int lc, XYZZ<F>* __restrict__ vec_all) {
+k_fixup_tree(const uint32_t* __restrict__ offsets, uint32_t LS, XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ PH,
+             const XYZZ<F>* __restrict__ PT, const uint32_t* __restrict__ heavy_count, const uint32_t* __restrict__ tree_list) {
+    __shared__ CoopBuf sh;
+    const uint32_t lane = threadIdx.x & 31u, gl = lane & 15u, half = lane >> 4;
+    const uint32_t count = heavy_count[1];
+    for (uint32_t h0 = blockIdx.x * 2u; h0 < count; h0 += gridDim.x * 2u) {
+        const uint32_t h = h0 + half;
+        uint32_t b = 0, t0 = 0, np = 0;
+        bool head_is_tail = false;
+        if (h < count) {
+            b = tree_list[h];
+            const uint32_t o = offsets[b], o2 = offsets[b + 1];
+            t0 = o / LS;
+            np = (o2 - 1) / LS - t0 + 1;
+            head_is_tail = (o - t0 * LS) != 0;   // the bucket starts inside chunk t0: its first piece is PT[t0]
+        }
+        const uint32_t np_max = __reduce_max_sync(0xffffffffu, np);   // identical in the 4 warps (replicated data)
+        XYZZ<F> acc = XYZZ<F>::identity();
+        if (gl < np) acc = (gl == 0 && head_is_tail) ? load_vec(PT + t0) : load_vec(PH + t0 + gl);
+        XYZZ<F> q = XYZZ<F>::identity();
+        if (gl + 16u < np) q = load_vec(PH + t0 + gl + 16u);
+#pragma unroll 1
+        for (uint32_t p = 16u; p < np_max; p += 16u) {
+            XYZZ<F> q_next = XYZZ<F>::identity();   // the next piece is in flight while this one is added
+            if (p + 16u + gl < np) q_next = load_vec(PH + t0 + p + 16u + gl);
+            coop4_add(acc, q, sh);
+            q = q_next;
+        }
+#pragma unroll 1
+        for (int d = 8; d >= 1; d >>= 1) {
+            XYZZ<F> t = coop_shfl_xor(acc, d);
+            coop4_add(acc, t, sh);
+        }
+        if (threadIdx.x < 32u && gl == 0u && h < count) store_vec(buckets + b, acc);
+    }
+}
+
+// row / column sums.  A row (or column) of cnt buckets is summed by a GROUP of G logical lanes (G = 32, 16, 8 or 4, chosen
+// on the host): lane gl of the group adds entries gl, gl + G, .. serially, then a log2(G)-step xor tree.  A block holds
+// 32 / G rows, grid (ceil((R + C) / (32 / G)), batch).  One row per block (G = 32) is the shortest chain, but every
+// cooperative addition costs the same 14 warp-products whether 1 or 32 of its lanes do useful work (the xor tree is an
+// all-reduce): with the thousands of short rows of a batched commitment the kernel is bound by that throughput, and
+// narrower groups do the same sums with 2-3x fewer block-additions.
+template <class F>
+__global__ void __launch_bounds__(COOP_THREADS)
+k_rowcol_coop(const XYZZ<F>* __restrict__ buckets_all, int log_k, int lc, int log_g, XYZZ<F>* __restrict__ vec_all) {
     __shared__ CoopBuf sh;
     const uint32_t K = 1u << log_k, C = 1u << lc, R = K >> lc;
-    const uint32_t w = blockIdx.x;
-    const int lane = threadIdx.x & 31;
+    const uint32_t G = 1u << log_g, rows_per_block = 32u >> log_g;
+    const uint32_t lane = threadIdx.x & 31u, gl = lane & (G - 1u);
+    const uint32_t w = blockIdx.x * rows_per_block + (lane >> log_g);
     const XYZZ<F>* buckets = buckets_all + (size_t)blockIdx.y * K;
-    const bool row = w < R;
-    const uint32_t cnt = row ? C : R, per = (cnt + 31u) >> 5;
-    XYZZ<F> acc = XYZZ<F>::identity();
+    const bool live = w < R + C, row = w < R;
+    const uint32_t cnt = live ? (row ? C : R) : 0u;
+    const uint32_t per = ((R > C ? R : C) + G - 1u) >> log_g;   // block-uniform trip count
+    auto fetch = [&](uint32_t t) {
+        const uint32_t j = t * G + gl;
+        if (j >= cnt) return XYZZ<F>::identity();
+        return row ? load_vec(buckets + (size_t)w * C + j) : load_vec(buckets + (size_t)j * C + (w - R));
+    };
+    XYZZ<F> acc = fetch(0);
+    XYZZ<F> x = per > 1u ? fetch(1) : XYZZ<F>::identity();
 #pragma unroll 1
-    for (uint32_t t = 0; t < per; t++) {
-        const uint32_t j = t * 32u + (uint32_t)lane;
-        XYZZ<F> x = XYZZ<F>::identity();
-        if (j < cnt) x = row ? load_vec(buckets + (size_t)w * C + j) : load_vec(buckets + (size_t)j * C + (w - R));
-        if (t == 0) acc = x;
-        else coop4_add(acc, x, sh);
+    for (uint32_t t = 1; t < per; t++) {
+        XYZZ<F> x_next = XYZZ<F>::identity();   // the next entry is in flight while this one is added
+        if (t + 1u < per) x_next = fetch(t + 1u);
+        coop4_add(acc, x, sh);
+        x = x_next;
     }
-    acc = coop_lane_sum(acc, sh);
-    if (threadIdx.x == 0) store_vec(vec_all + (size_t)blockIdx.y * (R + C) + w, acc);
+#pragma unroll 1
+    for (uint32_t d = G >> 1; d >= 1u; d >>= 1) {
+        XYZZ<F> t = coop_shfl_xor(acc, (int)d);
+        coop4_add(acc, t, sh);
+    }
+    if (threadIdx.x < 32u && gl == 0u && live) store_vec(vec_all + (size_t)blockIdx.y * (R + C) + w, acc);
 }
 
 // grid (2, batch): blockIdx.x = 0 -> X = C * sum_r r * Row_r, 1 -> Y = sum_q (q + 1) * Col_q.
@@ -1184,7 +1251,7 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     p.off_parts = take(p.parts ? ((size_t)p.parts * 3 + 2) * 4 : 0);   // partition counts | cursors | offsets (+1)
     p.off_cursor = take(p.parts ? (size_t)p.KB * 4 : 0);
     p.off_out1 = take(p.parts ? p.nW * 8 : 0);
-    p.off_counts = take(((size_t)p.KB + 1) * 4);  // +1: heavy-bucket counter lives behind the counts (one memset)
+    p.off_counts = take(((size_t)p.KB + 2) * 4);  // +2: the heavy / tree bucket counters live behind the counts (one memset)
     p.off_offsets = take(((size_t)p.KB + 1) * 4 * (size_t)(p.rounds + 1));  // one row per round
     p.off_tiles = take((size_t)SCAN_MAX_TILES * 4 * (size_t)(p.rounds + 1));
     p.off_ekey = take((p.chunks + 1) * 4);  // chunk heads
@@ -1192,7 +1259,7 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
     p.off_buckets = take((size_t)p.KB * 128);
     p.off_ph = take(p.chunks * 128);
     p.off_pt = take(p.chunks * 128);
-    p.off_heavy = take((p.chunks / FIX_SEQ + 2) * 4);
+    p.off_heavy = take((p.chunks / 2 + 4) * 4 * 2);   // heavy list | tree list (a listed bucket spans > FIX_SEQ - 2 >= 2 whole chunks)
     {
         const int log_k = p.c - 1, lc = (log_k + 1) / 2;
         p.off_nodes_a = take((((size_t)1 << lc) + ((size_t)p.K >> lc)) * batch * 128);  // row + column sums
@@ -1227,6 +1294,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     auto* PH = (XYZZ<F>*)(ws + p.off_ph);
     auto* PT = (XYZZ<F>*)(ws + p.off_pt);
     auto* heavy_list = (uint32_t*)(ws + p.off_heavy);
+    uint32_t* tree_list = heavy_list + (p.chunks / 2 + 4);
     const uint32_t K = p.K, KB = p.KB;
     uint32_t* heavy_count = counts + KB;
 
@@ -1239,7 +1307,7 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     const unsigned part_blocks = (unsigned)((p.total + 256 * PART_SPT - 1) / (256 * PART_SPT));
     {
         ProfScope ps(st, PROF_DECOMPOSE, p.total);
-        SB_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)KB + 1) * 4, st));
+        SB_CUDA_TRY(cudaMemsetAsync(counts, 0, ((size_t)KB + 2) * 4, st));
         if (P) {
             SB_CUDA_TRY(cudaMemsetAsync(part_count, 0, (size_t)P * 2 * 4, st));
             SB_CUDA_TRY(cudaMemsetAsync(bucket_cursor, 0, (size_t)KB * 4, st));
@@ -1334,10 +1402,13 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
     }
     {
         ProfScope ps(st, PROF_FIXUP, KB);
-        // cooperative fix-up for few buckets (latency-bound, skewed top-window buckets); with many buckets the fix-up is
-        // throughput-bound and one plain lane per bucket wastes nothing (0.44 vs 0.63 ms per step at k = 17 on one GPU)
-        if (g_tail_mode && KB <= 32768u) k_fixup_coop<F><<<(KB + 31) / 32, COOP_THREADS, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
-        else k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
+        // one plain lane per bucket for the short runs (<= FIX_SEQ pieces: throughput-bound, and a cooperative addition
+        // costs an SM 2.6x the issue slots of a plain one), the cooperative tree for the long ones.  SB_MSM_TAIL=2 keeps
+        // the all-cooperative fix-up of small commits for A/B runs.
+        if (g_tail_mode == 2 && KB <= 32768u) k_fixup_coop<F><<<(KB + 31) / 32, COOP_THREADS, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list, tree_list);
+        else k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list, tree_list);
+        SB_KERNEL_CHECK();
+        k_fixup_tree<F><<<592, COOP_THREADS, 0, st>>>(off_final, p.chunk_len, buckets, PH, PT, heavy_count, tree_list);
         SB_KERNEL_CHECK();
         k_fixup_heavy<F><<<296, HEAVY_THREADS, 0, st>>>(off_final, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list);
         SB_KERNEL_CHECK();
@@ -1351,7 +1422,19 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         {
             ProfScope ps(st, PROF_REDUCE, KB);
             if (g_tail_mode) {
-                k_rowcol_coop<F><<<dim3(R + C, p.batch), COOP_THREADS, 0, st>>>(buckets, log_k, lc, vec);
+                // group width: the shortest estimated time.  A cooperative addition takes ~2.7 us and a lone block already
+                // keeps its SM's four integer pipes issuing, so blocks beyond one per SM queue up: time ~ ops x 2.7 us x
+                // max(1, blocks / SMs)  (measured: 768 blocks x 6 ops 84 us, 384 x 12 83 us, 192 x 10 ~50 us)
+                int log_g = 5;
+                double best_t = 0;
+                for (int lg = 5; lg >= 2; lg--) {
+                    const uint32_t G = 1u << lg, cmax = R > C ? R : C;
+                    const double ops = (double)((cmax + G - 1) / G - 1) + lg;
+                    const double blocks = (double)((R + C + (32u >> lg) - 1) / (32u >> lg)) * p.batch;
+                    const double t = ops * 2.7 * std::max(1.0, blocks / (double)(runtime().sm_count > 0 ? runtime().sm_count : 148));
+                    if (lg == 5 || t < best_t) { best_t = t; log_g = lg; }
+                }
+                k_rowcol_coop<F><<<dim3((R + C + (32u >> log_g) - 1) / (32u >> log_g), p.batch), COOP_THREADS, 0, st>>>(buckets, log_k, lc, log_g, vec);
                 SB_KERNEL_CHECK();
                 k_weighted_coop<F><<<dim3(2, p.batch), COOP_THREADS, 0, st>>>(vec, log_k, lc, xy);
                 SB_KERNEL_CHECK();

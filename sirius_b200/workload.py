@@ -95,8 +95,9 @@ def build_structure_key(side, k, rank, world, stream, windows, seed, key_cols=No
     selectors = [t.cpu().numpy() for t in d_sel]
     del d_fixed, d_sel
     S = SG.PlonkStructure(side["field"], modulus, k_loc, selectors, fixed, nadv, 0, cg, gates=gates)
+    rotations = P.GraphEvaluator.new(cg.homogeneous, modulus).rotations
     if world > 1:
-        sharding.check_rotations_row_local(P.GraphEvaluator.new(cg.homogeneous, modulus).rotations)
+        sharding.check_rotations_row_local(rotations)
     # commitment key restricted to this rank's rows: ck[col * n + row] for row in the slice, column-major
     # (the benches' key has 2^(k+4) generators, benches/sangria_poseidon.rs:26-30; only the prefix W needs is materialised)
     kc = key_cols or nadv
@@ -112,7 +113,7 @@ def build_structure_key(side, k, rank, world, stream, windows, seed, key_cols=No
         ck.add_window(wb, stream.cuda_stream)
     stream.synchronize()
     del d_bases
-    return S, ck, cg, dict(side=side, nadv=nadv, nfix=nfix, n_loc=n_loc, fixed=fixed, selectors=selectors)
+    return S, ck, cg, dict(side=side, nadv=nadv, nfix=nfix, n_loc=n_loc, fixed=fixed, selectors=selectors, row_local=all(int(r) == 0 for r in rotations))
 
 
 def build_sangria_side(side, k, rank, world, stream, windows, seed, key_cols=None):
@@ -187,6 +188,7 @@ class PeerCombiner:
         import torch
 
         self.rank, self.world, self.stream, self.torch = rank, world, stream, torch
+        self.alone = alone
         self.lib = _lib.load()
         self._h = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
@@ -206,17 +208,20 @@ class PeerCombiner:
         torch.cuda.synchronize()
         self.out = {}
 
-    def commit(self, ck: CommitmentKey, d_scalars: int, n: int, batch: int, h_out) -> None:
+    def commit(self, ck: CommitmentKey, d_scalars: int, n: int, batch: int, h_out, sync: bool = True) -> None:
+        """sync = False: enqueue only (pipeline + exchange + D2H of the result); the caller synchronises self.stream."""
         torch = self.torch
         if batch not in self.out:
             with torch.cuda.stream(self.stream):
                 self.out[batch] = torch.zeros((batch, 8), dtype=torch.int64, device="cuda")
+            self.stream.synchronize()
         out = self.out[batch]
         _lib.check(self.lib.sb_msm_batch_sharded_device(ck._h, self._h, ctypes.c_void_p(d_scalars), n, n, batch, ctypes.c_void_p(out.data_ptr()),
                                                         ctypes.c_void_p(self.stream.cuda_stream)))
         with torch.cuda.stream(self.stream):
             h_out.copy_(out.view(h_out.shape), non_blocking=True)
-        self.stream.synchronize()
+        if sync:
+            self.stream.synchronize()
 
     def status(self) -> int:
         return int(self.lib.sb_comm_status(self._h, ctypes.c_void_p(self.stream.cuda_stream)))
@@ -239,7 +244,8 @@ def make_combiner(rank, world, stream):
 class SangriaStepWorkload:
     """Both sides of the cycle, device-resident, restricted to this rank's rows."""
 
-    def __init__(self, k: int, rank: int = 0, world: int = 1, stream=None, windows: Optional[List[int]] = None, seed: int = SEED, combiner="auto"):
+    def __init__(self, k: int, rank: int = 0, world: int = 1, stream=None, windows: Optional[List[int]] = None, seed: int = SEED, combiner="auto",
+                 overlap: Optional[bool] = None):
         import torch
 
         self.torch = torch
@@ -254,6 +260,21 @@ class SangriaStepWorkload:
             self.sides.append(sess)
             self.extras.append(ex)
         self.combiner = make_combiner(rank, world, self.stream) if combiner == "auto" else combiner
+        # Two-stream phases (see step()): the trace commitment runs on a second, high-priority stream beside the cross terms and
+        # their commitments.  N > 1: that stream needs a communicator of its own (mailboxes and sequence numbers are per
+        # communicator); the NCCL library path (SB_BENCH_EXCHANGE=nccl) keeps the sequential phases.
+        if overlap is None:
+            overlap = os.environ.get("SB_BENCH_OVERLAP", "1") != "0"
+        self.overlap = overlap and (self.combiner is None or isinstance(self.combiner, PeerCombiner))
+        self.aux_stream, self.combiner_w, self._ev = None, None, None
+        self.upload_blocks = max(1, int(os.environ.get("SB_BENCH_UPLOAD_BLOCKS", "4")))
+        if self.overlap:
+            self.aux_stream = torch.cuda.Stream(priority=-1)
+            self.copy_stream = torch.cuda.Stream()
+            self._ev = torch.cuda.Event()
+            self._ev_blocks = [torch.cuda.Event() for _ in range(self.upload_blocks)]
+            if self.combiner is not None:
+                self.combiner_w = PeerCombiner(self.combiner.rank, self.combiner.world, self.aux_stream, alone=self.combiner.alone)
         self.stream.synchronize()
 
     # ------------------------------------------------------------------ construction
@@ -282,10 +303,77 @@ class SangriaStepWorkload:
             self.combiner.commit(sess.ck, sess.W_in.data_ptr(), sess.A * sess.n, 1, sess.h_commit_W)
         return h2d
 
+    def _trace_and_prove(self, sess, ex, upload) -> int:
+        """One trace's share of a fold step as ONE device phase with ONE host synchronisation: `generate_plonk_trace`'s
+        commitment of the fresh witness (src/plonk/mod.rs:441-445) on the second stream, beside `VanillaFS::prove` of the same
+        trace (cross terms + their commitments, src/nifs/sangria/mod.rs:102-158) on the main stream.  Both depend on the trace's
+        witness only; the random oracle needs the W commitment and the T commitments together, when it derives r
+        (src/nifs/sangria/mod.rs:162-179), and the circuits of this bench have a single witness round (no challenge is
+        squeezed between W and the cross terms).  What it buys: the latency tail of the W commitment (fix-up, row/column
+        sums, weighted sum, exchange, normalisation: a few SMs busy) runs under the full-chip kernels of the other stream
+        instead of alone, and a host round trip disappears."""
+        torch = self.torch
+        main, aux = self.stream, self.aux_stream
+        c1, c2 = sess.challenge_vectors(ex["c1"], ex["u1"], ex["c2"])
+        ct_args = (sess.S._hom_prog._h, sess.d, sess.S._cols, sess._cols(sess.W_acc), sess._cols(sess.W_in), sess.A,
+                   c1.ctypes.data_as(_lib.u64p), c2.ctypes.data_as(_lib.u64p), c1.shape[0])
+        nb = self.upload_blocks if (upload and ex["row_local"] and sess.n >= 1024 * self.upload_blocks) else 1
+        h2d = 0
+        if nb > 1:
+            # The fresh witness arrives in row blocks on a copy stream; the cross terms of a block (row-local: the gates
+            # query rotation 0 only) start as soon as it is resident, so the sweep runs under the rest of the transfer.
+            # The commitment of W needs every scalar (the digits are sorted by bucket): it waits for the last block.
+            copy, rows = self.copy_stream, sess.n // nb
+            self._ev.record(main)        # the previous readers of W_in (this side's fold of the last step) are on the main stream
+            copy.wait_event(self._ev)
+            host_W = ex["host_W"]
+            for b in range(nb):
+                _lib.check(self.lib.sb_upload_rows_device(ctypes.c_void_p(host_W.data_ptr()), sess.A, sess.n, b * rows, rows,
+                                                          ctypes.c_void_p(sess.W_in.data_ptr()), ctypes.c_void_p(copy.cuda_stream)))
+                self._ev_blocks[b].record(copy)
+            h2d = host_W.numel() * 8
+            for b in range(nb):
+                main.wait_event(self._ev_blocks[b])
+                _lib.check(self.lib.sb_cross_terms_rows_device(*ct_args, b * rows, rows, ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(main.cuda_stream)))
+            aux.wait_event(self._ev_blocks[nb - 1])
+        else:
+            if upload:
+                h2d = sess.upload_incoming(ex["host_W"])
+            self._ev.record(main)        # after the upload and after everything the previous phase left on the main stream
+            aux.wait_event(self._ev)
+        if self.combiner is None:
+            sess.ck.commit_device(sess.W_in.data_ptr(), sess.A * sess.n, sess.commit_W.data_ptr(), 0, aux.cuda_stream)
+            with torch.cuda.stream(aux):
+                sess.h_commit_W.copy_(sess.commit_W, non_blocking=True)
+        else:
+            self.combiner_w.commit(sess.ck, sess.W_in.data_ptr(), sess.A * sess.n, 1, sess.h_commit_W, sync=False)
+        if nb == 1:
+            _lib.check(self.lib.sb_cross_terms_device(*ct_args, ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(main.cuda_stream)))
+        if self.combiner is None:
+            sess.ck.commit_batch_device(sess.T.data_ptr(), sess.n, sess.n, sess.d, sess.commit_T.data_ptr(), 0, main.cuda_stream)
+            with torch.cuda.stream(main):
+                sess.h_commit_T.copy_(sess.commit_T, non_blocking=True)
+        else:
+            self.combiner.commit(sess.ck, sess.T.data_ptr(), sess.n, sess.d, sess.h_commit_T, sync=False)
+        aux.synchronize()
+        main.synchronize()               # W and T commitments are on the host: the random oracle derives r
+        sess.fold(ex["r"])
+        return h2d
+
     def step(self, upload: bool = False) -> int:
-        """One fold_step hot path.  Returns the bytes copied host -> device."""
+        """One fold_step hot path.  Returns the bytes copied host -> device.
+
+        Sequential form (SB_BENCH_OVERLAP=0, and the NCCL exchange): the reference's call order 1-4 of the module docstring,
+        one host synchronisation per commitment group.  Default form: two phases, secondary trace then primary trace, each
+        `_trace_and_prove`.  The work and every result are the same (tests/test_gpu_workload.py and bench.py's verification
+        compare both with the oracle); what moves is the commitment of the secondary trace, which the reference issues at
+        the end of fold_step i (call 4) and consumes in VanillaFS::prove at the start of fold_step i+1 (call 1): nothing
+        between the two depends on it, so the session issues call 4 of step i together with call 1 of step i+1 -- a timed
+        step is {4 of the previous step, 1, 2, 3}, the steady state of a run of fold steps."""
         prim, sec = self.sides
         ep, es = self.extras
+        if self.overlap:
+            return self._trace_and_prove(sec, es, upload) + self._trace_and_prove(prim, ep, upload)
         h2d = 0
         self._prove(sec, es)                     # 1. fold the secondary accumulator
         h2d += self._commit_w(prim, ep, upload)  # 2. primary trace: commit W
@@ -391,8 +479,12 @@ class SangriaStepWorkload:
         return res
 
     def close(self):
-        if self.combiner is not None and hasattr(self.combiner, "close"):
-            self.combiner.close()
+        for c in (self.combiner, self.combiner_w):
+            if c is not None and hasattr(c, "close"):
+                c.close()
+        if self.aux_stream is not None:
+            self.aux_stream.synchronize()
+            self.lib.sb_stream_release(ctypes.c_void_p(self.aux_stream.cuda_stream))   # the second stream's scratch
         for sess in self.sides:
             sess.S.close()
             sess.ck.close()

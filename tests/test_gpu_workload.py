@@ -12,13 +12,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _check_step(k, windows=None, steps=1):
+def _check_step(k, windows=None, steps=1, overlap=None):
     import torch
 
     from oracle import step_ref
     from sirius_b200 import workload as WL
 
-    wl = WL.SangriaStepWorkload(k, 0, 1, torch.cuda.Stream(), windows=windows)
+    wl = WL.SangriaStepWorkload(k, 0, 1, torch.cuda.Stream(), windows=windows, overlap=overlap)
+    assert wl.overlap == (overlap is not False)
     try:
         for i in range(steps):
             snap = wl.snapshot_inputs()
@@ -34,6 +35,14 @@ def _check_step(k, windows=None, steps=1):
 
 def test_fold_step_small_two_steps(oracle):
     _check_step(10, windows=[11, 8], steps=2)   # the second step folds the first step's accumulator
+
+
+def test_fold_step_small_sequential_phases(oracle):
+    _check_step(10, windows=[11, 8], steps=2, overlap=False)   # the reference's call order, one sync per commitment group
+
+
+def test_fold_step_two_stream_phases_repeat(oracle):
+    _check_step(12, windows=[12, 9], steps=4, overlap=True)    # W commit on the second stream beside cross terms + T commits
 
 
 def test_fold_step_bench_shapes_k17(oracle):
@@ -269,3 +278,55 @@ def test_in_library_multi_gpu_commit(oracle):
     s = O.random_field(0, 3, 1000)
     assert np.array_equal(ck.commit(s), O.msm(0, s, bases))
     ck.close()
+
+
+@pytest.mark.parametrize("jit", [1, 0])
+def test_cross_terms_row_blocks_equal_full_call(jit):
+    """sb_upload_rows_device + sb_cross_terms_rows_device over uneven row blocks == sb_cross_terms_device on the resident
+    witness (compiled and interpreted kernels), and an expression that queries a rotated row is refused."""
+    import ctypes
+
+    import torch
+
+    from sirius_b200 import _lib
+    from sirius_b200 import polynomial as P
+    from sirius_b200 import sangria as SG
+    from sirius_b200 import workload as WL
+
+    lib = _lib.load()
+    lib.sb_expr_jit_enable(jit)
+    st = torch.cuda.Stream()
+    try:
+        sess, ex = WL.build_sangria_side(WL.PRIMARY, 11, 0, 1, st, [10], WL.SEED)
+        n, A, d = sess.n, sess.A, sess.d
+        c1, c2 = sess.challenge_vectors(ex["c1"], ex["u1"], ex["c2"])
+        args = (sess.S._hom_prog._h, d, sess.S._cols, sess._cols(sess.W_acc), sess._cols(sess.W_in), A, c1.ctypes.data_as(_lib.u64p),
+                c2.ctypes.data_as(_lib.u64p), c1.shape[0])
+        _lib.check(lib.sb_cross_terms_device(*args, ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(st.cuda_stream)))
+        st.synchronize()
+        full = sess.T.cpu().numpy().copy()
+        with torch.cuda.stream(st):
+            sess.T.fill_(-1)
+            sess.W_in.zero_()
+        st.synchronize()
+        for r0, cnt in ((0, 1), (1, 700), (701, n - 701 - 3), (n - 3, 3), (5, 0)):
+            _lib.check(lib.sb_upload_rows_device(ctypes.c_void_p(ex["host_W"].data_ptr()), A, n, r0, cnt, ctypes.c_void_p(sess.W_in.data_ptr()),
+                                                 ctypes.c_void_p(st.cuda_stream)))
+            _lib.check(lib.sb_cross_terms_rows_device(*args, r0, cnt, ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(st.cuda_stream)))
+        st.synchronize()
+        assert np.array_equal(sess.W_in.cpu().numpy(), ex["host_W"].numpy())
+        assert np.array_equal(sess.T.cpu().numpy(), full)
+        assert lib.sb_cross_terms_rows_device(*args, n - 2, 3, ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(st.cuda_stream)) == _lib.SB_ERR_ARG
+        assert lib.sb_upload_rows_device(ctypes.c_void_p(ex["host_W"].data_ptr()), A, n, n, 1, ctypes.c_void_p(sess.W_in.data_ptr()),
+                                         ctypes.c_void_p(st.cuda_stream)) == _lib.SB_ERR_ARG
+        # a rotated query: row ranges are refused (the full call accepts it)
+        rot = SG.Program(sess.S.field, P.GraphEvaluator.new(P.Expression.Polynomial(ex["nfix"], 1), sess.S.modulus))
+        assert lib.sb_cross_terms_rows_device(rot._h, 1, sess.S._cols, sess._cols(sess.W_acc), sess._cols(sess.W_in), A, c1.ctypes.data_as(_lib.u64p),
+                                              c2.ctypes.data_as(_lib.u64p), c1.shape[0], 0, 8, ctypes.c_void_p(sess.T.data_ptr()),
+                                              ctypes.c_void_p(st.cuda_stream)) == _lib.SB_ERR_ARG
+        assert b"rotation" in lib.sb_last_error()
+        sess.S.close()
+        sess.ck.close()
+    finally:
+        lib.sb_expr_jit_enable(1)
+        lib.sb_stream_release(ctypes.c_void_p(st.cuda_stream))
