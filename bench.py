@@ -614,6 +614,133 @@ def _cyclefold_synthetic_inputs(k):
                 betas=[rng.randrange(M) for _ in range(k + 1)], delta=rng.randrange(M), alpha=rng.randrange(M), gamma=rng.randrange(M), support=sup)
 
 
+def run_gate_scaling(args):
+    """--workload gate_scaling: BASELINE config 5 (benches/ivc_gate_scaling.rs).  The reference scales the NUMBER of parallel
+    Poseidon sub-circuits (5 / 10 / 20 for sangria::IVC at k = 17, :221-223; 6 / 12 / 24 / 48 for cyclefold::IVC at k = 20,
+    :229-232); there is no degree knob.  Sangria arm: the same fold_step hot path as the main line with the primary
+    circuit widened to N sub-circuits (A = 7 + 5N, F = 15 + 11N, N + 1 gates, folding degree 5 + N: N + 5 cross terms and
+    commitments).  Cyclefold arm: ProtoGalaxy::prove (F, G, K, fold_witness) on the same shapes in the correct row mode.
+    The smallest cell of each arm is checked bit for bit against the CPU restatement before timing."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    k_s, k_pg = args.k, args.pg_k
+    sg_counts = [int(x) for x in args.gates.split(",") if x]
+    pg_counts = [int(x) for x in args.pg_gates.split(",") if x]
+    metric = "ivc_gate_scaling prover hot-path time vs gate count"
+    config = {"workload": f"benches/ivc_gate_scaling: sangria fold_step at k={k_s} for N={sg_counts} sub-circuits; ProtoGalaxy::prove at k={k_pg} for N={pg_counts}",
+              "k": k_s, "pg_k": k_pg, "sharding": "single GPU"}
+    if args.impl == "reference":
+        import oracle
+        from oracle import step_ref
+        from sirius_b200 import workload as WL
+
+        oracle.build()
+        N = sg_counts[0]
+        inp = step_ref.synthetic_inputs([WL.gate_scaling_side(N), WL.SECONDARY], k_s, SEED)
+        bases = step_ref.bases_for(inp)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_ref.fold_step(inp, bases, threads=cpu_threads())
+        ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        base = {"value": round(ms, 2), "unit": "ms", "cores": cpu_threads(), "kind": "port", "sample": f"full fold_step hot path at N={N} sub-circuits per step (CPU restatement)"}
+        print(json.dumps({"impl": "reference", "metric": metric, "value": round(ms, 2), "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": 0, "ms_per_step": round(ms, 2),
+                          "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u64 limbs (254-bit modular integers)", "data": "synthetic",
+                          "config": config, "cpu_baseline": base, "e2e": {"value": round(ms, 2), "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    arm = GpuArm(args)
+    torch = arm.torch
+    from sirius_b200 import workload as WL
+
+    sampler = ClockSampler(arm.local_rank)
+    sampler.start()
+    cells, cpu_base, verified = [], None, None
+
+    def release(wl):
+        wl.close()
+        import gc
+
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+    for i, N in enumerate(sg_counts):
+        side = WL.gate_scaling_side(N)
+        windows = [17, 15, 13] + ([20] if (7 + 5 * N) << k_s >= 1 << 23 else [])
+        t_build = time.perf_counter()
+        wl = WL.SangriaStepWorkload(k_s, 0, 1, arm.stream, windows=windows, primary=side)
+        build_s = time.perf_counter() - t_build
+        cell = {"arm": "sangria", "gates": N + 1, "sub_circuits": N, "k": k_s, "advice": 7 + 5 * N, "fixed": 15 + 11 * N, "cross_terms": wl.sides[0].d,
+                "msm_points": [(7 + 5 * N) << k_s, f"{wl.sides[0].d}x{1 << k_s}"], "setup_s": round(build_s, 1)}
+        if i == 0 and not args.no_verify:
+            from oracle import step_ref
+
+            snap = wl.snapshot_inputs()
+            wl.step(upload=True)
+            res = wl.snapshot_results()
+            t0 = time.perf_counter()
+            exp = step_ref.fold_step(snap, step_ref.bases_for(snap), threads=cpu_threads())
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            rep = step_ref.compare(res, exp)
+            if not rep["ok"]:
+                raise SystemExit(f"bench.py: gate_scaling sangria N={N} disagrees with the oracle: {rep['bad']}")
+            cell["verified"] = True
+            verified = True
+            cpu_base = {"value": round(cpu_ms, 2), "unit": "ms", "cores": cpu_threads(), "kind": "port",
+                        "sample": f"1 full fold_step hot path at N={N} sub-circuits on the same inputs as the verified GPU step (CPU restatement, OpenMP)"}
+        dev = arm.timed(wl, False, args.steps, args.warmup)
+        e2e = arm.timed(wl, True, args.steps, args.warmup)
+        wl.overlap = False
+        seq = arm.timed(wl, False, max(2, args.steps // 2), 1)
+        cell.update(ms=round(dev["ms"], 3), e2e_ms=round(e2e["ms"], 3), h2d_bytes_per_step=int(e2e["h2d"]), launches=int(dev["launches"]),
+                    sequential_phases_ms=round(seq["ms"], 3), breakdown_ms=seq["breakdown"])
+        cells.append(cell)
+        release(wl)
+        del wl
+    for i, N in enumerate(pg_counts):
+        if i == 0 and not args.no_verify:
+            from oracle import step_ref
+
+            kv = min(k_pg, 12)
+            for mode, name in ((0, "compat"), (1, "correct")):
+                wl = WL.GateScalingPgWorkload(kv, N, arm.stream, row_mode=mode)
+                snap = wl.snapshot_inputs()
+                wl.step()
+                res = wl.snapshot_results()
+                exp = step_ref.protogalaxy_prove(snap, wl.side, threads=cpu_threads())
+                rep = step_ref.compare_protogalaxy(res, exp)
+                if not rep["ok"]:
+                    raise SystemExit(f"bench.py: gate_scaling protogalaxy N={N} k={kv} ({name}) disagrees with the oracle: {rep['bad']}")
+                release(wl)
+                del wl
+        # one straight-line kernel per gate and per leaf kind costs ~5 s of NVRTC each: beyond a few gates the interpreter kernel is used
+        jit = N + 1 <= args.pg_jit_max_gates
+        arm.lib.sb_expr_jit_enable(1 if jit else 0)
+        t_build = time.perf_counter()
+        wl = WL.GateScalingPgWorkload(k_pg, N, arm.stream, row_mode=1)
+        build_s = time.perf_counter() - t_build
+        dev = arm.timed(wl, False, max(2, args.steps // 2), 1)
+        cell = {"arm": "protogalaxy", "gates": N + 1, "sub_circuits": N, "k": k_pg, "advice": 7 + 5 * N, "fixed": 15 + 11 * N, "leaves_log2": wl.pg.t,
+                "points_F": wl.pg.nF, "points_G": wl.pg.nG, "ms": round(dev["ms"], 3), "launches": int(dev["launches"]), "breakdown_ms": dev["breakdown"],
+                "setup_s": round(build_s, 1), "row_mode": "correct", "evaluator": "run-time compiled straight-line kernels" if jit else "interpreter kernel"}
+        if i == 0 and not args.no_verify:
+            cell["verified"] = f"bit-exact vs the CPU restatement at k={min(k_pg, 12)}, both row modes (the k={k_pg} run uses the same kernels)"
+        cells.append(cell)
+        release(wl)
+        del wl
+    arm.lib.sb_expr_jit_enable(1)
+    clocks = sampler.stop()
+    head = cells[0]
+    line = {"metric": metric, "value": head["ms"], "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms"],
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (254-bit modular integers)", "data": "synthetic", "config": config,
+            "value_is": f"the first cell ({head['arm']}, {head['sub_circuits']} sub-circuits); every cell is in `cells`",
+            "e2e": {"value": head.get("e2e_ms", head["ms"]), "unit": "ms", "h2d_bytes_per_step": head.get("h2d_bytes_per_step", 0), "d2h_bytes_per_step": 64 * (head.get("cross_terms", 0) + 7)},
+            "gpu_launches": head["launches"], "clocks": clocks, "verified": verified, "cells": cells}
+    if cpu_base:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
+
+
 def run_msm_sweep(args):
     """--workload msm_sweep: BASELINE config 4, Pedersen MSM 2^16..2^24 bn256 G1, U (uniform) and W (witness-like: 60 % zero,
     20 % < 2^8, 10 % < 2^64, 10 % uniform) scalar distributions, every cell checked against the CPU oracle.
@@ -739,7 +866,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sangria_poseidon", choices=["sangria_poseidon", "cyclefold_poseidon", "msm_sweep"])
+    ap.add_argument("--workload", default="sangria_poseidon", choices=["sangria_poseidon", "cyclefold_poseidon", "msm_sweep", "gate_scaling"])
+    ap.add_argument("--gates", default="5,10,20", help="gate_scaling: sub-circuit counts of the sangria arm (benches/ivc_gate_scaling.rs:221-223)")
+    ap.add_argument("--pg-gates", default="6,12,24", help="gate_scaling: sub-circuit counts of the Protogalaxy arm (:229-232 also lists 48: ~60 GB of columns at k=20)")
+    ap.add_argument("--pg-k", type=int, default=20, help="gate_scaling: table size of the Protogalaxy arm")
+    ap.add_argument("--pg-jit-max-gates", type=int, default=7, help="gate_scaling: compile the per-gate leaf kernels up to this many gates")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the bit-for-bit comparison of one timed step with the oracle")
     ap.add_argument("--no-k20", action="store_true", help="skip the extra.k20 block (the same measurement at k = 20)")
@@ -755,6 +886,8 @@ def main():
         return run_cyclefold(args)
     if args.workload == "msm_sweep":
         return run_msm_sweep(args)
+    if args.workload == "gate_scaling":
+        return run_gate_scaling(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -137,17 +137,17 @@ class _PgCtx:
         return p
 
 
-def cyclefold_step(inp: Dict, threads: int = 0) -> Dict:
-    """The prover hot path of cyclefold::IVC::next (src/ivc/cyclefold/incrementally_verifiable_computation/mod.rs:210-335) on the
-    inputs of sirius_b200.workload.CyclefoldStepWorkload.snapshot_inputs(): ProtoGalaxy::prove (F, G, K, fold_witness,
-    src/nifs/protogalaxy/mod.rs:400-481), fold_support_circuit (:404-473), commit of the next primary trace."""
+def protogalaxy_prove(inp: Dict, side: Dict, threads: int = 0) -> Dict:
+    """ProtoGalaxy::prove (src/nifs/protogalaxy/mod.rs:400-481) for one accumulator + one incoming trace of the circuit `side`
+    describes (gate list by MainGate widths): poly_F (poly/mod.rs:68-203), poly_G (:308-425), poly_K (:205-269) and the folded
+    witness (mod.rs:176-210).  inp: k, row_mode, fixed, nadv, W_acc, W_in, betas, delta, alpha, gamma."""
     from oracle import pg_fast as PF
     from oracle import pg_ref as PG
     from sirius_b200 import workload as WL   # side descriptions only (shapes), no device code
 
     k, nadv = inp["k"], inp["nadv"]
     mode = "correct" if inp["row_mode"] == 1 else "compat"
-    gates, nfix, _ = WL.compressed_gates(WL.PRIMARY, E)
+    gates, nfix, _ = WL.compressed_gates(side, E)
     S = PF.Structure(k, [], inp["fixed"], nadv, gates)
     ctx = E.Ctx(num_fixed=nfix, num_advice=nadv)
     max_degree = max(PG.gate_degree(g, ctx) for g in gates)
@@ -160,6 +160,31 @@ def cyclefold_step(inp: Dict, threads: int = 0) -> Dict:
     poly_K = PG.compute_K_from_G(pctx, poly_G, PG.poly_eval(poly_F, alpha))
     Lg = R.eval_lagrange_polys(pctx.lagrange_domain(), gamma)
     W = PF.fold_witness(inp["W_acc"], [inp["W_in"]], Lg)
+    return dict(poly_F=poly_F, poly_G=poly_G, poly_K=poly_K, W=W)
+
+
+def compare_protogalaxy(g: Dict, c: Dict) -> Dict:
+    checked, bad = [], []
+    for key in ("poly_F", "poly_G", "poly_K"):
+        checked.append(key)
+        if list(g[key]) != list(c[key]):
+            bad.append(key)
+    checked.append("W")
+    a, b = np.asarray(g["W"], dtype=np.uint64).reshape(-1), np.asarray(c["W"], dtype=np.uint64).reshape(-1)
+    if a.shape != b.shape or not np.array_equal(a, b):
+        bad.append("W")
+    return {"ok": not bad, "checked": checked, "bad": bad}
+
+
+def cyclefold_step(inp: Dict, threads: int = 0) -> Dict:
+    """The prover hot path of cyclefold::IVC::next (src/ivc/cyclefold/incrementally_verifiable_computation/mod.rs:210-335) on the
+    inputs of sirius_b200.workload.CyclefoldStepWorkload.snapshot_inputs(): ProtoGalaxy::prove (F, G, K, fold_witness,
+    src/nifs/protogalaxy/mod.rs:400-481), fold_support_circuit (:404-473), commit of the next primary trace."""
+    from sirius_b200 import workload as WL   # side descriptions only (shapes), no device code
+
+    pg = protogalaxy_prove(inp, WL.PRIMARY, threads)
+    poly_F, poly_G, poly_K, W = pg["poly_F"], pg["poly_G"], pg["poly_K"], pg["W"]
+    k, nadv = inp["k"], inp["nadv"]
     sup = inp["support"]
     sup_bases = oracle.running_bases(sup["side"]["curve"], sup["nadv"] << sup["k"])
     sres = prove(sup, sup_bases, threads)

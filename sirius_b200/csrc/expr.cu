@@ -31,7 +31,7 @@
 namespace sb {
 
 constexpr int EXPR_THREADS = 128;
-constexpr int EXPR_MAX_DEGREE = 15;
+constexpr int EXPR_MAX_DEGREE = 31;   // d + 1 <= 32 evaluation points per row (a compressed expression of g gates of degree 5 has d = 5 + g - 1)
 
 enum : uint32_t { VS_CONSTANT = 0, VS_INTERMEDIATE = 1, VS_FIXED = 2, VS_POLY = 3, VS_CHALLENGE = 4 };
 enum : uint32_t { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_SQUARE = 3, OP_DOUBLE = 4, OP_NEGATE = 5, OP_HORNER = 6, OP_STORE = 7 };
@@ -583,10 +583,18 @@ static int g_jit_on = []() {
     return (!e || atoi(e) != 0) ? 1 : 0;
 }();
 static bool jit_enabled() { return g_jit_on != 0; }
+// Straight-line code grows with the calculation list (every product is inlined: ~180 instructions): beyond a few hundred
+// calculations the compile takes minutes, the kernel spills and no longer fits the instruction cache (measured with NVRTC
+// here: 136 calculations 5 s / 128 registers, 349: 17 s / 168 registers, 619: 48 s / 255 registers + spills), so larger
+// programs (the gate-scaling circuits) stay on the interpreter kernel.
+static size_t g_jit_max_ops = []() {
+    const char* e = getenv("SB_EXPR_JIT_MAX_OPS");
+    return e ? (size_t)atol(e) : (size_t)400;
+}();
 
 // the compiled kernel for (prog, degree, layout), built on first use; nullptr -> use the interpreter
 static sb_jit_entry* jit_lookup(sb_prog* prog, uint32_t degree, const sb_columns* cols, uint32_t nfv, uint32_t nch, uint32_t num_blend = 0) {
-    if (!jit_enabled()) return nullptr;
+    if (!jit_enabled() || prog->h_ops.size() > g_jit_max_ops) return nullptr;
     for (sb_jit_entry* e : prog->jit)
         if (e->degree == degree && e->num_blend == num_blend && e->num_selectors == cols->num_selectors && e->num_fixed == cols->num_fixed && e->nfv == nfv &&
             e->nch == nch)

@@ -36,6 +36,13 @@ SUPPORT = dict(name="support", curve=1, field=1, kind="tiny", T_list=[])
 SEED = 0x5349524955530000
 
 
+def gate_scaling_side(gates_count: int):
+    """Primary circuit of benches/ivc_gate_scaling.rs:131-140 (`MultiStepCircuit` of GATES_COUNT Poseidon step circuits): the
+    step-folding circuit's MainGate<5> plus one MainGate<3> per sub-circuit: A = 7 + 5N advice, F = 15 + 11N
+    fixed columns, N + 1 gates of degree 5 -- compressed with powers of one challenge, so the folding degree is 5 + N."""
+    return dict(name="primary", curve=0, field=0, T_list=[5] + [3] * int(gates_count))
+
+
 def shapes(side):
     if side.get("kind") == "tiny":
         return 4, 3
@@ -245,17 +252,18 @@ class SangriaStepWorkload:
     """Both sides of the cycle, device-resident, restricted to this rank's rows."""
 
     def __init__(self, k: int, rank: int = 0, world: int = 1, stream=None, windows: Optional[List[int]] = None, seed: int = SEED, combiner="auto",
-                 overlap: Optional[bool] = None):
+                 overlap: Optional[bool] = None, primary=None, secondary=None):
         import torch
 
         self.torch = torch
         self.k, self.rank, self.world, self.seed = k, rank, world, seed
+        self.side_desc = (primary or PRIMARY, secondary or SECONDARY)
         self.stream = stream if stream is not None else torch.cuda.Stream()
         self.windows = windows or default_windows(k)
         self.lib = _lib.load()
         self.sides: List[device.DeviceSangriaSide] = []
         self.extras: List[Dict] = []
-        for side in (PRIMARY, SECONDARY):
+        for side in self.side_desc:
             sess, ex = self._build_side(side)
             self.sides.append(sess)
             self.extras.append(ex)
@@ -574,3 +582,55 @@ class CyclefoldStepWorkload:
         self.pg.ck.close()
         self.sup.S.close()
         self.sup.ck.close()
+
+
+class GateScalingPgWorkload:
+    """BASELINE config 5, Cyclefold arm of benches/ivc_gate_scaling.rs (:183-199: `cyclefold::IVC::next` over a primary circuit
+    of N parallel Poseidon sub-circuits): the Protogalaxy side of one `next()` -- compute_F over 2^t leaves
+    (t = k + ceil(log2(N + 1))), compute_G over the Lagrange blends, K, fold_witness -- on the synthetic shapes
+    A = 7 + 5N, F = 15 + 11N, N + 1 gates.  No commitment is timed here: at k = 20 the trace has (7 + 5N) * 2^20 >= 38.8 M
+    cells, more than the bench's 2^25-generator key (the reference itself would stop with TooLongInput), so the
+    key of this workload holds one column only and is never used."""
+
+    def __init__(self, k: int, gates_count: int, stream=None, seed: int = SEED, row_mode: int = 1):
+        import random
+
+        import torch
+
+        self.torch = torch
+        self.k, self.gates_count, self.seed = k, gates_count, seed
+        self.stream = stream if stream is not None else torch.cuda.Stream()
+        st = self.stream
+        self.side = gate_scaling_side(gates_count)
+        S, ck, cg, info = build_structure_key(self.side, k, 0, 1, st, [10], seed, key_cols=1)
+        self.pg = device.DeviceProtogalaxySide(S, ck, st, row_mode)
+        self.info = info
+        A, n = info["nadv"], 1 << k
+        with torch.cuda.stream(st):
+            self.pg.W_acc.copy_(device.random_field_device(A * n, seed + 21))
+            self.pg.W_in.copy_(device.random_field_device(A * n, seed + 22))
+        st.synchronize()
+        rng = random.Random(seed)
+        M = S.modulus
+        self.betas = [rng.randrange(M) for _ in range(self.pg.t)]
+        self.delta, self.alpha, self.gamma = rng.randrange(M), rng.randrange(M), rng.randrange(M)
+        self.last = None
+
+    def step(self, upload: bool = False) -> int:
+        self.last = self.pg.prove(self.betas, self.delta, self.alpha, self.gamma)
+        return 0
+
+    def snapshot_inputs(self) -> Dict:
+        self.stream.synchronize()
+        cpu = lambda t: t.cpu().numpy().view(np.uint64).copy()  # noqa: E731
+        return dict(k=self.k, row_mode=self.pg.row_mode, side=self.side, fixed=self.info["fixed"], nadv=self.info["nadv"], W_acc=cpu(self.pg.W_acc),
+                    W_in=cpu(self.pg.W_in), betas=list(self.betas), delta=self.delta, alpha=self.alpha, gamma=self.gamma)
+
+    def snapshot_results(self) -> Dict:
+        self.stream.synchronize()
+        poly_F, poly_G, poly_K = self.last
+        return dict(poly_F=poly_F, poly_G=poly_G, poly_K=poly_K, W=self.pg.W_acc.cpu().numpy().view(np.uint64).copy())
+
+    def close(self):
+        self.pg.S.close()
+        self.pg.ck.close()

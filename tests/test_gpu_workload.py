@@ -330,3 +330,43 @@ def test_cross_terms_row_blocks_equal_full_call(jit):
     finally:
         lib.sb_expr_jit_enable(1)
         lib.sb_stream_release(ctypes.c_void_p(st.cuda_stream))
+
+
+def test_gate_scaling_sangria_step(oracle):
+    """BASELINE config 5, Sangria arm at a small size: N = 3 sub-circuits (4 gates, folding degree 8 -> 8 cross terms) and
+    N = 11 (degree 16: above the straight-line kernels' size limit, interpreter kernel) against the CPU restatement."""
+    import torch
+
+    from oracle import step_ref
+    from sirius_b200 import workload as WL
+
+    for N, k in ((3, 9), (11, 7)):
+        wl = WL.SangriaStepWorkload(k, 0, 1, torch.cuda.Stream(), windows=[10, 8], primary=WL.gate_scaling_side(N))
+        try:
+            assert wl.sides[0].d == 5 + N and wl.sides[0].A == 7 + 5 * N
+            for i in range(2):
+                snap = wl.snapshot_inputs()
+                wl.step(upload=(i == 0))
+                rep = step_ref.compare(wl.snapshot_results(), step_ref.fold_step(snap, step_ref.bases_for(snap)))
+                assert rep["ok"], (N, rep["bad"])
+        finally:
+            wl.close()
+
+
+@pytest.mark.parametrize("row_mode", [0, 1])
+def test_gate_scaling_protogalaxy_prove(oracle, row_mode):
+    """BASELINE config 5, Cyclefold arm: ProtoGalaxy::prove over N = 3 sub-circuits (4 gates -> 2^(k+2) leaves) == oracle."""
+    import torch
+
+    from oracle import step_ref
+    from sirius_b200 import workload as WL
+
+    wl = WL.GateScalingPgWorkload(8, 3, torch.cuda.Stream(), row_mode=row_mode)
+    try:
+        assert wl.pg.t == 8 + 2
+        snap = wl.snapshot_inputs()
+        wl.step()
+        rep = step_ref.compare_protogalaxy(wl.snapshot_results(), step_ref.protogalaxy_prove(snap, wl.side))
+        assert rep["ok"], rep["bad"]
+    finally:
+        wl.close()

@@ -119,3 +119,18 @@ def test_setup_smallest_key_size_rule():
         for K in (0, 5, 17, 20):
             w = smallest_power(n, K)
             assert (1 << w) >= n << K and (w == 0 or (1 << (w - 1)) < n << K)
+
+
+def test_gate_scaling_shapes_and_folding_degree():
+    """benches/ivc_gate_scaling.rs widens the primary circuit by N Poseidon sub-circuits: A = 7 + 5N, F = 15 + 11N, N + 1 gates of
+    degree 5 compressed with powers of one challenge (src/plonk/util.rs:35-55) -> folding degree 5 + N."""
+    from sirius_b200 import polynomial as P
+    from sirius_b200 import workload as WL
+
+    for N in (1, 5, 10, 20):
+        side = WL.gate_scaling_side(N)
+        gates, nfix, nadv = WL.compressed_gates(side)
+        assert (len(gates), nfix, nadv) == (N + 1, 15 + 11 * N, 7 + 5 * N)
+        cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_selectors=0, num_fixed=nfix, num_advice=nadv))
+        assert cg.degree == 5 + N and cg.ctx.num_challenges == 2
+    assert WL.gate_scaling_side(1)["T_list"] == WL.PRIMARY["T_list"]
