@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <functional>
 #include <stdexcept>
@@ -136,7 +137,9 @@ class CommitmentKey {
         }
         if (!setup) throw std::logic_error("CommitmentKey::setup needs halo2curves' hash_to_curve (un-vendored); supply `setup`");
         CommitmentKey key(curve, setup(k, label));
-        if (std::system(("mkdir -p '" + dir + "'").c_str()) != 0) throw IoError(IoError::Other, "cannot create " + dir);
+        std::error_code ec;
+        std::filesystem::create_directories(dir, ec);   // no shell: the folder / label may contain any character
+        if (ec) throw IoError(IoError::Other, "cannot create " + dir + ": " + ec.message());
         key.save_to_file(path);
         return key;
     }
