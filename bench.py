@@ -208,6 +208,8 @@ class GpuArm:
     # -------------------------------------------------------------------------- verification against the oracle
     def verify(self, wl):
         """One step of the timed objects vs the CPU restatement on identical inputs (rank 0 runs the oracle)."""
+        wl.step(upload=False)    # two unchecked steps first: the library captures each commitment pipeline into a CUDA graph on its
+        wl.step(upload=True)     # second call and replays it afterwards -- the step that is checked runs on the replayed graphs
         snap = wl.snapshot_inputs()
         wl.step(upload=True)     # the e2e form: the uploaded pinned copy equals W_in, so both timed variants are covered
         res = wl.snapshot_results()
@@ -218,12 +220,15 @@ class GpuArm:
             bases = step_ref.bases_for(snap)
             cpu_res, cpu_ms = cpu_fold_step(snap, bases)
             report = step_ref.compare(res, cpu_res)
-            report["what"] = "13 commitments + folded W and E of both sides, bit for bit, one step of the timed objects vs oracle/step_ref.py on identical inputs"
+            report["what"] = ("13 commitments + folded W and E of both sides, bit for bit, the third step of the timed objects (captured commitment pipelines "
+                              "replaying, as in the timed region) vs oracle/step_ref.py on identical inputs")
         self.barrier()
         return report, cpu_ms
 
     # -------------------------------------------------------------------------- timing
-    def timed(self, wl, upload, steps, warmup):
+    def timed(self, wl, upload, steps, warmup, profile=True):
+        """profile = False: no per-kernel-group events in the timed region (two cudaEventRecord per group and commit: ~60 driver
+        calls per step, which sit on the critical path once the phases are short -- the multi-GPU shards)."""
         import ctypes
 
         torch, lib = self.torch, self.lib
@@ -232,8 +237,9 @@ class GpuArm:
         self.barrier()
         NT = len(TAGS)
         ms_arr, un_arr, ln_arr = (ctypes.c_double * NT)(), (ctypes.c_uint64 * NT)(), (ctypes.c_uint64 * NT)()
-        lib.sb_profile_enable(1)
-        lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
+        if profile:
+            lib.sb_profile_enable(1)
+            lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
         launches0 = lib.sb_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(self.stream)
@@ -243,8 +249,9 @@ class GpuArm:
         e1.record(self.stream)
         self.barrier()
         ms = e0.elapsed_time(e1)
-        self._lib.check(lib.sb_profile_collect(ms_arr, un_arr, ln_arr))
-        lib.sb_profile_enable(0)
+        if profile:
+            self._lib.check(lib.sb_profile_collect(ms_arr, un_arr, ln_arr))
+            lib.sb_profile_enable(0)
         breakdown = {t: round(ms_arr[i] / steps, 4) for i, t in enumerate(TAGS) if ln_arr[i]}
         launches = lib.sb_launch_count() - launches0
         ms = self.max_over_ranks(ms)
@@ -327,8 +334,9 @@ class GpuArm:
                 out["verify"] = report
                 if not report["ok"]:
                     raise SystemExit(f"bench.py: the timed path disagrees with the oracle: {report['bad']}")
-        dev = self.timed(wl, False, steps, warmup)
-        e2e = self.timed(wl, True, steps, warmup)
+        two_streams = bool(getattr(wl, "overlap", False))
+        dev = self.timed(wl, False, steps, warmup, profile=not two_streams)
+        e2e = self.timed(wl, True, steps, warmup, profile=not two_streams)
         # per-kernel durations (roofline, breakdown) come from a leg with the two streams serialised: in the timed region
         # above the W commitment shares the SMs with the cross terms / T commitments of the other stream, so a kernel's
         # event-to-event time there is not the kernel's own
@@ -365,7 +373,6 @@ def roofline_block(m, world, peaks):
     k, steps = m["k"], m["seq"]["steps"]
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     acc_ms, acc_madds, acc_n = m["seq"]["acc"]
-    ov_ms, _, ov_n = m["dev"]["acc"]
     points_per_step = (12 + 6 + 7 + 5) * (1 << k)
     acc_pts = points_per_step * steps / world   # points this rank pushed through k_accumulate in the timed region
     achieved = (96.0 * acc_pts / 1e9) / (acc_ms / 1e3) if acc_ms else 0.0
@@ -387,10 +394,9 @@ def roofline_block(m, world, peaks):
         "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
         "launches": int(acc_n), "avg_launch_ms": round(acc_ms / acc_n, 4) if acc_n else None,
-        "avg_launch_ms_two_streams": round(ov_ms / ov_n, 4) if ov_n else None,
-        "timing": "CUDA events around the kernel on its own stream, inside bench.py; avg_launch_ms (and achieved) from the leg that runs the step's phases "
-                  "sequentially (one stream busy at a time), avg_launch_ms_two_streams from the timed region itself, where the kernel shares the SMs with the "
-                  "other stream's cross terms / commitments",
+        "timing": "CUDA events around the kernel on its own stream, inside bench.py, from the leg that runs the step's phases sequentially (sequential_phases_ms): "
+                  "in the two-stream timed region the kernel shares the SMs with the other stream's cross terms / commitments and an event pair around it would "
+                  "not measure the kernel alone (nor are the ~60 extra event records per step wanted on the critical path of the short multi-GPU phases)",
         "note": "algorithmic 96 B/point; the kernel is integer-pipe bound (SURVEY F7): see int_pipe and DESIGN.md 4.2",
         "int_pipe": {
             "achieved_gmadd_per_s": round(gmadd, 3) if gmadd else None,

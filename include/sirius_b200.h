@@ -109,7 +109,11 @@ int sb_ck_window_bits(sb_ck_t ck);
  * key 1: outputs per thread of one round (8 or 16);
  * key 2: sort of the digit entries (0 = automatic, 1 = counting sort with one atomic per entry, 2 = two-level
  *        partition sort through shared-memory histograms whenever the bucket count allows);
- * key 3: commitment tail (1 = 4-warp cooperative group law, the default; 0 = the single-lane / quad-lane kernels). */
+ * key 3: commitment tail (1 = 4-warp cooperative group law, the default; 0 = the single-lane / quad-lane kernels;
+ *        2 = cooperative fix-up as well);
+ * key 4: CUDA-graph cache of the _device commitment pipelines (1 = on, the default: a commitment called again with the same
+ *        key, device buffers and stream is captured on its second call and replayed as one graph launch afterwards;
+ *        0 = every call launches its kernels one by one). */
 int sb_msm_tune(int key, int value);
 
 /* CommitmentKey::commit (src/commitment.rs:81-90): out = sum_{i<n} scalars[i] * ck[i], affine.
@@ -131,6 +135,8 @@ int sb_msm_combine_device(int curve, const void* d_partials_xyzz, int count, voi
 int sb_msm_combine_batch_device(int curve, const void* d_partials_xyzz, int count, size_t batch, size_t stride, void* d_out_xy, void* stream);
 
 /* ---- multi-GPU, one process per GPU: exchange over NVLink / NVSwitch peer memory (csrc/comm.cu) -----------------------
+ * A communicator serves ONE stream at a time (its call sequence counter lives in device memory and advances in stream order);
+ * concurrent commitment groups on two streams use two communicators.
  * sb_comm_create allocates this rank's mailbox and returns its 64-byte CUDA IPC handle; the caller all-gathers the handles
  * (any transport: torch.distributed, MPI, a file) and passes the world * 64 bytes, rank-major, to sb_comm_connect on every
  * rank, followed by a barrier of its own.  max_batch = the largest commitment group (<= 4096). */

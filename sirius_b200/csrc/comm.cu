@@ -65,11 +65,15 @@ SB_D uint4 ld_volatile_v4(const uint4* p) {
 // in: pairs ? xy[b][2] (the two halves of the weighted bucket sum) : partial[b].
 template <class F>
 __global__ void __launch_bounds__(COOP_THREADS)
-k_exchange_combine(CommView c, uint32_t seq, const XYZZ<F>* __restrict__ in, int pairs, Affine<F>* __restrict__ out_xy,
+k_exchange_combine(CommView c, const unsigned int* __restrict__ seq_counter, const XYZZ<F>* __restrict__ in, int pairs, Affine<F>* __restrict__ out_xy,
                    unsigned int* __restrict__ status) {
     __shared__ CoopBuf sh;
     __shared__ XYZZ<F> mine;
     __shared__ int failed;
+    // The call sequence number lives in DEVICE memory (k_seq_bump raises it behind this kernel, in stream order), not in a
+    // kernel argument: a captured pipeline (CUDA graph, msm.cu) replays with identical arguments.  Every rank issues the
+    // same exchanges in the same order on a communicator, so the counters agree.
+    const uint32_t seq = *reinterpret_cast<const volatile unsigned int*>(seq_counter) + 1u;
     const uint32_t b = blockIdx.x, parity = seq & 1u;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) failed = 0;
@@ -128,6 +132,8 @@ k_exchange_combine(CommView c, uint32_t seq, const XYZZ<F>* __restrict__ in, int
     }
 }
 
+__global__ void k_seq_bump(unsigned int* seq_counter) { *seq_counter += 1u; }
+
 }  // namespace sb
 
 struct sb_comm {
@@ -136,14 +142,14 @@ struct sb_comm {
     char* local;
     char* peers[sb::COMM_MAX_WORLD];
     bool opened[sb::COMM_MAX_WORLD];
-    unsigned int* d_status;
-    uint32_t seq;
+    unsigned int* d_status;   // [0] status word, [1] call sequence counter
     bool connected;
 };
 
 using namespace sb;
 
 namespace sb {
+void msm_graphs_drop(const void* ck, cudaStream_t st, const void* comm, bool all);   // msm.cu
 // used by msm.cu's sharded commit: run the exchange on `in` (pairs: xy halves in the MSM workspace)
 int comm_exchange_enqueue(sb_comm* c, int curve, const void* d_in, int pairs, size_t batch, void* d_out_xy, cudaStream_t st) {
     if (!c || !c->connected) {
@@ -160,15 +166,17 @@ int comm_exchange_enqueue(sb_comm* c, int curve, const void* d_in, int pairs, si
     v.rank = c->rank;
     v.world = c->world;
     v.max_batch = (uint32_t)c->max_batch;
-    const uint32_t seq = ++c->seq;
+    unsigned int* seq_counter = c->d_status + 1;
     if (curve == CURVE_BN256)
-        k_exchange_combine<Fq><<<(unsigned)batch, COOP_THREADS, 0, st>>>(v, seq, (const XYZZ<Fq>*)d_in, pairs, (Affine<Fq>*)d_out_xy, c->d_status);
+        k_exchange_combine<Fq><<<(unsigned)batch, COOP_THREADS, 0, st>>>(v, seq_counter, (const XYZZ<Fq>*)d_in, pairs, (Affine<Fq>*)d_out_xy, c->d_status);
     else if (curve == CURVE_GRUMPKIN)
-        k_exchange_combine<Fr><<<(unsigned)batch, COOP_THREADS, 0, st>>>(v, seq, (const XYZZ<Fr>*)d_in, pairs, (Affine<Fr>*)d_out_xy, c->d_status);
+        k_exchange_combine<Fr><<<(unsigned)batch, COOP_THREADS, 0, st>>>(v, seq_counter, (const XYZZ<Fr>*)d_in, pairs, (Affine<Fr>*)d_out_xy, c->d_status);
     else {
         set_error("sb_comm: unknown curve %d", curve);
         return SB_ERR_ARG;
     }
+    SB_KERNEL_CHECK();
+    k_seq_bump<<<1, 1, 0, st>>>(seq_counter);
     SB_KERNEL_CHECK();
     return SB_OK;
 }
@@ -192,8 +200,8 @@ int sb_comm_create(int rank, int world, size_t max_batch, sb_comm_t* out, unsign
     const size_t bytes = mailbox_bytes(world, max_batch);
     cudaError_t e = cudaMalloc((void**)&c->local, bytes);
     if (e == cudaSuccess) e = cudaMemset(c->local, 0, bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_status, 4);
-    if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_status, 8);
+    if (e == cudaSuccess) e = cudaMemset(c->d_status, 0, 8);
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->local);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -236,6 +244,10 @@ int sb_comm_connect(sb_comm_t c, const unsigned char* all_handles) {
 void sb_comm_destroy(sb_comm_t c) {
     if (!c) return;
     cudaDeviceSynchronize();
+    {
+        RtLock lk(runtime().mu);
+        msm_graphs_drop(nullptr, nullptr, c, false);
+    }
     for (int r = 0; r < c->world; r++)
         if (c->opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
     if (c->local) cudaFree(c->local);

@@ -1486,6 +1486,110 @@ static int msm_dispatch(const sb_ck* ck, const MsmPlan& p, char* ws, const void*
     return msm_enqueue<Fr, Fq>(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
 }
 
+// ------------------------------------------------------------------------------------------------
+// CUDA-graph cache of whole commitment pipelines.
+// A prover calls the same commitment again and again: same key, same device buffers, same stream (the device-resident
+// session of sirius_b200/device.py commits W_in and T every fold step).  The pipeline is ~20 launches and memsets whose
+// arguments depend only on those inputs and on the stream's scratch address, so the second call with an identical
+// signature is captured into a graph and every later one is ONE cudaGraphLaunch: the host spends ~10 us instead of
+// ~100 us per pipeline (it sits on the critical path of the short phases of a multi-GPU shard), and the kernels of the
+// sort chain follow each other without launch gaps.  Eager launches stay for first calls, for profiling runs (event
+// records between the kernels) and with SB_MSM_GRAPH=0.  Entries die with their key, stream or communicator.
+// ------------------------------------------------------------------------------------------------
+struct GraphKey {
+    const sb_ck* ck;
+    const void* table;
+    size_t n, stride, batch, ws_bytes;
+    const void* in;
+    void *out_xy, *out_xyzz;
+    cudaStream_t st;
+    ::sb_comm* comm;
+    char* ws;
+    uint64_t epoch;
+    bool operator==(const GraphKey& o) const {
+        return ck == o.ck && table == o.table && n == o.n && stride == o.stride && batch == o.batch && ws_bytes == o.ws_bytes && in == o.in &&
+               out_xy == o.out_xy && out_xyzz == o.out_xyzz && st == o.st && comm == o.comm && ws == o.ws && epoch == o.epoch;
+    }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;   // nullptr: seen once, not captured yet
+    bool refused;           // capture failed once: stay eager
+    uint64_t launches, last_use;
+};
+static std::vector<GraphEntry> g_graphs;   // under runtime().mu
+static uint64_t g_graph_epoch = 1, g_graph_clock = 0;
+static int g_graph_on = []() {
+    const char* e = getenv("SB_MSM_GRAPH");
+    return (!e || atoi(e) != 0) ? 1 : 0;
+}();
+constexpr size_t GRAPH_CACHE_MAX = 64;
+uint64_t launch_count_now();   // runtime.cu
+void count_launches(uint64_t n);
+
+void msm_graphs_drop(const void* ck, cudaStream_t st, const void* comm, bool all) {   // caller holds runtime().mu
+    for (size_t i = 0; i < g_graphs.size();) {
+        const GraphKey& k = g_graphs[i].key;
+        if (all || (ck && k.ck == ck) || (st && k.st == st) || (comm && k.comm == comm)) {
+            if (g_graphs[i].exec) cudaGraphExecDestroy(g_graphs[i].exec);
+            g_graphs[i] = g_graphs.back();
+            g_graphs.pop_back();
+        } else {
+            i++;
+        }
+    }
+}
+
+static int msm_dispatch_cached(const sb_ck* ck, const MsmPlan& p, char* ws, const void* d_scalars, size_t stride, void* d_out_xy, void* d_out_xyzz,
+                               cudaStream_t st, ::sb_comm* comm = nullptr) {
+    if (!g_graph_on || profile_enabled() || p.batch == 0 || p.n == 0) return msm_dispatch(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
+    const GraphKey key{ck, p.table, p.n, stride, (size_t)p.batch, p.total_bytes, d_scalars, d_out_xy, d_out_xyzz, st, comm, ws, g_graph_epoch};
+    GraphEntry* e = nullptr;
+    for (GraphEntry& g : g_graphs)
+        if (g.key == key) { e = &g; break; }
+    if (!e) {   // first sight: run eagerly (grows the scratch, sets kernel attributes), remember the signature
+        if (g_graphs.size() >= GRAPH_CACHE_MAX) {
+            size_t old = 0;
+            for (size_t i = 1; i < g_graphs.size(); i++)
+                if (g_graphs[i].last_use < g_graphs[old].last_use) old = i;
+            if (g_graphs[old].exec) cudaGraphExecDestroy(g_graphs[old].exec);
+            g_graphs[old] = g_graphs.back();
+            g_graphs.pop_back();
+        }
+        g_graphs.push_back(GraphEntry{key, nullptr, false, 0, ++g_graph_clock});
+        return msm_dispatch(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
+    }
+    e->last_use = ++g_graph_clock;
+    if (e->refused) return msm_dispatch(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
+    if (!e->exec) {   // second call: capture
+        const uint64_t l0 = launch_count_now();
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            e->refused = true;
+            return msm_dispatch(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
+        }
+        const int rc = msm_dispatch(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        cudaGraphExec_t exec = nullptr;
+        if (rc != SB_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            e->refused = true;
+            if (rc != SB_OK) return rc;   // an argument error of the pipeline itself
+            return msm_dispatch(ck, p, ws, d_scalars, stride, d_out_xy, d_out_xyzz, st, comm);
+        }
+        cudaGraphDestroy(graph);
+        e->exec = exec;
+        e->launches = launch_count_now() - l0;   // counted once during the capture: this call launches the graph once
+        SB_CUDA_TRY(cudaGraphLaunch(exec, st));
+        return SB_OK;
+    }
+    SB_CUDA_TRY(cudaGraphLaunch(e->exec, st));
+    count_launches(e->launches);
+    return SB_OK;
+}
+
 static int ck_add_table(sb_ck* ck, const void* d_bases, int c, cudaStream_t st) {
     if (c < 2 || c > 24) {
         set_error("sb_ck: window_bits %d out of range [2,24]", c);
@@ -1741,6 +1845,10 @@ int sb_ck_register_device(int curve, const void* d_bases_xy, size_t n, int windo
 
 void sb_ck_release(sb_ck_t ck) {
     if (!ck) return;
+    {
+        RtLock lk(runtime().mu);
+        msm_graphs_drop(ck, nullptr, nullptr, false);
+    }
     for (sb_ck* sh : ck->shards) sb_ck_release(sh);
     if (!ck->tables.empty()) {
         Runtime& rt = runtime();
@@ -1784,10 +1892,15 @@ size_t sb_ck_len(sb_ck_t ck) { return ck ? ck->n : 0; }
  * round (8 or 16), key 2 = sort (0 automatic, 1 per-entry atomic counting sort, 2 two-level partition sort whenever the
  * bucket count allows).  Results are bit-identical for every setting. */
 int sb_msm_tune(int key, int value) {
+    {
+        RtLock lk(runtime().mu);
+        g_graph_epoch++;   // captured pipelines were planned with the old setting
+    }
     if (key == 0 && value >= -1 && value <= MAX_AFFINE_ROUNDS) g_affine_rounds = value;
     else if (key == 1 && (value == 8 || value == 16)) g_pair_b = value;
     else if (key == 2 && value >= 0 && value <= 2) g_sort_mode = value;
-    else if (key == 3 && (value == 0 || value == 1)) g_tail_mode = value;
+    else if (key == 3 && value >= 0 && value <= 2) g_tail_mode = value;
+    else if (key == 4 && (value == 0 || value == 1)) g_graph_on = value;
     else {
         set_error("sb_msm_tune: bad key/value %d/%d", key, value);
         return SB_ERR_ARG;
@@ -1823,7 +1936,7 @@ int sb_msm_batch_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, size_t
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     Scratch& ws = ws_slot(st, WS_MSM);
     SB_TRY(ws.reserve(p.total_bytes));
-    return msm_dispatch(ck, p, (char*)ws.ptr, d_scalars_mont, stride, d_out_xy, d_out_xyzz, st);
+    return msm_dispatch_cached(ck, p, (char*)ws.ptr, d_scalars_mont, stride, d_out_xy, d_out_xyzz, st);
 }
 
 /* Row-sharded commitment group: this rank's scalars against this rank's slice of the key; the partial sums are
@@ -1843,7 +1956,7 @@ int sb_msm_batch_sharded_device(sb_ck_t ck, sb_comm_t comm, const void* d_scalar
     cudaStream_t st = stream ? (cudaStream_t)stream : rt.stream;
     Scratch& ws = ws_slot(st, WS_MSM);
     SB_TRY(ws.reserve(p.total_bytes));
-    return msm_dispatch(ck, p, (char*)ws.ptr, d_scalars_mont, stride, d_out_xy, nullptr, st, comm);
+    return msm_dispatch_cached(ck, p, (char*)ws.ptr, d_scalars_mont, stride, d_out_xy, nullptr, st, comm);
 }
 
 int sb_msm_device(sb_ck_t ck, const void* d_scalars_mont, size_t n, void* d_out_xy, void* d_out_xyzz, void* stream) {

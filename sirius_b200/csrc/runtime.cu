@@ -23,6 +23,9 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }   // a replayed graph of n kernels (msm.cu)
+uint64_t launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
+void msm_graphs_drop(const void* ck, cudaStream_t st, const void* comm, bool all);        // msm.cu
 
 struct ProfileRec { cudaEvent_t e0, e1; uint64_t units; int tag; };
 static std::atomic<bool> g_profile{false};
@@ -380,6 +383,7 @@ void sb_shutdown(void) {
     if (rt.stream) {
         cudaStreamSynchronize(rt.stream);
         cudaDeviceSynchronize();
+        msm_graphs_drop(nullptr, nullptr, nullptr, true);
         ws_release_all();
         cudaStreamDestroy(rt.stream);
         rt.stream = nullptr;
@@ -393,6 +397,7 @@ void sb_stream_release(void* stream) {
     Runtime& rt = runtime();
     RtLock lk(rt.mu);
     if (stream) cudaStreamSynchronize((cudaStream_t)stream);
+    msm_graphs_drop(nullptr, (cudaStream_t)stream, nullptr, stream == nullptr);
     ws_release_stream((cudaStream_t)stream);
 }
 

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import time
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -268,7 +269,7 @@ class SangriaStepWorkload:
             self.sides.append(sess)
             self.extras.append(ex)
         self.combiner = make_combiner(rank, world, self.stream) if combiner == "auto" else combiner
-        # Two-stream phases (see step()): the trace commitment runs on a second, high-priority stream beside the cross terms and
+        # Two-stream phases (see step()): the trace commitment runs on a second stream beside the cross terms and
         # their commitments.  N > 1: that stream needs a communicator of its own (mailboxes and sequence numbers are per
         # communicator); the NCCL library path (SB_BENCH_EXCHANGE=nccl) keeps the sequential phases.
         if overlap is None:
@@ -276,8 +277,14 @@ class SangriaStepWorkload:
         self.overlap = overlap and (self.combiner is None or isinstance(self.combiner, PeerCombiner))
         self.aux_stream, self.combiner_w, self._ev = None, None, None
         self.upload_blocks = max(1, int(os.environ.get("SB_BENCH_UPLOAD_BLOCKS", "4")))
+        self.host_enqueue_s = 0.0
+        self.ct_first = os.environ.get("SB_BENCH_CT_FIRST", "1") == "1"   # enqueue the cross terms before the W commitment
         if self.overlap:
-            self.aux_stream = torch.cuda.Stream(priority=-1)
+            # A/B knobs.  Measured (tools/shard_profile.py, k = 17): equal priorities + cross terms enqueued first 13.72 ms on one GPU and
+            # 2.69 ms for one rank of eight, against 14.47 / 3.05 ms with a high-priority W stream enqueued first (the W pipeline's
+            # ~17 launches cost the host ~0.1 ms during which the GPU had nothing of this phase to run)
+            prio = os.environ.get("SB_BENCH_AUX_PRIORITY", "normal")   # "normal" (default) | "high"
+            self.aux_stream = torch.cuda.Stream(priority=-1 if prio == "high" else 0)
             self.copy_stream = torch.cuda.Stream()
             self._ev = torch.cuda.Event()
             self._ev_blocks = [torch.cuda.Event() for _ in range(self.upload_blocks)]
@@ -322,6 +329,7 @@ class SangriaStepWorkload:
         instead of alone, and a host round trip disappears."""
         torch = self.torch
         main, aux = self.stream, self.aux_stream
+        t_host = time.perf_counter()
         c1, c2 = sess.challenge_vectors(ex["c1"], ex["u1"], ex["c2"])
         ct_args = (sess.S._hom_prog._h, sess.d, sess.S._cols, sess._cols(sess.W_acc), sess._cols(sess.W_in), sess.A,
                    c1.ctypes.data_as(_lib.u64p), c2.ctypes.data_as(_lib.u64p), c1.shape[0])
@@ -349,13 +357,16 @@ class SangriaStepWorkload:
                 h2d = sess.upload_incoming(ex["host_W"])
             self._ev.record(main)        # after the upload and after everything the previous phase left on the main stream
             aux.wait_event(self._ev)
+        ct_first = self.ct_first and nb == 1
+        if ct_first:
+            _lib.check(self.lib.sb_cross_terms_device(*ct_args, ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(main.cuda_stream)))
         if self.combiner is None:
             sess.ck.commit_device(sess.W_in.data_ptr(), sess.A * sess.n, sess.commit_W.data_ptr(), 0, aux.cuda_stream)
             with torch.cuda.stream(aux):
                 sess.h_commit_W.copy_(sess.commit_W, non_blocking=True)
         else:
             self.combiner_w.commit(sess.ck, sess.W_in.data_ptr(), sess.A * sess.n, 1, sess.h_commit_W, sync=False)
-        if nb == 1:
+        if nb == 1 and not ct_first:
             _lib.check(self.lib.sb_cross_terms_device(*ct_args, ctypes.c_void_p(sess.T.data_ptr()), ctypes.c_void_p(main.cuda_stream)))
         if self.combiner is None:
             sess.ck.commit_batch_device(sess.T.data_ptr(), sess.n, sess.n, sess.d, sess.commit_T.data_ptr(), 0, main.cuda_stream)
@@ -363,6 +374,7 @@ class SangriaStepWorkload:
                 sess.h_commit_T.copy_(sess.commit_T, non_blocking=True)
         else:
             self.combiner.commit(sess.ck, sess.T.data_ptr(), sess.n, sess.d, sess.h_commit_T, sync=False)
+        self.host_enqueue_s += time.perf_counter() - t_host   # host time spent enqueuing (diagnostic: tools/shard_profile.py)
         aux.synchronize()
         main.synchronize()               # W and T commitments are on the host: the random oracle derives r
         sess.fold(ex["r"])

@@ -370,3 +370,52 @@ def test_gate_scaling_protogalaxy_prove(oracle, row_mode):
         assert rep["ok"], rep["bad"]
     finally:
         wl.close()
+
+
+def test_captured_commit_pipelines_replay_on_fresh_data(oracle):
+    """The CUDA-graph cache of msm.cu: the same commitment signature (key, device buffers, stream) is run eagerly, captured on the
+    second call and replayed afterwards.  The scalars are rewritten in place between the calls, single and batched commits
+    alternate on one stream, a profiling run and sb_msm_tune drop back to eager launches: every result must equal the oracle's,
+    and the launch counter must advance by the same amount whether a pipeline is launched or replayed."""
+    import ctypes
+
+    import torch
+
+    import oracle as O
+    import sirius_b200
+    from sirius_b200 import _lib
+
+    lib = _lib.load()
+    n, batch = 5000, 3
+    st = torch.cuda.Stream()
+    for curve in (0, 1):
+        bases = O.running_bases(curve, n)
+        ck = sirius_b200.CommitmentKey(curve, bases, window_bits=9)
+        with torch.cuda.stream(st):
+            d_s = torch.zeros((batch * n, 4), dtype=torch.int64, device="cuda")
+            d_o = torch.zeros((batch, 8), dtype=torch.int64, device="cuda")
+            d_o1 = torch.zeros(8, dtype=torch.int64, device="cuda")
+        per_call = []
+        for it in range(6):
+            if it == 4:
+                lib.sb_profile_enable(1)      # event records between the kernels: eager again
+            if it == 5:
+                lib.sb_profile_enable(0)
+                _lib.check(lib.sb_msm_tune(2, 1))   # another sort path: the captured pipelines are stale
+            vs = [O.random_field(curve, 100 * it + j + curve, n) for j in range(batch)]
+            with torch.cuda.stream(st):
+                d_s.copy_(torch.from_numpy(np.concatenate(vs).view(np.int64)), non_blocking=False)
+            l0 = lib.sb_launch_count()
+            ck.commit_batch_device(d_s.data_ptr(), n, n, batch, d_o.data_ptr(), 0, st.cuda_stream)
+            l1 = lib.sb_launch_count()
+            ck.commit_device(d_s.data_ptr() + 32 * n, n - 7, d_o1.data_ptr(), 0, st.cuda_stream)
+            st.synchronize()
+            per_call.append(l1 - l0)
+            got = d_o.cpu().numpy().view(np.uint64)
+            for j in range(batch):
+                assert np.array_equal(got[j], O.msm(curve, vs[j], bases)), (curve, it, j)
+            assert np.array_equal(d_o1.cpu().numpy().view(np.uint64), O.msm(curve, vs[1][: n - 7], bases)), (curve, it)
+        assert len(set(per_call[:5])) == 1 and per_call[0] > 5, per_call
+        _lib.check(lib.sb_msm_tune(2, 0))
+        ck.close()
+    lib.sb_stream_release(ctypes.c_void_p(st.cuda_stream))

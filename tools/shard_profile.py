@@ -24,6 +24,7 @@ ap.add_argument("--k", type=int, default=17)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--exchange", default="peer", choices=["peer", "local"])
+ap.add_argument("--no-profile", action="store_true", help="no per-kernel-group events in the timed region (what bench.py's value is timed with)")
 args = ap.parse_args()
 
 lib = sirius_b200.load()
@@ -55,8 +56,10 @@ torch.cuda.synchronize()
 TAGS = ["decompose", "sort", "accumulate", "fixup", "reduce", "finalize", "cross_terms", "fold", "ntt", "protogalaxy"]
 NT = len(TAGS)
 ms_arr, un_arr, ln_arr = (ctypes.c_double * NT)(), (ctypes.c_uint64 * NT)(), (ctypes.c_uint64 * NT)()
-lib.sb_profile_enable(1)
-lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
+if not args.no_profile:
+    lib.sb_profile_enable(1)
+    lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
+wl.host_enqueue_s = 0.0
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 l0 = lib.sb_launch_count()
 e0.record(stream)
@@ -64,9 +67,10 @@ for _ in range(args.steps):
     wl.step(False)
 e1.record(stream)
 torch.cuda.synchronize()
-lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
-lib.sb_profile_enable(0)
+if not args.no_profile:
+    lib.sb_profile_collect(ms_arr, un_arr, ln_arr)
+    lib.sb_profile_enable(0)
 ms = e0.elapsed_time(e1) / args.steps
 bd = {t: round(ms_arr[i] / args.steps, 4) for i, t in enumerate(TAGS) if ln_arr[i]}
-print(json.dumps({"world": args.world, "k": args.k, "ms_per_step_rank0": round(ms, 4), "sum_kernel_groups": round(sum(bd.values()), 4), "breakdown": bd,
+print(json.dumps({"world": args.world, "k": args.k, "ms_per_step_rank0": round(ms, 4), "host_enqueue_ms_per_step": round(wl.host_enqueue_s * 1e3 / args.steps, 4), "sum_kernel_groups": round(sum(bd.values()), 4), "breakdown": bd,
                   "launches_per_step": (lib.sb_launch_count() - l0) // args.steps}))
