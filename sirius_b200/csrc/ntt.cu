@@ -26,6 +26,7 @@ namespace sb {
 
 constexpr int NTT_MAX_LOG_R = 10;
 constexpr int NTT_LO_BITS = 10;
+constexpr int NTT_FULL_MAX_LOG = 21;
 
 template <class T>
 SB_D T ld16(const T* p) {
@@ -75,17 +76,33 @@ SB_D void sm_store(uint4* lo, uint4* hi, uint32_t idx, const F& v) {
     hi[idx] = s[1];
 }
 
+// out[idx] = lo[e & (2^LO - 1)] * hi[e >> LO] with e = (idx >> logR) * (idx & (R - 1)): the inter-pass twiddle of column
+// jm = idx >> logR and input r, as ONE table entry (built once per (size, omega), read coalesced by the pass kernel)
+template <class F>
+__global__ void k_full_twiddles(const F* __restrict__ tw_lo, const F* __restrict__ tw_hi, uint32_t logR, uint32_t count, F* __restrict__ out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const uint32_t e = (idx >> logR) * (idx & ((1u << logR) - 1u));
+    F tw = ld16(tw_lo + (e & ((1u << NTT_LO_BITS) - 1)));
+    if (e >> NTT_LO_BITS) tw = mul(tw, ld16(tw_hi + (e >> NTT_LO_BITS)));
+    st16(out + idx, tw);
+}
+
+// One pass.  Values stay in the lazy domain [0, 2p) between the stages (field.cuh: no final subtraction in the products)
+// and are canonicalised when they leave the block.  Inner twiddles are staged PER STAGE, contiguously (stage s reads
+// entries 2^s - 1 + i, i < 2^s): consecutive lanes read consecutive 16-byte words in every stage, where one strided table
+// of R/2 entries gave 8-way conflicts in the middle stages (ncu, round 2: 1.48x the conflict-free wavefronts on loads).
 template <class F>
 __global__ void k_ntt_pass(const F* __restrict__ in, F* __restrict__ out, uint32_t logN, uint32_t logR, uint32_t logNs,
                            uint32_t log_tj, const F* __restrict__ inner_tw, const F* __restrict__ tw_lo,
-                           const F* __restrict__ tw_hi, F scale, int has_scale) {
+                           const F* __restrict__ tw_hi, const F* __restrict__ tw_full, F scale, int has_scale) {
     extern __shared__ uint4 smem_raw[];
     const uint32_t R = 1u << logR, halfR = R >> 1;
     const uint32_t total = R << log_tj;           // data elements in the block
     uint4* d_lo = smem_raw;
     uint4* d_hi = smem_raw + total;
-    uint4* t_lo = smem_raw + 2 * total;           // inner twiddles, R/2 elements
-    uint4* t_hi = t_lo + halfR;
+    uint4* t_lo = smem_raw + 2 * total;           // inner twiddles, stage by stage: R - 1 entries (R slots)
+    uint4* t_hi = t_lo + R;
 
     const uint32_t tj = threadIdx.x >> (logR - 1);  // which transform of this block
     const uint32_t t = threadIdx.x & (halfR - 1);
@@ -94,18 +111,26 @@ __global__ void k_ntt_pass(const F* __restrict__ in, F* __restrict__ out, uint32
     const uint32_t Ns_mask = (1u << logNs) - 1;
     const uint32_t my = tj << logR;                // base index of this transform
 
-    for (uint32_t k = threadIdx.x; k < halfR; k += blockDim.x) sm_store(t_lo, t_hi, k, ld16(inner_tw + k));
+    for (uint32_t k = threadIdx.x; k + 1 < R; k += blockDim.x) {
+        const uint32_t s = 31u - (uint32_t)__clz(k + 1u), i = k + 1u - (1u << s);
+        sm_store(t_lo, t_hi, k, ld16(inner_tw + (i << (logR - 1 - s))));
+    }
 
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const uint32_t r = t + h * halfR;
         F v = ld16(in + (size_t)j + ((size_t)r << col_stride_log));
         if (logNs) {
-            const uint32_t e = (j & Ns_mask) * r;
+            const uint32_t jm = j & Ns_mask, e = jm * r;
             if (e) {
-                F tw = ld16(tw_lo + (e & ((1u << NTT_LO_BITS) - 1)));
-                if (e >> NTT_LO_BITS) tw = mul(tw, ld16(tw_hi + (e >> NTT_LO_BITS)));
-                v = mul(v, tw);
+                F tw;
+                if (tw_full) {
+                    tw = ld16(tw_full + ((size_t)jm << logR) + r);
+                } else {
+                    tw = ld16(tw_lo + (e & ((1u << NTT_LO_BITS) - 1)));
+                    if (e >> NTT_LO_BITS) tw = mul_lazy(tw, ld16(tw_hi + (e >> NTT_LO_BITS)));
+                }
+                v = mul_lazy(v, tw);
             }
         }
         const uint32_t br = __brev(r) >> (32 - logR);
@@ -119,9 +144,9 @@ __global__ void k_ntt_pass(const F* __restrict__ in, F* __restrict__ out, uint32
         const uint32_t p = my + ((t >> s) << (s + 1)) + i;
         F x = sm_load<F>(d_lo, d_hi, p);
         F y = sm_load<F>(d_lo, d_hi, p + half);
-        if (i) y = mul(y, sm_load<F>(t_lo, t_hi, i << (logR - 1 - s)));
-        sm_store(d_lo, d_hi, p, add(x, y));
-        sm_store(d_lo, d_hi, p + half, sub(x, y));
+        if (i) y = mul_lazy(y, sm_load<F>(t_lo, t_hi, half - 1u + i));
+        sm_store(d_lo, d_hi, p, add_lazy(x, y));
+        sm_store(d_lo, d_hi, p + half, sub_lazy(x, y));
         __syncthreads();
     }
 
@@ -130,8 +155,8 @@ __global__ void k_ntt_pass(const F* __restrict__ in, F* __restrict__ out, uint32
     for (int h = 0; h < 2; h++) {
         const uint32_t r = t + h * halfR;
         F v = sm_load<F>(d_lo, d_hi, my + r);
-        if (has_scale) v = mul(v, scale);
-        st16(out + j0 + ((size_t)r << logNs), v);
+        if (has_scale) v = mul_lazy(v, scale);
+        st16(out + j0 + ((size_t)r << logNs), canon(v));
     }
 }
 
@@ -175,6 +200,8 @@ struct NttTables {
     size_t inner_off[3] = {0, 0, 0};
     size_t lo_off[3] = {0, 0, 0};
     size_t hi_off[3] = {0, 0, 0};
+    size_t full_off[3] = {0, 0, 0};   // full inter-pass table of the pass (0 = none: too large, or first pass)
+    bool has_full[3] = {false, false, false};
 };
 
 struct NttKey {
@@ -231,6 +258,12 @@ static int build_tables(int log_n, const uint64_t omega_limbs[4], cudaStream_t s
             int span = logNs + T.logR[p];
             hi_count[p] = span > NTT_LO_BITS ? ((size_t)1 << (span - NTT_LO_BITS)) : 1;
             T.hi_off[p] = take(hi_count[p]);
+            // one entry per (column mod Ns, input): saves the lo x hi product per element (1 of ~7 in the pass) for 32 more
+            // bytes read per element; kept up to 2^21 entries = 64 MB per cached (size, omega) -- the two-pass sizes
+            if (span <= NTT_FULL_MAX_LOG) {
+                T.has_full[p] = true;
+                T.full_off[p] = take((size_t)1 << span);
+            }
         }
         logNs += T.logR[p];
     }
@@ -250,6 +283,12 @@ static int build_tables(int log_n, const uint64_t omega_limbs[4], cudaStream_t s
             F base_hi = host_pow(base, (uint64_t)1 << NTT_LO_BITS);
             k_powers<F><<<((uint32_t)hi_count[p] + 127) / 128, 128, 0, st>>>(base_hi, (uint32_t)hi_count[p], (F*)(T.dev + T.hi_off[p]));
             SB_KERNEL_CHECK();
+            if (T.has_full[p]) {
+                const uint32_t count = 1u << (logNs + T.logR[p]);
+                k_full_twiddles<F><<<(count + 255) / 256, 256, 0, st>>>((const F*)(T.dev + T.lo_off[p]), (const F*)(T.dev + T.hi_off[p]), (uint32_t)T.logR[p], count,
+                                                                      (F*)(T.dev + T.full_off[p]));
+                SB_KERNEL_CHECK();
+            }
         }
         logNs += T.logR[p];
     }
@@ -289,7 +328,11 @@ static int ntt_enqueue(F* d_a, int log_n, const uint64_t omega[4], const uint64_
     F* src = d_a;
     F* dst = (F*)g_ntt_tmp.ptr;
     int logNs = 0;
-    SB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    SB_CUDA_TRY(cudaFuncSetAttribute(k_ntt_pass<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    static const int use_full = []() {
+        const char* e = getenv("SB_NTT_FULL_TWIDDLES");
+        return (!e || atoi(e) != 0) ? 1 : 0;
+    }();
     for (int p = 0; p < T.passes; p++) {
         const int logR = T.logR[p];
         // transforms per block: fill 256 threads when R is small
@@ -298,11 +341,12 @@ static int ntt_enqueue(F* d_a, int log_n, const uint64_t omega[4], const uint64_
         if (log_tj > log_n - logR) log_tj = log_n - logR;
         const uint32_t threads = 1u << (logR - 1 + log_tj);
         const uint32_t blocks = 1u << (log_n - logR - log_tj);
-        const size_t smem = (((size_t)1 << (logR + log_tj)) + ((size_t)1 << (logR - 1))) * sizeof(F);
+        const size_t smem = (((size_t)1 << (logR + log_tj)) + ((size_t)1 << logR)) * sizeof(F);
         const bool last = (p == T.passes - 1);
         k_ntt_pass<F><<<blocks, threads, smem, st>>>(src, dst, (uint32_t)log_n, (uint32_t)logR, (uint32_t)logNs, (uint32_t)log_tj,
                                                     (const F*)(T.dev + T.inner_off[p]), logNs ? (const F*)(T.dev + T.lo_off[p]) : nullptr,
-                                                    logNs ? (const F*)(T.dev + T.hi_off[p]) : nullptr, sc, last ? has_scale : 0);
+                                                    logNs ? (const F*)(T.dev + T.hi_off[p]) : nullptr,
+                                                    (logNs && T.has_full[p] && use_full) ? (const F*)(T.dev + T.full_off[p]) : nullptr, sc, last ? has_scale : 0);
         SB_KERNEL_CHECK();
         std::swap(src, dst);
         logNs += logR;
