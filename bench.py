@@ -74,16 +74,44 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread = index, [], False, None
 
+    def _nvml(self):
+        """In-process NVML handle (the library behind nvidia-smi): a query costs microseconds.  Spawning `nvidia-smi` ten times a
+        second next to phases of a millisecond was visible in the timed region (each start-up re-initialises the driver's
+        management interface); it stays as the fallback when the nvidia-ml-py binding is missing."""
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    pass
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception:
+            return None, None
+
     def _run(self):
+        nv, h = self._nvml()
+        self.source = "nvml (nvidia-ml-py, in process)" if nv else "nvidia-smi"
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if nv:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    flag = lambda bit: "Active" if r & bit else "Not Active"  # noqa: E731
+                    self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                                         flag(nv.nvmlClocksEventReasonHwSlowdown), flag(nv.nvmlClocksEventReasonHwThermalSlowdown),
+                                         flag(nv.nvmlClocksEventReasonSwThermalSlowdown), flag(nv.nvmlClocksEventReasonSwPowerCap)])
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if nv else 0.25)
 
     def start(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -101,7 +129,8 @@ class ClockSampler:
             for nm, v in zip(names, s[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": getattr(self, "source", "nvidia-smi")}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
@@ -869,7 +898,7 @@ def _to_montgomery_device(s, lib, _lib, stream):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sangria_poseidon", choices=["sangria_poseidon", "cyclefold_poseidon", "msm_sweep", "gate_scaling"])

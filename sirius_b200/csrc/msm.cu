@@ -37,7 +37,7 @@ namespace sb {
 
 constexpr int LS_MIN_LOG = 4;   // sorted entries per accumulate chunk (one thread each): 2^4 .. 2^8, chosen per call
 constexpr int LS_MAX_LOG = 8;
-constexpr int FIX_SEQ = 6;      // buckets split in <= FIX_SEQ pieces are summed serially by their own lane in k_fixup[_coop] ..
+constexpr int FIX_SEQ = 6;      // buckets split in <= fix_seq pieces (>= FIX_SEQ, chosen per plan) are summed serially by their own lane ..
 constexpr int FIX_TREE = 1024;  // .. up to FIX_TREE pieces by a cooperative block (k_fixup_tree: lane-strided runs + a 5-step lane tree) ..
                                 // .. and beyond that (all-equal scalars) by the 256-thread k_fixup_heavy
 constexpr int HEAVY_THREADS = 256;
@@ -653,7 +653,7 @@ template <class F>
 __global__ void __launch_bounds__(128)
 k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>* __restrict__ buckets,
         const XYZZ<F>* __restrict__ PH, const XYZZ<F>* __restrict__ PT, uint32_t* __restrict__ heavy_count,
-        uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ tree_list) {
+        uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ tree_list, uint32_t fix_seq) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= KB) return;
     const uint32_t o = offsets[b], o2 = offsets[b + 1];
@@ -664,7 +664,7 @@ k_fixup(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>*
     const uint32_t t0 = o / LS;
     const uint32_t np = (o2 - 1) / LS - t0 + 1;
     if (np == 1) return;  // written by k_accumulate
-    if (np > (uint32_t)FIX_SEQ) {   // heavy_count[0]: buckets for k_fixup_heavy, heavy_count[1]: buckets for k_fixup_tree
+    if (np > fix_seq) {   // heavy_count[0]: buckets for k_fixup_heavy, heavy_count[1]: buckets for k_fixup_tree
         if (np > (uint32_t)FIX_TREE) heavy_list[atomicAdd(heavy_count, 1u)] = b;
         else tree_list[atomicAdd(heavy_count + 1, 1u)] = b;
         return;
@@ -865,7 +865,7 @@ template <class F>
 __global__ void __launch_bounds__(COOP_THREADS)
 k_fixup_coop(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZZ<F>* __restrict__ buckets,
              const XYZZ<F>* __restrict__ PH, const XYZZ<F>* __restrict__ PT, uint32_t* __restrict__ heavy_count,
-             uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ tree_list) {
+             uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ tree_list, uint32_t fix_seq) {
     __shared__ CoopBuf sh;
     const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * 32u + (uint32_t)lane;
@@ -880,7 +880,7 @@ k_fixup_coop(const uint32_t* __restrict__ offsets, uint32_t KB, uint32_t LS, XYZ
             np = (o2 - 1) / LS - t0 + 1;
             head_tail = (o - t0 * LS) != 0;
             if (np == 1) np = 0;   // written by k_accumulate
-            else if (np > (uint32_t)FIX_SEQ) {
+            else if (np > fix_seq) {
                 if (role == 0) {
                     if (np > (uint32_t)FIX_TREE) heavy_list[atomicAdd(heavy_count, 1u)] = b;
                     else tree_list[atomicAdd(heavy_count + 1, 1u)] = b;
@@ -1127,6 +1127,7 @@ struct MsmPlan {
     size_t n, total, nW, chunks;
     uint32_t batch, K, KB, tiles;
     uint32_t chunk_len;  // sorted entries per thread of k_accumulate
+    uint32_t fix_seq;    // buckets split over more chunks than this leave the lane-per-bucket fix-up for the cooperative tree
     uint32_t parts;      // level-1 partitions of the two-level sort (0 = per-entry atomic counting sort)
     int rounds;          // batched-affine reduction rounds before the XYZZ chunk kernel (0 = none), affine.cuh
     int pair_b;          // outputs per thread in k_pair_round (8 or 16)
@@ -1238,6 +1239,15 @@ static int make_plan(const sb_ck* ck, size_t n, size_t batch, bool stage_scalars
             if (len < 16) len = 16;
         }
         p.chunk_len = (uint32_t)len;
+        // The tree kernel is for the FEW long buckets (a cooperative addition costs 2.6x the issue slots of a plain one): the
+        // threshold sits well above the pieces an average bucket has, or a tenth of all buckets ends up there (k = 20, batched
+        // cross-term commits: 240 entries per bucket in chunks of 64 -- fix-up 1.8 -> 2.7 ms per step with a fixed threshold of 6)
+        const size_t typical = per_bucket / len + 1;
+        p.fix_seq = (uint32_t)std::min<size_t>(32, std::max<size_t>(FIX_SEQ, 2 * typical + 2));
+        // With very many buckets the lane-per-bucket kernel is throughput-bound for longer than its longest serial run lasts
+        // (k = 20, 2^19 buckets: 0.44 ms against 27 pieces x 6.8 us), so the long runs are free there and the tree only adds its
+        // own time (measured: +0.47 ms per 12.6 M-point commit, profiles/r2g_k20_launches.csv): keep it for the small commits
+        if (p.KB > 65536u) p.fix_seq = 32;
     }
     p.chunks = (p.m_final + p.chunk_len - 1) / p.chunk_len;
     p.tiles = (p.KB + SCAN_TILE - 1) / SCAN_TILE;
@@ -1405,8 +1415,8 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         // one plain lane per bucket for the short runs (<= FIX_SEQ pieces: throughput-bound, and a cooperative addition
         // costs an SM 2.6x the issue slots of a plain one), the cooperative tree for the long ones.  SB_MSM_TAIL=2 keeps
         // the all-cooperative fix-up of small commits for A/B runs.
-        if (g_tail_mode == 2 && KB <= 32768u) k_fixup_coop<F><<<(KB + 31) / 32, COOP_THREADS, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list, tree_list);
-        else k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list, tree_list);
+        if (g_tail_mode == 2 && KB <= 32768u) k_fixup_coop<F><<<(KB + 31) / 32, COOP_THREADS, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list, tree_list, p.fix_seq);
+        else k_fixup<F><<<(KB + 127) / 128, 128, 0, st>>>(off_final, KB, p.chunk_len, buckets, PH, PT, heavy_count, heavy_list, tree_list, p.fix_seq);
         SB_KERNEL_CHECK();
         k_fixup_tree<F><<<592, COOP_THREADS, 0, st>>>(off_final, p.chunk_len, buckets, PH, PT, heavy_count, tree_list);
         SB_KERNEL_CHECK();
@@ -1422,17 +1432,20 @@ static int msm_enqueue(const sb_ck* ck, const MsmPlan& p, char* ws, const void* 
         {
             ProfScope ps(st, PROF_REDUCE, KB);
             if (g_tail_mode) {
-                // group width: the shortest estimated time.  A cooperative addition takes ~2.7 us and a lone block already
-                // keeps its SM's four integer pipes issuing, so blocks beyond one per SM queue up: time ~ ops x 2.7 us x
-                // max(1, blocks / SMs)  (measured: 768 blocks x 6 ops 84 us, 384 x 12 83 us, 192 x 10 ~50 us)
+                // group width, from a model fitted to the launches of profiles/r2_shard8_launches_tree.csv and r2f_ncu_full_summary.txt:
+                // a dependent cooperative addition of this kernel takes ~4.5 us (it waits for a 128-byte bucket load), an SM sustains
+                // ~0.4 of them per us with 3 resident blocks, so time ~ ops x max(4.5, blocks per SM / 0.4).  Narrower groups pay
+                // when there are thousands of SHORT rows (batched cross-term commits of a multi-GPU shard: 768 rows of 64: 75 -> 55 us);
+                // a narrower group must win by 10 % to be taken (one row per block is the form measured longest)
                 int log_g = 5;
                 double best_t = 0;
-                for (int lg = 5; lg >= 2; lg--) {
+                const double sms = (double)(runtime().sm_count > 0 ? runtime().sm_count : 148);
+                for (int lg = 5; lg >= 3; lg--) {
                     const uint32_t G = 1u << lg, cmax = R > C ? R : C;
                     const double ops = (double)((cmax + G - 1) / G - 1) + lg;
                     const double blocks = (double)((R + C + (32u >> lg) - 1) / (32u >> lg)) * p.batch;
-                    const double t = ops * 2.7 * std::max(1.0, blocks / (double)(runtime().sm_count > 0 ? runtime().sm_count : 148));
-                    if (lg == 5 || t < best_t) { best_t = t; log_g = lg; }
+                    const double t = ops * std::max(4.5, blocks / sms / 0.4);
+                    if (lg == 5 || t < 0.9 * best_t) { best_t = t; log_g = lg; }
                 }
                 k_rowcol_coop<F><<<dim3((R + C + (32u >> log_g) - 1) / (32u >> log_g), p.batch), COOP_THREADS, 0, st>>>(buckets, log_k, lc, log_g, vec);
                 SB_KERNEL_CHECK();
