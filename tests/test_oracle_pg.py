@@ -156,3 +156,37 @@ def test_c_tree_parallel_levels_equal_serial_subtrees(oracle):
     small = oracle.random_field(R.FIELD_FR, 7, 8)
     vals = R.from_mont_limbs(small, M)
     assert PF.tree(small, c[:3]) == sum(w * v for w, v in zip(_pow_weights(8, c[:3]), vals)) % M
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_step_ref_protogalaxy_prove_equals_literal_restatement(oracle, mode):
+    """oracle/step_ref.protogalaxy_prove -- the checker of bench.py's cyclefold_poseidon and gate_scaling workloads and of the GPU
+    parity tests -- on a gate-scaling structure (MainGate<5> + two MainGate<3>: 3 gates, 2^(k+2) leaves) against pg_ref.py's
+    element-by-element compute_F / compute_G / compute_K_from_G / fold_witness, both row modes."""
+    from oracle import step_ref
+    from sirius_b200 import workload as WL   # shapes only
+
+    k = 3
+    side = WL.gate_scaling_side(2)
+    gates, nfix, nadv = WL.compressed_gates(side, E)
+    n = 1 << k
+    fixed = [oracle.random_field(R.FIELD_FR, 400 + i, n) for i in range(nfix)]
+    W_acc, W_in = oracle.random_field(R.FIELD_FR, 1, nadv * n), oracle.random_field(R.FIELD_FR, 2, nadv * n)
+    So = PG.PGStructure(k, [], [R.from_mont_limbs(f, M) for f in fixed], nadv, 0, gates)
+    ctx = PG.PolyContext(So, 1)
+    t = ctx.betas_count()
+    assert t == k + 2
+    rng = R.Xoshiro256ss(11)
+    betas = [rng.field(M) for _ in range(t)]
+    delta, alpha, gamma = rng.field(M), rng.field(M), rng.field(M)
+    got = step_ref.protogalaxy_prove(dict(k=k, row_mode=mode, fixed=fixed, nadv=nadv, W_acc=W_acc, W_in=W_in, betas=betas, delta=delta,
+                                          alpha=alpha, gamma=gamma), side)
+    name = "correct" if mode == 1 else "compat"
+    Wa, Wi = [R.from_mont_limbs(W_acc, M)], [R.from_mont_limbs(W_in, M)]
+    F = PG.compute_F(ctx, betas, delta, Wa, [], name)
+    bs = PG.beta_stroke(betas, alpha, delta)
+    G = PG.compute_G(ctx, bs, Wa, [], [Wi], [[]], name)
+    assert got["poly_F"] == F and got["poly_G"] == G
+    assert got["poly_K"] == PG.compute_K_from_G(ctx, G, PG.poly_eval(F, alpha))
+    Lg = R.eval_lagrange_polys(ctx.lagrange_domain(), gamma)
+    assert R.from_mont_limbs(got["W"], M) == PG.fold_witness(Wa, [Wi], Lg)[0]
