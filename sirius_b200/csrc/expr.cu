@@ -429,6 +429,15 @@ static std::string jit_source(int field, const std::vector<DevOp>& ops, const st
     s += "\nusing namespace sb;\ntypedef ";
     s += field == FIELD_FR ? "Fr" : "Fq";
     s += " F;\n";
+    // Long calculation lists (the gate-scaling circuits: 600-1200 calculations): the product is CALLED, not inlined -- the
+    // code stays a few hundred KB and compiles in seconds instead of minutes
+    static const size_t inline_max_ops = []() {
+        const char* e = getenv("SB_EXPR_JIT_INLINE_MAX_OPS");
+        return e ? (size_t)atol(e) : (size_t)400;
+    }();
+    const bool call_form = ops.size() > inline_max_ops;
+    const std::string mul_name = call_form ? "mul_c(" : "mul_lazy(";
+    if (call_form) s += "__device__ __noinline__ F mul_c(F a, F b) { return mul_lazy(a, b); }\n";
     s += "struct JitArgs { const void* const* fixed; const uint8_t* const* selectors; const void* const* adv1; const void* const* adv2; const void* constants;\n"
          "  const void* challenges; const void* vinv; void* out; uint32_t n, rows_per_block, row0, row_end; };\n"
          "__device__ __forceinline__ F ld(const void* p, uint32_t i) { F r; const uint4* s = reinterpret_cast<const uint4*>(p) + 2 * (size_t)i; uint4* d = reinterpret_cast<uint4*>(&r);\n"
@@ -525,8 +534,8 @@ static std::string jit_source(int field, const std::vector<DevOp>& ops, const st
         switch (op) {
             case OP_ADD: expr = "add_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
             case OP_SUB: expr = "sub_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
-            case OP_MUL: expr = "mul_lazy(" + a + ", " + operand(bk, o.b) + ")"; break;
-            case OP_SQUARE: expr = "mul_lazy(" + a + ", " + a + ")"; break;
+            case OP_MUL: expr = mul_name + a + ", " + operand(bk, o.b) + ")"; break;
+            case OP_SQUARE: expr = mul_name + a + ", " + a + ")"; break;
             case OP_DOUBLE: expr = "dbl_lazy(" + a + ")"; break;
             case OP_NEGATE: expr = "neg_lazy(" + a + ")"; break;
             default: expr = a; break;  // OP_STORE
@@ -585,11 +594,12 @@ static int g_jit_on = []() {
 static bool jit_enabled() { return g_jit_on != 0; }
 // Straight-line code grows with the calculation list (every product is inlined: ~180 instructions): beyond a few hundred
 // calculations the compile takes minutes, the kernel spills and no longer fits the instruction cache (measured with NVRTC
-// here: 136 calculations 5 s / 128 registers, 349: 17 s / 168 registers, 619: 48 s / 255 registers + spills), so larger
-// programs (the gate-scaling circuits) stay on the interpreter kernel.
+// here: 136 calculations 5 s / 128 registers, 349: 17 s / 168 registers, 619: 48 s / 255 registers + spills).  Above
+// SB_EXPR_JIT_INLINE_MAX_OPS (400) calculations the generated code CALLS the product (jit_source: 619 calculations 4 s / 205
+// registers / no stack, 1159: 18 s / 255 registers / 280 bytes of spills); above SB_EXPR_JIT_MAX_OPS the interpreter kernel runs.
 static size_t g_jit_max_ops = []() {
     const char* e = getenv("SB_EXPR_JIT_MAX_OPS");
-    return e ? (size_t)atol(e) : (size_t)400;
+    return e ? (size_t)atol(e) : (size_t)2000;
 }();
 
 // the compiled kernel for (prog, degree, layout), built on first use; nullptr -> use the interpreter

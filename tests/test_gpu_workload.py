@@ -334,7 +334,7 @@ def test_cross_terms_row_blocks_equal_full_call(jit):
 
 def test_gate_scaling_sangria_step(oracle):
     """BASELINE config 5, Sangria arm at a small size: N = 3 sub-circuits (4 gates, folding degree 8 -> 8 cross terms) and
-    N = 11 (degree 16: above the straight-line kernels' size limit, interpreter kernel) against the CPU restatement."""
+    N = 11 (degree 16, ~670 calculations: the compiled kernel that CALLS its products) against the CPU restatement."""
     import torch
 
     from oracle import step_ref

@@ -90,3 +90,24 @@ def test_plain_and_blended_evaluation_kernels_compile(num_blend):
     rc, nbytes, log = _compile(0, ev, num_blend << 8, 0, 15, 7, 0)
     assert rc == 0, log
     assert nbytes > 1000 and "0 bytes spill stores" in log
+
+
+def test_long_programs_compile_in_the_call_form():
+    """Above SB_EXPR_JIT_INLINE_MAX_OPS calculations (the gate-scaling circuits) the generated kernel calls the product instead of
+    inlining it: N = 10 sub-circuits (619 calculations, folding degree 15) must compile in seconds, without a stack frame."""
+    import time
+
+    from sirius_b200 import curves
+    from sirius_b200 import polynomial as P
+    from sirius_b200 import workload as WL
+
+    side = WL.gate_scaling_side(10)
+    gates, nfix, nadv = WL.compressed_gates(side)
+    cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_selectors=0, num_fixed=nfix, num_advice=nadv))
+    ev = P.GraphEvaluator.new(cg.homogeneous, curves.SCALAR_FIELD[0])
+    assert len(ev.calculations) > 400 and cg.degree == 15
+    t0 = time.time()
+    rc, nbytes, log = _compile(0, ev, cg.degree, 0, nfix, nadv, cg.ctx.num_challenges)
+    assert rc == 0, log
+    assert time.time() - t0 < 60
+    assert "0 bytes spill stores" in log and nbytes < 2_000_000, log[-600:]
