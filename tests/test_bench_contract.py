@@ -34,3 +34,18 @@ def test_gpu_arm_fails_loudly_without_a_device():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert not any(l.strip().startswith("{") for l in r.stdout.splitlines())   # no number is reported
+
+
+def test_reference_arm_of_the_other_workloads():
+    """`--workload cyclefold_poseidon | gate_scaling --impl reference`: the CPU restatement of those hot paths, one contract line
+    each (small tables so that the CPU suite stays short)."""
+    for extra, needle in ((["--workload", "cyclefold_poseidon", "--k", "8"], "benches/cyclefold_poseidon k=8"),
+                          (["--workload", "gate_scaling", "--k", "7", "--gates", "2"], "benches/ivc_gate_scaling")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra,
+                           capture_output=True, text=True, timeout=900, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+        assert len(lines) == 1, (extra, r.stdout[-500:])
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["unit"] == "ms" and d["value"] > 0 and needle in d["config"]["workload"], d
+        assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
