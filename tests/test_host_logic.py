@@ -134,3 +134,17 @@ def test_gate_scaling_shapes_and_folding_degree():
         cg = P.CompressedGates.new(gates, P.QueryIndexContext(num_selectors=0, num_fixed=nfix, num_advice=nadv))
         assert cg.degree == 5 + N and cg.ctx.num_challenges == 2
     assert WL.gate_scaling_side(1)["T_list"] == WL.PRIMARY["T_list"]
+
+
+def test_integration_doc_names_only_declared_entry_points():
+    """Every `sb_*` function INTEGRATION.md binds or calls is declared in include/sirius_b200.h (the Rust shim a maintainer copies
+    from the document must link)."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "sirius_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", header))
+    used = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", doc))
+    assert used and not (used - declared), sorted(used - declared)
