@@ -1905,10 +1905,8 @@ size_t sb_ck_len(sb_ck_t ck) { return ck ? ck->n : 0; }
  * round (8 or 16), key 2 = sort (0 automatic, 1 per-entry atomic counting sort, 2 two-level partition sort whenever the
  * bucket count allows).  Results are bit-identical for every setting. */
 int sb_msm_tune(int key, int value) {
-    {
-        RtLock lk(runtime().mu);
-        g_graph_epoch++;   // captured pipelines were planned with the old setting
-    }
+    RtLock lk(runtime().mu);   // the knobs are read by make_plan / msm_enqueue under the same lock
+    g_graph_epoch++;           // captured pipelines were planned with the old setting
     if (key == 0 && value >= -1 && value <= MAX_AFFINE_ROUNDS) g_affine_rounds = value;
     else if (key == 1 && (value == 8 || value == 16)) g_pair_b = value;
     else if (key == 2 && value >= 0 && value <= 2) g_sort_mode = value;
